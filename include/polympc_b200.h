@@ -1,0 +1,179 @@
+/* polympc_b200.h — C ABI of the B200-native batched SQP engine (drop-in boundary for PolyMPC's collocated-NLP hot path).
+ *
+ * The reference (PREDICT-EPFL/polympc) is a header-only C++ template library with no FFI of its own; its plug-in seams
+ * are C++ concepts.  Each entry point below replaces one of those seams for a *batch* of independent instances and cites
+ * the reference interface it stands for (paths relative to the reference root).  Plain pointers and sizes only; all
+ * arrays are caller-owned HOST memory unless the name ends in `_dev`; matrices are column-major (Eigen default);
+ * batched arrays are instance-major (instance b at offset b*len).  Every function returns 0 on success and a negative
+ * pmb_error_t otherwise; per-instance solver outcomes are reported through the info arrays, never through the return code
+ * (the reference reports them through status enums as well: src/solvers/sqp_base.hpp:49-61, src/solvers/qp_base.hpp:55-72).
+ *
+ * The same signatures with the prefix `orc_` are exported by the CPU oracle (oracle/, test infrastructure only).
+ */
+#ifndef POLYMPC_B200_H
+#define POLYMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pmb_error {
+    PMB_OK = 0,
+    PMB_ERR_UNKNOWN_PROBLEM = -1,   /* name not in the registry */
+    PMB_ERR_BAD_ARGUMENT = -2,      /* null pointer, non-positive batch, size not instantiated ... */
+    PMB_ERR_CUDA = -3,              /* a CUDA runtime call failed; see pmb_last_error() */
+    PMB_ERR_NO_DEVICE = -4,         /* no usable CUDA device: the engine has no CPU fallback */
+    PMB_ERR_UNSUPPORTED = -5
+} pmb_error_t;
+
+/* ---- problem sizes: enums of ContinuousOCP (src/control/continuous_ocp.hpp:69-98) -------------------------------- */
+typedef struct pmb_dims {
+    int NX, NU, NP, ND, NG;   /* polympc_traits<OCP> (continuous_ocp.hpp:23-33) */
+    int P, S, NN;             /* POLY_ORDER, NUM_SEGMENTS, NUM_NODES = P*S+1 */
+    int N;                    /* VAR_SIZE  = NX*NN + NU*NN + NP */
+    int M;                    /* NUM_EQ + NUM_INEQ = NX*NN + NG*NN */
+    int DUAL;                 /* DUAL_SIZE = M + N */
+    int NPARAM;               /* number of doubles in the flattened data members of the problem class (Q, R, xs ...) */
+} pmb_dims_t;
+
+/* ---- sqp_settings_t / sqp_info_t (src/solvers/sqp_base.hpp:24-61) ----------------------------------------------- */
+typedef struct pmb_sqp_settings {
+    double tau, eta, rho, eps_prim, eps_dual;
+    int max_iter, line_search_max_iter;
+} pmb_sqp_settings_t;
+
+typedef enum pmb_sqp_status { PMB_SQP_SOLVED = 0, PMB_SQP_MAX_ITER_EXCEEDED = 1, PMB_SQP_INVALID_SETTINGS = 2 } pmb_sqp_status_t;
+
+typedef struct pmb_sqp_info {
+    int iter;             /* number of QPs solved (starts at 1) */
+    int qp_solver_iter;   /* accumulated ADMM iterations */
+    int status;           /* pmb_sqp_status_t */
+} pmb_sqp_info_t;
+
+/* ---- qp_solver_settings_t / qp_solver_info_t / status_t (src/solvers/qp_base.hpp:17-72), ADMM-related fields ----- */
+typedef struct pmb_qp_settings {
+    double eps_rel, eps_abs;
+    int max_iter, warm_start, reuse_pattern, verbose;
+    double rho, sigma, alpha;
+    int check_termination, adaptive_rho;
+    double adaptive_rho_tolerance;
+    int adaptive_rho_interval;
+    int _pad;
+} pmb_qp_settings_t;
+
+typedef enum pmb_qp_status {
+    PMB_QP_SOLVED = 0, PMB_QP_MAX_ITER_EXCEEDED = 1, PMB_QP_UNSOLVED = 2, PMB_QP_UNINITIALIZED = 3,
+    PMB_QP_INFEASIBLE = 4, PMB_QP_INCONSISTENT = 5
+} pmb_qp_status_t;
+
+/* QPBase::constraint_type (qp_base.hpp:132-136) */
+typedef enum pmb_constraint_type { PMB_INEQUALITY_CONSTRAINT = 0, PMB_EQUALITY_CONSTRAINT = 1, PMB_LOOSE_BOUNDS = 2 } pmb_constraint_type_t;
+
+typedef struct pmb_qp_info {
+    int status, iter, rho_updates, _pad;
+    double rho_estimate, res_prim, res_dual;
+} pmb_qp_info_t;
+
+/* ---- library / registry ----------------------------------------------------------------------------------------- */
+const char* pmb_version(void);
+const char* pmb_last_error(void);
+int pmb_device_count(void);
+int pmb_problem_count(void);
+const char* pmb_problem_name(int index);
+int pmb_problem_dims(const char* name, pmb_dims_t* out);
+
+void pmb_qp_default_settings(pmb_qp_settings_t* s);      /* qp_base.hpp:17-53 defaults */
+void pmb_sqp_default_settings(pmb_sqp_settings_t* s);    /* sqp_base.hpp:24-34 defaults */
+void pmb_sqp_default_qp_settings(pmb_qp_settings_t* s);  /* defaults after the SQPBase ctor overrides, sqp_base.hpp:83-90 */
+
+/* a1: Chebyshev<P, GAUSS_LOBATTO>::compute_nodes / compute_diff_matrix / compute_int_weights
+ *     (src/polynomials/ebyshev.hpp:111-117, 198-214, 120-159).  nodes[P+1], D[(P+1)^2] column-major, w[P+1]. */
+int pmb_cheb_tables(int P, double* nodes, double* D, double* w);
+
+/* ---- ContinuousOCP: the "Problem" concept SQPBase consumes (continuous_ocp.hpp:430-647) -------------------------- */
+typedef struct pmb_ocp pmb_ocp_t;
+pmb_ocp_t* pmb_ocp_create(const char* problem_name, int device);
+void pmb_ocp_destroy(pmb_ocp_t* ocp);
+int pmb_ocp_dims(const pmb_ocp_t* ocp, pmb_dims_t* out);
+int pmb_ocp_set_params(pmb_ocp_t* ocp, const double* values, int count);   /* data members of the problem class */
+int pmb_ocp_get_params(const pmb_ocp_t* ocp, double* values, int count);
+int pmb_ocp_set_time_limits(pmb_ocp_t* ocp, double t0, double tf);         /* continuous_ocp.hpp:147-159 */
+int pmb_ocp_time_nodes(const pmb_ocp_t* ocp, double* time_nodes);          /* NN values, descending */
+
+/* var[batch*N], d[batch*ND] (may be NULL when ND == 0), lam[batch*DUAL] */
+int pmb_ocp_cost(pmb_ocp_t* ocp, int batch, const double* var, const double* d, double* cost);                    /* :1180-1207 */
+int pmb_ocp_equalities(pmb_ocp_t* ocp, int batch, const double* var, const double* d, double* c);                 /* :738-766  */
+int pmb_ocp_inequalities(pmb_ocp_t* ocp, int batch, const double* var, const double* d, double* g);               /* :769-782  */
+int pmb_ocp_equalities_linearised(pmb_ocp_t* ocp, int batch, const double* var, const double* d,
+                                  double* c, double* jac /* NUM_EQ x N */);                                        /* :794-878  */
+int pmb_ocp_cost_gradient(pmb_ocp_t* ocp, int batch, const double* var, const double* d,
+                          double* cost, double* grad);                                                             /* :1209-1249 */
+int pmb_ocp_cost_gradient_hessian(pmb_ocp_t* ocp, int batch, const double* var, const double* d,
+                                  double* cost, double* grad, double* hess /* N x N */);                           /* :1253-1367 */
+int pmb_ocp_lagrangian_gradient(pmb_ocp_t* ocp, int batch, const double* var, const double* d, const double* lam,
+                                double* cost, double* lag_grad, double* cost_grad,
+                                double* g /* M */, double* jac /* M x N */);                                        /* :1957-1975 */
+int pmb_ocp_lagrangian_gradient_hessian(pmb_ocp_t* ocp, int batch, const double* var, const double* d, const double* lam,
+                                        double* cost, double* lag_grad, double* lag_hess /* N x N */, double* cost_grad,
+                                        double* g, double* jac);                                                    /* :2097-2174 */
+
+/* ---- QPBase<boxADMM<N,M,double,DENSE,LDLT,Lower>>::solve (qp_base.hpp:161-175, box_admm.hpp:81-205) --------------- */
+/* H[batch*N*N], h[batch*N], A[batch*M*N], Alb/Aub[batch*M], xlb/xub[batch*N]; x_guess/y_guess may be NULL (cold start,
+ * the 7-argument form).  Outputs: x[batch*N] = primal_solution(), y[batch*(M+N)] = dual_solution() = [y_A ; y_box].
+ * Optional outputs (may be NULL): z[batch*M], q[batch*N] (ADMM splitting variables; the active set is
+ * {i: z_i==Alb_i or z_i==Aub_i} U {j: q_j==xlb_j or q_j==xub_j}), perm[batch*(N+M)] (LDLT pivot permutation of the first
+ * factorisation), ctype[batch*(M+N)] = [constr_type ; box_constr_type], n_factor[batch] (number of factorisations). */
+int pmb_qp_solve(int N, int M, int batch,
+                 const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
+                 const double* xlb, const double* xub, const double* x_guess, const double* y_guess,
+                 const pmb_qp_settings_t* settings,
+                 double* x, double* y, pmb_qp_info_t* info,
+                 double* z, double* q, int* perm, int* ctype, int* n_factor);
+
+/* a17: boxADMM::construct_kkt_matrix, dense (box_admm.hpp:207-223).  K[batch*(N+M)^2] column-major; like the reference
+ * only the lower triangle and the diagonal blocks are written (upper-right block is zero). */
+int pmb_kkt_assemble(int N, int M, int batch, const double* H, const double* A, const double* rho_box,
+                     const double* rho_inv, double sigma, double* K);
+
+/* a12: BFGS_update (src/solvers/bfgs.hpp:23-52). B[batch*N*N] in/out, s,y[batch*N]; branch[batch]: 0 plain, 1 damped, 2 skipped */
+int pmb_bfgs_update(int N, int batch, double* B, const double* s, const double* y, int* branch);
+
+/* ---- SQPBase<..., ContinuousOCP<.., DENSE>, boxADMM, IdentityPreconditioner>::solve (sqp_base.hpp:568-696) -------- */
+typedef struct pmb_sqp pmb_sqp_t;
+pmb_sqp_t* pmb_sqp_create(const char* problem_name, int batch, int device);
+void pmb_sqp_destroy(pmb_sqp_t* s);
+pmb_ocp_t* pmb_sqp_problem(pmb_sqp_t* s);                                   /* SQPBase::get_problem() */
+int pmb_sqp_batch(const pmb_sqp_t* s);
+int pmb_sqp_set_settings(pmb_sqp_t* s, const pmb_sqp_settings_t* st);       /* SQPBase::settings()    */
+int pmb_sqp_get_settings(const pmb_sqp_t* s, pmb_sqp_settings_t* st);
+int pmb_sqp_set_qp_settings(pmb_sqp_t* s, const pmb_qp_settings_t* st);     /* SQPBase::qp_settings() */
+int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st);
+/* stride == 0: one vector broadcast to every instance; stride == len: one vector per instance */
+int pmb_sqp_set_bounds_x(pmb_sqp_t* s, const double* lbx, const double* ubx, int stride);   /* lower/upper_bound_x() */
+int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lbg, const double* ubg, int stride);   /* lower/upper_bound_g() */
+int pmb_sqp_set_parameters(pmb_sqp_t* s, const double* d, int stride);                      /* parameters()          */
+int pmb_sqp_set_primal(pmb_sqp_t* s, const double* x, int stride);                          /* primal_solution() =   */
+int pmb_sqp_set_dual(pmb_sqp_t* s, const double* lam, int stride);                          /* dual_solution() =     */
+/* MPC::initial_conditions(x0) (src/control/mpc_wrapper.hpp:89-99): box equality on the LAST NX entries of the X block.
+ * x0_lb/x0_ub[batch*NX] */
+int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const double* x0_ub);
+int pmb_sqp_solve(pmb_sqp_t* s);                                            /* SQPBase::solve(), whole batch */
+int pmb_sqp_get_primal(const pmb_sqp_t* s, double* x);                      /* [batch*N]    */
+int pmb_sqp_get_dual(const pmb_sqp_t* s, double* lam);                      /* [batch*DUAL] */
+int pmb_sqp_get_info(const pmb_sqp_t* s, pmb_sqp_info_t* info);             /* [batch]      */
+/* stats[batch*4] = {cost(), primal_norm(), dual_norm(), constr_violation()} (sqp_base.hpp:192-195) */
+int pmb_sqp_get_stats(const pmb_sqp_t* s, double* stats);
+/* decision trace, row-major [batch][rows], rows <= max_iter; entries of iterations not executed are -1 / NaN.
+ * qp_iter: ADMM trips of the QP; alpha: accepted step; bfgs: -1 exact Hessian, 0 plain, 1 damped, 2 skipped;
+ * ls_trials: merit evaluations; qp_factor: LDLT factorisations in the QP. Any pointer may be NULL. */
+int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qp_iter, double* alpha, int* bfgs, int* ls_trials, int* qp_factor);
+/* device time of the last pmb_sqp_solve in milliseconds (CUDA events on the engine's stream) and launches it issued */
+double pmb_sqp_last_solve_ms(const pmb_sqp_t* s);
+long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s);
+/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the engine's own stream */
+int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYMPC_B200_H */

@@ -1,0 +1,574 @@
+// pmb_capi.cu — the extern "C" boundary of include/polympc_b200.h: problem registry, device workspaces, kernel launches.
+// Compiled by nvcc for sm_100a into polympc_b200/libpolympc_b200.so.  There is no CPU execution path in that library:
+// every compute entry point returns PMB_ERR_NO_DEVICE when no CUDA device is present.
+// (tests/warp_emu compiles this same file with g++ -DPMB_EMU into a test-only library; see pmb_warp.hpp.)
+#ifdef PMB_EMU
+#include "emu_names.h"
+#endif
+#include "../../include/polympc_b200.h"
+#include "pmb_rt.hpp"
+#include "pmb_problems.hpp"
+#include "pmb_kernels.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace pmb;
+
+namespace {
+
+#define PMB_FAIL(code, msg) do { last_error_string() = (msg); return (code); } while (0)
+
+// ---- type-erased problem -----------------------------------------------------------------------------------------
+struct IProblem {
+    pmb_dims_t dims{};
+    int device = 0;
+    virtual ~IProblem() {}
+    virtual void set_params(const double*) = 0;
+    virtual void get_params(double*) const = 0;
+    virtual void set_time_limits(double, double) = 0;
+    virtual void time_nodes(double*) const = 0;
+    virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
+    virtual bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const = 0;
+    virtual bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const = 0;
+};
+
+template <class O>
+struct ProblemImpl : IProblem {
+    O o;
+    ProblemImpl()
+    {
+        o.init();
+        dims.NX = O::NX; dims.NU = O::NU; dims.NP = O::NP; dims.ND = O::ND; dims.NG = O::NG; dims.P = O::P; dims.S = O::S; dims.NN = O::NN;
+        dims.N = O::N; dims.M = O::M; dims.DUAL = O::DUAL; dims.NPARAM = O::Model::NPARAM;
+    }
+    void set_params(const double* v) override { o.model.set_params(v); }
+    void get_params(double* v) const override { o.model.get_params(v); }
+    void set_time_limits(double a, double b) override { o.set_time_limits(a, b); }
+    void time_nodes(double* t) const override { for (int i = 0; i < O::NN; ++i) t[i] = o.time_nodes[i]; }
+    template <int MODE> bool ev(int batch, const OcpIo& io, stream_t s) const { return rt_launch<OcpEvalBody<O, MODE>>(batch, 0, s, o, io); }
+    bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const override
+    {
+        switch (mode) {
+        case OCP_COST: return ev<OCP_COST>(batch, io, s);
+        case OCP_EQ: return ev<OCP_EQ>(batch, io, s);
+        case OCP_INEQ: return ev<OCP_INEQ>(batch, io, s);
+        case OCP_EQ_LIN: return ev<OCP_EQ_LIN>(batch, io, s);
+        case OCP_COST_GRAD: return ev<OCP_COST_GRAD>(batch, io, s);
+        case OCP_COST_GRAD_HESS: return ev<OCP_COST_GRAD_HESS>(batch, io, s);
+        case OCP_LAG_GRAD: return ev<OCP_LAG_GRAD>(batch, io, s);
+        case OCP_LAG_GRAD_HESS: return ev<OCP_LAG_GRAD_HESS>(batch, io, s);
+        }
+        return false;
+    }
+    bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const override
+    { return rt_launch<SqpLineariseBody<O>>(n_active, SqpLineariseBody<O>::SMEM, s, o, ws, first); }
+    bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const override
+    { return rt_launch<SqpStepBody<O>>(n_active, SqpStepBody<O>::SMEM, s, o, ws, st); }
+};
+
+struct Registry { const char* name; IProblem* (*make)(); };
+template <class O> IProblem* mk() { return new ProblemImpl<O>(); }
+#define PMB_REG(NAME, MODEL, P, S) { NAME, &mk<Ocp<MODEL, P, S>> }
+const Registry g_registry[] = {
+    PMB_REG("mobile_robot_6x2", MobileRobot, 6, 2),   // BASELINE.json configs 1, 2, 5
+    PMB_REG("mobile_robot_5x2", MobileRobot, 5, 2),   // reference CasADi fixture / continuous_ocp_test.cpp
+    PMB_REG("mobile_robot_5x3", MobileRobot, 5, 3),   // reference mpc_wrapper_test.cpp
+    PMB_REG("cstr_5x2", Cstr, 5, 2),                  // reference cstr_control_test.cpp, BASELINE.json config 3
+    PMB_REG("kite_12x1", Kite, 12, 1),                // BASELINE.json config 4 (our model)
+    PMB_REG("kite_4x2", Kite, 4, 2),                  // small kite variant for fast parity tests
+};
+const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
+const Registry* find_problem(const char* name)
+{
+    if (!name) return nullptr;
+    for (int i = 0; i < g_nreg; ++i) if (std::strcmp(g_registry[i].name, name) == 0) return &g_registry[i];
+    return nullptr;
+}
+
+bool have_device() { return rt_device_count() > 0; }
+
+/** scoped set of device buffers filled from / drained to host arrays */
+struct Staging {
+    stream_t s = nullptr;
+    std::vector<void*> bufs;
+    bool ok = true;
+    ~Staging() { for (void* p : bufs) rt_free(p); }
+    template <class T> T* in(const T* host, size_t count)
+    {
+        if (!host) return nullptr;
+        T* p = (T*)rt_alloc(count * sizeof(T));
+        if (!p) { ok = false; return nullptr; }
+        bufs.push_back(p);
+        ok = rt_h2d(p, host, count * sizeof(T), s) && ok;
+        return p;
+    }
+    template <class T> T* out(const T* host_flag, size_t count)
+    {
+        if (!host_flag) return nullptr;
+        T* p = (T*)rt_alloc(count * sizeof(T));
+        if (!p) { ok = false; return nullptr; }
+        bufs.push_back(p);
+        return p;
+    }
+    template <class T> void back(T* host, const T* dev, size_t count) { if (host && dev) ok = rt_d2h(host, dev, count * sizeof(T), s) && ok; }
+};
+
+template <int R> bool launch_qp_r(int grid, size_t smem, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, const int* active)
+{ return rt_launch<QpBody<R>>(grid, smem, s, st, qb, active); }
+
+bool launch_qp(int grid, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, const int* active)
+{
+    const int n = qb.N + qb.M;
+    const int R = (n + 31) / 32;
+    const size_t smem = qp_smem_bytes(qb.N, qb.M);
+    if (smem > 227 * 1024) { last_error_string() = "QP too large for the shared-memory LDLT kernel (needs " + std::to_string(smem) + " bytes)"; return false; }
+    switch (R) {
+    case 1: return launch_qp_r<1>(grid, smem, s, st, qb, active);
+    case 2: return launch_qp_r<2>(grid, smem, s, st, qb, active);
+    case 3: return launch_qp_r<3>(grid, smem, s, st, qb, active);
+    case 4: return launch_qp_r<4>(grid, smem, s, st, qb, active);
+    case 5: return launch_qp_r<5>(grid, smem, s, st, qb, active);
+    case 6: return launch_qp_r<6>(grid, smem, s, st, qb, active);
+    default: break;
+    }
+    last_error_string() = "QP dimension N+M > 192 not instantiated";
+    return false;
+}
+
+void sqp_defaults(pmb_sqp_settings_t* s)
+{ s->tau = 0.5; s->eta = 0.25; s->rho = 0.5; s->eps_prim = 1e-3; s->eps_dual = 1e-3; s->max_iter = 100; s->line_search_max_iter = 100; }
+void qp_defaults(pmb_qp_settings_t* s)
+{
+    s->eps_rel = 1e-3; s->eps_abs = 1e-3; s->max_iter = 1000; s->warm_start = 0; s->reuse_pattern = 0; s->verbose = 0;
+    s->rho = 1e-1; s->sigma = 1e-6; s->alpha = 1.0; s->check_termination = 25; s->adaptive_rho = 0; s->adaptive_rho_tolerance = 5;
+    s->adaptive_rho_interval = 25; s->_pad = 0;
+}
+
+} // namespace
+
+struct pmb_ocp { IProblem* impl = nullptr; bool owned = true; };
+
+struct pmb_sqp {
+    pmb_ocp ocp;
+    int batch = 0, device = 0;
+    pmb_sqp_settings_t settings;
+    pmb_qp_settings_t qp_settings;
+    stream_t own_stream = nullptr, stream = nullptr;
+    event_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<double> x, lam, lam_k, H, A, h, al, au, lx, ux, lbx, ubx, lbg, ubg, d, lag_grad, step_prev, p, plam, stats, tr_alpha;
+    DevBuf<pmb_sqp_info_t> info;
+    DevBuf<pmb_qp_info_t> qp_info;
+    DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, active, next_active, next_count;
+    int trace_rows = 0;
+    int* h_count = nullptr;   // pinned
+    double last_ms = 0;
+    long long last_launches = 0;
+    ~pmb_sqp()
+    {
+        rt_set_device(device);
+        rt_host_free(h_count);
+        rt_event_destroy(ev0); rt_event_destroy(ev1);
+        rt_stream_destroy(own_stream);
+        delete ocp.impl;
+    }
+};
+
+extern "C" {
+
+const char* pmb_version(void)
+{
+#ifdef PMB_EMU
+    return "polympc-b200 0.1 (warp-emulator build: TEST INFRASTRUCTURE)";
+#else
+    return "polympc-b200 0.1 (sm_100a)";
+#endif
+}
+const char* pmb_last_error(void) { return last_error_string().c_str(); }
+int pmb_device_count(void) { return rt_device_count(); }
+int pmb_problem_count(void) { return g_nreg; }
+const char* pmb_problem_name(int i) { return (i >= 0 && i < g_nreg) ? g_registry[i].name : nullptr; }
+int pmb_problem_dims(const char* name, pmb_dims_t* out)
+{
+    const Registry* r = find_problem(name);
+    if (!r) PMB_FAIL(PMB_ERR_UNKNOWN_PROBLEM, "unknown problem");
+    if (!out) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null output");
+    std::unique_ptr<IProblem> p(r->make());
+    *out = p->dims;
+    return PMB_OK;
+}
+void pmb_qp_default_settings(pmb_qp_settings_t* s) { if (s) qp_defaults(s); }
+void pmb_sqp_default_settings(pmb_sqp_settings_t* s) { if (s) sqp_defaults(s); }
+void pmb_sqp_default_qp_settings(pmb_qp_settings_t* s)
+{
+    if (!s) return;
+    qp_defaults(s);   // then the SQPBase constructor overrides (sqp_base.hpp:83-90)
+    s->warm_start = 0; s->check_termination = 10; s->eps_abs = 1e-4; s->eps_rel = 1e-4; s->max_iter = 100;
+    s->adaptive_rho = 1; s->adaptive_rho_interval = 50; s->alpha = 1.0;
+}
+
+int pmb_cheb_tables(int P, double* nodes, double* D, double* w)
+{
+    if (P < 2 || P > 64 || !nodes || !D || !w) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "cheb_tables: bad argument");
+    cheb_tables(P, nodes, D, w);
+    return PMB_OK;
+}
+
+// ---- ContinuousOCP ---------------------------------------------------------------------------------------------
+pmb_ocp_t* pmb_ocp_create(const char* name, int device)
+{
+    const Registry* r = find_problem(name);
+    if (!r) { last_error_string() = "unknown problem"; return nullptr; }
+    pmb_ocp_t* h = new pmb_ocp_t();
+    h->impl = r->make();
+    h->impl->device = device;
+    return h;
+}
+void pmb_ocp_destroy(pmb_ocp_t* h) { if (h) { if (h->owned) delete h->impl; delete h; } }
+int pmb_ocp_dims(const pmb_ocp_t* h, pmb_dims_t* out) { if (!h || !out) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *out = h->impl->dims; return PMB_OK; }
+int pmb_ocp_set_params(pmb_ocp_t* h, const double* v, int n)
+{ if (!h || !v || n != h->impl->dims.NPARAM) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_params: bad argument"); h->impl->set_params(v); return PMB_OK; }
+int pmb_ocp_get_params(const pmb_ocp_t* h, double* v, int n)
+{ if (!h || !v || n != h->impl->dims.NPARAM) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "get_params: bad argument"); h->impl->get_params(v); return PMB_OK; }
+int pmb_ocp_set_time_limits(pmb_ocp_t* h, double t0, double tf) { if (!h) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); h->impl->set_time_limits(t0, tf); return PMB_OK; }
+int pmb_ocp_time_nodes(const pmb_ocp_t* h, double* t) { if (!h || !t) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); h->impl->time_nodes(t); return PMB_OK; }
+
+static int ocp_eval_host(pmb_ocp_t* h, int mode, int batch, const double* var, const double* d, const double* lam, double* cost, double* c,
+                         double* g, double* jac, double* grad, double* hess, double* lag_grad)
+{
+    if (!h || batch < 0 || !var) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ocp: bad argument");
+    const pmb_dims_t& D = h->impl->dims;
+    if (D.ND > 0 && !d) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ocp: static parameters required");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    if (!rt_set_device(h->impl->device)) return PMB_ERR_CUDA;
+    const size_t B = batch, N = D.N, M = D.M, NE = (size_t)D.NX * D.NN, NI = (size_t)D.NG * D.NN;
+    const bool full = (mode == OCP_LAG_GRAD || mode == OCP_LAG_GRAD_HESS);
+    const size_t crow = full ? M : NE;
+    Staging st;
+    OcpIo io{};
+    io.var = st.in(var, B * N);
+    io.d = D.ND > 0 ? st.in(d, B * D.ND) : nullptr;
+    io.lam = st.in(lam, B * D.DUAL);
+    io.cost = st.out(cost, B);
+    io.c = st.out(c, B * crow);
+    io.g = NI > 0 ? st.out(g, B * NI) : nullptr;
+    io.jac = st.out(jac, B * crow * N);
+    io.grad = st.out(grad, B * N);
+    io.hess = st.out(hess, B * N * N);
+    io.lag_grad = st.out(lag_grad, B * N);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (mode == OCP_INEQ && NI == 0) return PMB_OK;
+    if (!h->impl->launch_eval(mode, batch, io, st.s)) return PMB_ERR_CUDA;
+    st.back(cost, io.cost, B); st.back(c, io.c, B * crow); if (NI > 0) st.back(g, io.g, B * NI);
+    st.back(jac, io.jac, B * crow * N); st.back(grad, io.grad, B * N); st.back(hess, io.hess, B * N * N); st.back(lag_grad, io.lag_grad, B * N);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+int pmb_ocp_cost(pmb_ocp_t* h, int batch, const double* var, const double* d, double* cost)
+{ return ocp_eval_host(h, OCP_COST, batch, var, d, nullptr, cost, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); }
+int pmb_ocp_equalities(pmb_ocp_t* h, int batch, const double* var, const double* d, double* c)
+{ return ocp_eval_host(h, OCP_EQ, batch, var, d, nullptr, nullptr, c, nullptr, nullptr, nullptr, nullptr, nullptr); }
+int pmb_ocp_inequalities(pmb_ocp_t* h, int batch, const double* var, const double* d, double* g)
+{ return ocp_eval_host(h, OCP_INEQ, batch, var, d, nullptr, nullptr, nullptr, g, nullptr, nullptr, nullptr, nullptr); }
+int pmb_ocp_equalities_linearised(pmb_ocp_t* h, int batch, const double* var, const double* d, double* c, double* jac)
+{ return ocp_eval_host(h, OCP_EQ_LIN, batch, var, d, nullptr, nullptr, c, nullptr, jac, nullptr, nullptr, nullptr); }
+int pmb_ocp_cost_gradient(pmb_ocp_t* h, int batch, const double* var, const double* d, double* cost, double* grad)
+{ return ocp_eval_host(h, OCP_COST_GRAD, batch, var, d, nullptr, cost, nullptr, nullptr, nullptr, grad, nullptr, nullptr); }
+int pmb_ocp_cost_gradient_hessian(pmb_ocp_t* h, int batch, const double* var, const double* d, double* cost, double* grad, double* hess)
+{ return ocp_eval_host(h, OCP_COST_GRAD_HESS, batch, var, d, nullptr, cost, nullptr, nullptr, nullptr, grad, hess, nullptr); }
+int pmb_ocp_lagrangian_gradient(pmb_ocp_t* h, int batch, const double* var, const double* d, const double* lam, double* cost,
+                                double* lag_grad, double* cost_grad, double* g, double* jac)
+{
+    if (!lam) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "lagrangian_gradient: lam required");
+    return ocp_eval_host(h, OCP_LAG_GRAD, batch, var, d, lam, cost, g, nullptr, jac, cost_grad, nullptr, lag_grad);
+}
+int pmb_ocp_lagrangian_gradient_hessian(pmb_ocp_t* h, int batch, const double* var, const double* d, const double* lam, double* cost,
+                                        double* lag_grad, double* lag_hess, double* cost_grad, double* g, double* jac)
+{
+    if (!lam) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "lagrangian_gradient_hessian: lam required");
+    return ocp_eval_host(h, OCP_LAG_GRAD_HESS, batch, var, d, lam, cost, g, nullptr, jac, cost_grad, lag_hess, lag_grad);
+}
+
+// ---- QP / KKT / BFGS operators ------------------------------------------------------------------------------------
+int pmb_qp_solve(int N, int M, int batch, const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
+                 const double* xlb, const double* xub, const double* x_guess, const double* y_guess, const pmb_qp_settings_t* settings,
+                 double* x, double* y, pmb_qp_info_t* info, double* z, double* q, int* perm, int* ctype, int* n_factor)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !h || (M > 0 && (!A || !Alb || !Aub)) || !xlb || !xub || !settings || !x || !y || !info)
+        PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "qp_solve: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch, n = (size_t)N + M;
+    Staging st;
+    QpBatch qb{};
+    qb.N = N; qb.M = M;
+    qb.H = st.in(H, B * N * N); qb.h = st.in(h, B * N); qb.A = st.in(A, B * M * N); qb.Alb = st.in(Alb, B * M); qb.Aub = st.in(Aub, B * M);
+    qb.xlb = st.in(xlb, B * N); qb.xub = st.in(xub, B * N); qb.xg = st.in(x_guess, B * N); qb.yg = st.in(y_guess, B * n);
+    qb.x = st.out(x, B * N); qb.y = st.out(y, B * n); qb.info = st.out(info, B); qb.z = st.out(z, B * M); qb.q = st.out(q, B * N);
+    qb.perm = st.out(perm, B * n); qb.ctype = st.out(ctype, B * n); qb.nfac = st.out(n_factor, B);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!launch_qp(batch, st.s, *settings, qb, nullptr)) return PMB_ERR_CUDA;
+    st.back(x, qb.x, B * N); st.back(y, qb.y, B * n); st.back(info, qb.info, B); st.back(z, qb.z, B * M); st.back(q, qb.q, B * N);
+    st.back(perm, qb.perm, B * n); st.back(ctype, qb.ctype, B * n); st.back(n_factor, qb.nfac, B);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+int pmb_kkt_assemble(int N, int M, int batch, const double* H, const double* A, const double* rho_box, const double* rho_inv, double sigma,
+                     double* K)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !A || !rho_box || !rho_inv || !K) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "kkt_assemble: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch, n = (size_t)N + M;
+    Staging st;
+    const double* dH = st.in(H, B * N * N); const double* dA = st.in(A, B * M * N);
+    const double* drb = st.in(rho_box, B * N); const double* dri = st.in(rho_inv, B * M);
+    double* dK = st.out(K, B * n * n);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!rt_launch<KktDenseBody>(batch, 0, st.s, N, M, dH, dA, drb, dri, sigma, dK)) return PMB_ERR_CUDA;
+    st.back(K, dK, B * n * n);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double* y, int* branch)
+{
+    if (N <= 0 || batch < 0 || !Bm || !s || !y) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "bfgs_update: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch;
+    Staging st;
+    double* dB = st.in((const double*)Bm, B * N * N);
+    const double* ds = st.in(s, B * N); const double* dy = st.in(y, B * N);
+    int* dbr = st.out(branch, B);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!rt_launch<BfgsBody>(batch, 2 * (size_t)N * sizeof(double), st.s, N, dB, ds, dy, dbr)) return PMB_ERR_CUDA;
+    st.back(Bm, (const double*)dB, B * N * N); st.back(branch, (const int*)dbr, B);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+// ---- SQP -------------------------------------------------------------------------------------------------------
+pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
+{
+    const Registry* r = find_problem(name);
+    if (!r || batch <= 0) { last_error_string() = "sqp_create: unknown problem or bad batch"; return nullptr; }
+    if (!have_device()) { last_error_string() = "no CUDA device: the engine has no CPU fallback"; return nullptr; }
+    if (device < 0 || device >= rt_device_count() || !rt_set_device(device)) { last_error_string() = "sqp_create: bad device"; return nullptr; }
+    std::unique_ptr<pmb_sqp_t> s(new pmb_sqp_t());
+    s->ocp.impl = r->make(); s->ocp.impl->device = device; s->ocp.owned = false;
+    s->batch = batch; s->device = device;
+    sqp_defaults(&s->settings);
+    pmb_sqp_default_qp_settings(&s->qp_settings);
+    const pmb_dims_t& D = s->ocp.impl->dims;
+    const size_t B = batch, N = D.N, M = D.M, DU = D.DUAL, NI = (size_t)D.NG * D.NN, ND = D.ND;
+    bool ok = s->x.resize(B * N) && s->lam.resize(B * DU) && s->lam_k.resize(B * DU) && s->H.resize(B * N * N) && s->A.resize(B * M * N) &&
+              s->h.resize(B * N) && s->al.resize(B * M) && s->au.resize(B * M) && s->lx.resize(B * N) && s->ux.resize(B * N) &&
+              s->lbx.resize(B * N) && s->ubx.resize(B * N) && s->lbg.resize(B * NI + 1) && s->ubg.resize(B * NI + 1) && s->d.resize(B * ND + 1) &&
+              s->lag_grad.resize(B * N) && s->step_prev.resize(B * N) && s->p.resize(B * N) && s->plam.resize(B * DU) && s->stats.resize(B * 4) &&
+              s->info.resize(B) && s->qp_info.resize(B) && s->qp_nfac.resize(B) && s->active.resize(B) && s->next_active.resize(B) &&
+              s->next_count.resize(1);
+    ok = ok && rt_stream_create(&s->own_stream) && rt_event_create(&s->ev0) && rt_event_create(&s->ev1);
+    if (!ok) return nullptr;
+    s->stream = s->own_stream;
+    s->h_count = (int*)rt_host_alloc(sizeof(int));
+    if (!s->h_count) return nullptr;
+    // SQPBase constructor state (sqp_base.hpp:72-99): x = 0, lam = 0, bounds +-inf
+    const double INF = std::numeric_limits<double>::infinity();
+    std::vector<double> lo(B * N, -INF), hi(B * N, INF);
+    ok = rt_memset(s->x.p, 0, s->x.bytes(), s->stream) && rt_memset(s->lam.p, 0, s->lam.bytes(), s->stream) &&
+         rt_memset(s->d.p, 0, s->d.bytes(), s->stream) && rt_memset(s->stats.p, 0, s->stats.bytes(), s->stream) &&
+         rt_memset(s->info.p, 0, s->info.bytes(), s->stream) &&
+         rt_h2d(s->lbx.p, lo.data(), B * N * sizeof(double), s->stream) && rt_h2d(s->ubx.p, hi.data(), B * N * sizeof(double), s->stream);
+    if (NI > 0) ok = ok && rt_h2d(s->lbg.p, lo.data(), B * NI * sizeof(double), s->stream) && rt_h2d(s->ubg.p, hi.data(), B * NI * sizeof(double), s->stream);
+    ok = ok && rt_sync(s->stream);
+    if (!ok) return nullptr;
+    return s.release();
+}
+void pmb_sqp_destroy(pmb_sqp_t* s) { delete s; }
+pmb_ocp_t* pmb_sqp_problem(pmb_sqp_t* s) { return s ? &s->ocp : nullptr; }
+int pmb_sqp_batch(const pmb_sqp_t* s) { return s ? s->batch : (int)PMB_ERR_BAD_ARGUMENT; }
+int pmb_sqp_set_settings(pmb_sqp_t* s, const pmb_sqp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->settings = *st; return PMB_OK; }
+int pmb_sqp_get_settings(const pmb_sqp_t* s, pmb_sqp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *st = s->settings; return PMB_OK; }
+int pmb_sqp_set_qp_settings(pmb_sqp_t* s, const pmb_qp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->qp_settings = *st; return PMB_OK; }
+int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *st = s->qp_settings; return PMB_OK; }
+
+static int sqp_set_vec(pmb_sqp_t* s, double* dst, const double* v, int stride, size_t len)
+{
+    if (len == 0) return PMB_OK;
+    if (!v || (stride != 0 && (size_t)stride != len)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "sqp setter: bad pointer or stride");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const size_t B = s->batch;
+    bool ok;
+    if (stride == 0) {
+        std::vector<double> tmp(B * len);
+        for (size_t b = 0; b < B; ++b) std::memcpy(tmp.data() + b * len, v, len * sizeof(double));
+        ok = rt_h2d(dst, tmp.data(), B * len * sizeof(double), s->stream) && rt_sync(s->stream);
+    } else {
+        ok = rt_h2d(dst, v, B * len * sizeof(double), s->stream) && rt_sync(s->stream);
+    }
+    return ok ? PMB_OK : PMB_ERR_CUDA;
+}
+int pmb_sqp_set_bounds_x(pmb_sqp_t* s, const double* lb, const double* ub, int stride)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    const size_t N = s->ocp.impl->dims.N;
+    const int r = sqp_set_vec(s, s->lbx.p, lb, stride, N);
+    return r ? r : sqp_set_vec(s, s->ubx.p, ub, stride, N);
+}
+int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lb, const double* ub, int stride)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    const size_t n = (size_t)s->ocp.impl->dims.NG * s->ocp.impl->dims.NN;
+    const int r = sqp_set_vec(s, s->lbg.p, lb, stride, n);
+    return r ? r : sqp_set_vec(s, s->ubg.p, ub, stride, n);
+}
+int pmb_sqp_set_parameters(pmb_sqp_t* s, const double* d, int stride)
+{ if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->d.p, d, stride, s->ocp.impl->dims.ND); }
+int pmb_sqp_set_primal(pmb_sqp_t* s, const double* x, int stride)
+{ if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->x.p, x, stride, s->ocp.impl->dims.N); }
+int pmb_sqp_set_dual(pmb_sqp_t* s, const double* l, int stride)
+{ if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->lam.p, l, stride, s->ocp.impl->dims.DUAL); }
+
+/** strided 2-D copy helper for the initial-condition rows: dst[b*N + off + i] = src[b*NX + i] */
+struct ScatterRowsBody {
+    static constexpr int THREADS = 128;
+    static constexpr const char* NAME = "scatter_rows";
+    static constexpr size_t EMU_STACK_BYTES = 128u << 10;
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char*, int batch, int len, int ld, int off, const double* src, double* dst)
+    {
+        const int e = blk * THREADS + w.tid();
+        if (e < batch * len) { const int b = e / len, i = e - b * len; dst[(size_t)b * ld + off + i] = src[e]; }
+    }
+};
+
+int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const double* x0_ub)
+{
+    if (!s || !x0_lb || !x0_ub) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_initial_conditions: null");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const pmb_dims_t& D = s->ocp.impl->dims;
+    const int B = s->batch, NX = D.NX, off = D.NX * D.NN - D.NX;
+    DevBuf<double> tmp;
+    if (!tmp.resize((size_t)2 * B * NX)) return PMB_ERR_CUDA;
+    bool ok = rt_h2d(tmp.p, x0_lb, (size_t)B * NX * sizeof(double), s->stream) &&
+              rt_h2d(tmp.p + (size_t)B * NX, x0_ub, (size_t)B * NX * sizeof(double), s->stream);
+    const int grid = (B * NX + ScatterRowsBody::THREADS - 1) / ScatterRowsBody::THREADS;
+    ok = ok && rt_launch<ScatterRowsBody>(grid, 0, s->stream, B, NX, D.N, off, (const double*)tmp.p, s->lbx.p);
+    ok = ok && rt_launch<ScatterRowsBody>(grid, 0, s->stream, B, NX, D.N, off, (const double*)(tmp.p + (size_t)B * NX), s->ubx.p);
+    ok = ok && rt_sync(s->stream);
+    return ok ? PMB_OK : PMB_ERR_CUDA;
+}
+
+struct IotaBody {
+    static constexpr int THREADS = 256;
+    static constexpr const char* NAME = "sqp_init";
+    static constexpr size_t EMU_STACK_BYTES = 128u << 10;
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char*, int n, int* active, pmb_sqp_info_t* info)
+    {
+        const int e = blk * THREADS + w.tid();
+        if (e < n) { active[e] = e; info[e].iter = 1; info[e].qp_solver_iter = 0; info[e].status = PMB_SQP_MAX_ITER_EXCEEDED; }
+    }
+};
+
+int pmb_sqp_solve(pmb_sqp_t* s)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const int B = s->batch;
+    const int rows = s->settings.max_iter > 0 ? s->settings.max_iter : 1;
+    if (rows != s->trace_rows) {
+        const size_t T = (size_t)B * rows;
+        if (!(s->tr_qp_iter.resize(T) && s->tr_bfgs.resize(T) && s->tr_ls.resize(T) && s->tr_qp_factor.resize(T) && s->tr_alpha.resize(T))) return PMB_ERR_CUDA;
+        s->trace_rows = rows;
+    }
+    stream_t st = s->stream;
+    bool ok = rt_event_record(s->ev0, st);
+    {
+        const size_t T = (size_t)B * rows;
+        ok = ok && rt_memset(s->tr_qp_iter.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_bfgs.p, 0xFF, T * sizeof(int), st) &&
+             rt_memset(s->tr_ls.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_qp_factor.p, 0xFF, T * sizeof(int), st) &&
+             rt_memset(s->tr_alpha.p, 0xFF, T * sizeof(double), st);
+    }
+    SqpWs ws{};
+    ws.x = s->x.p; ws.lam = s->lam.p; ws.lam_k = s->lam_k.p; ws.H = s->H.p; ws.A = s->A.p; ws.h = s->h.p; ws.al = s->al.p; ws.au = s->au.p;
+    ws.lx = s->lx.p; ws.ux = s->ux.p; ws.lbx = s->lbx.p; ws.ubx = s->ubx.p; ws.lbg = s->lbg.p; ws.ubg = s->ubg.p; ws.d = s->d.p;
+    ws.lag_grad = s->lag_grad.p; ws.step_prev = s->step_prev.p; ws.p = s->p.p; ws.plam = s->plam.p; ws.stats = s->stats.p;
+    ws.info = s->info.p; ws.qp_info = s->qp_info.p; ws.qp_nfac = s->qp_nfac.p;
+    ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p;
+    ws.trace_rows = rows;
+    ws.active = s->active.p; ws.next_active = s->next_active.p; ws.next_count = s->next_count.p;
+
+    long long launches = 0;
+    ok = ok && rt_launch<IotaBody>((B + IotaBody::THREADS - 1) / IotaBody::THREADS, 0, st, B, ws.active, ws.info);
+    ++launches;
+    const IProblem& P = *s->ocp.impl;
+    const pmb_dims_t& D = P.dims;
+    QpBatch qb{};
+    qb.N = D.N; qb.M = D.M; qb.H = ws.H; qb.h = ws.h; qb.A = ws.A; qb.Alb = ws.al; qb.Aub = ws.au; qb.xlb = ws.lx; qb.xub = ws.ux;
+    qb.x = ws.p; qb.y = ws.plam; qb.info = ws.qp_info; qb.nfac = ws.qp_nfac;
+
+    int n_active = B;
+    for (int it = 1; ok && n_active > 0 && it <= s->settings.max_iter; ++it) {
+        ok = ok && rt_memset(ws.next_count, 0, sizeof(int), st);
+        ok = ok && P.launch_linearise(n_active, ws, it == 1 ? 1 : 0, st);
+        ok = ok && launch_qp(n_active, st, s->qp_settings, qb, ws.active);
+        ok = ok && P.launch_step(n_active, ws, s->settings, st);
+        launches += 3;
+        ok = ok && rt_d2h(s->h_count, ws.next_count, sizeof(int), st) && rt_sync(st);
+        if (!ok) break;
+        n_active = *s->h_count;
+        int* t = ws.active; ws.active = ws.next_active; ws.next_active = t;
+    }
+    ok = ok && rt_event_record(s->ev1, st) && rt_sync(st);
+    if (!ok) return PMB_ERR_CUDA;
+    s->last_ms = rt_event_ms(s->ev0, s->ev1);
+    s->last_launches = launches;
+    return PMB_OK;
+}
+
+static int sqp_get(const pmb_sqp_t* s, void* host, const void* dev, size_t bytes)
+{
+    if (!s || !host) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    return (rt_d2h(host, dev, bytes, s->stream) && rt_sync(s->stream)) ? PMB_OK : PMB_ERR_CUDA;
+}
+int pmb_sqp_get_primal(const pmb_sqp_t* s, double* x) { return sqp_get(s, x, s ? s->x.p : nullptr, s ? (size_t)s->batch * s->ocp.impl->dims.N * sizeof(double) : 0); }
+int pmb_sqp_get_dual(const pmb_sqp_t* s, double* l) { return sqp_get(s, l, s ? s->lam.p : nullptr, s ? (size_t)s->batch * s->ocp.impl->dims.DUAL * sizeof(double) : 0); }
+int pmb_sqp_get_info(const pmb_sqp_t* s, pmb_sqp_info_t* info) { return sqp_get(s, info, s ? s->info.p : nullptr, s ? (size_t)s->batch * sizeof(pmb_sqp_info_t) : 0); }
+int pmb_sqp_get_stats(const pmb_sqp_t* s, double* st) { return sqp_get(s, st, s ? s->stats.p : nullptr, s ? (size_t)s->batch * 4 * sizeof(double) : 0); }
+int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf, int* ls, int* qf)
+{
+    if (!s || rows <= 0) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "get_trace: bad argument");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const size_t B = s->batch, T = s->trace_rows;
+    std::vector<int> ti(B * T); std::vector<double> td(B * T);
+    auto pull_i = [&](int* out, const int* dev) -> bool {
+        if (!out) return true;
+        if (T > 0 && !(rt_d2h(ti.data(), dev, B * T * sizeof(int), s->stream) && rt_sync(s->stream))) return false;
+        for (size_t b = 0; b < B; ++b) for (int r = 0; r < rows; ++r) out[b * rows + r] = (size_t)r < T ? ti[b * T + r] : -1;
+        return true;
+    };
+    bool ok = pull_i(qi, s->tr_qp_iter.p) && pull_i(bf, s->tr_bfgs.p) && pull_i(ls, s->tr_ls.p) && pull_i(qf, s->tr_qp_factor.p);
+    if (ok && al) {
+        if (T > 0) ok = rt_d2h(td.data(), s->tr_alpha.p, B * T * sizeof(double), s->stream) && rt_sync(s->stream);
+        for (size_t b = 0; b < B; ++b) for (int r = 0; r < rows; ++r) al[b * rows + r] = (size_t)r < T ? td[b * T + r] : std::nan("");
+    }
+    return ok ? PMB_OK : PMB_ERR_CUDA;
+}
+double pmb_sqp_last_solve_ms(const pmb_sqp_t* s) { return s ? s->last_ms : 0.0; }
+long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s) { return s ? s->last_launches : 0; }
+int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    s->stream = cuda_stream ? (stream_t)cuda_stream : s->own_stream;
+    return PMB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,191 @@
+// pmb_kernels.hpp — kernel bodies (one warp = one block = one OCP/QP instance unless noted) launched by pmb_capi.cu.
+// Every body is a struct with THREADS, NAME, EMU_STACK_BYTES and a static run(); see pmb_warp.hpp.
+#pragma once
+#include "pmb_ocp.hpp"
+#include "pmb_qp.hpp"
+#include "pmb_sqp.hpp"
+
+namespace pmb {
+
+// ---- transcription operators (C ABI pmb_ocp_*) ----------------------------------------------------------------------
+enum OcpMode { OCP_COST = 0, OCP_EQ, OCP_INEQ, OCP_EQ_LIN, OCP_COST_GRAD, OCP_COST_GRAD_HESS, OCP_LAG_GRAD, OCP_LAG_GRAD_HESS };
+
+struct OcpIo {
+    const double *var, *d, *lam;
+    double *cost, *c, *g, *jac, *grad, *hess, *lag_grad;
+};
+
+template <class O, int MODE>
+struct OcpEvalBody {
+    static constexpr int THREADS = 32;
+    static constexpr const char* NAME = "ocp_eval";
+    static constexpr size_t EMU_STACK_BYTES = 4u << 20;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char*, O o, OcpIo io)
+    {
+        using E = OcpEval<O>;
+        const double* var = io.var + (size_t)b * O::N;
+        const double* d = io.d ? io.d + (size_t)b * O::ND : nullptr;
+        const double* lam = io.lam ? io.lam + (size_t)b * O::DUAL : nullptr;
+        double cost = 0.0;
+        if (MODE == OCP_COST) cost = E::cost(w, o, var, d);
+        else if (MODE == OCP_EQ) E::equalities(w, o, var, d, io.c + (size_t)b * O::NUM_EQ);
+        else if (MODE == OCP_INEQ) E::inequalities(w, o, var, d, io.g + (size_t)b * O::NUM_INEQ);
+        else if (MODE == OCP_EQ_LIN)
+            E::constraints_linearised(w, o, var, d, io.c + (size_t)b * O::NUM_EQ, io.jac + (size_t)b * O::NUM_EQ * O::N, O::NUM_EQ, false);
+        else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(w, o, var, d, io.grad + (size_t)b * O::N);
+        else if (MODE == OCP_COST_GRAD_HESS)
+            cost = E::cost_gradient_hessian(w, o, var, d, nullptr, io.grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N);
+        else if (MODE == OCP_LAG_GRAD)
+            cost = E::lagrangian_gradient(w, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.grad + (size_t)b * O::N,
+                                          io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N);
+        else if (MODE == OCP_LAG_GRAD_HESS)
+            cost = E::lagrangian_gradient_hessian(w, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N,
+                                                  io.grad + (size_t)b * O::N, io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N);
+        if (io.cost && w.lane() == 0 && MODE != OCP_EQ && MODE != OCP_INEQ && MODE != OCP_EQ_LIN) io.cost[b] = cost;
+    }
+};
+
+// ---- QP -------------------------------------------------------------------------------------------------------------
+struct QpBatch {
+    int N, M;
+    const double *H, *h, *A, *Alb, *Aub, *xlb, *xub, *xg, *yg;
+    double *x, *y;
+    pmb_qp_info_t* info;
+    double *z, *q;
+    int *perm, *ctype, *nfac;
+};
+
+PMB_DEV QpArgs qp_instance(const QpBatch& q, int b)
+{
+    const size_t N = q.N, M = q.M, n = N + M;
+    QpArgs a;
+    a.N = q.N; a.M = q.M;
+    a.H = q.H + b * N * N; a.h = q.h + b * N; a.A = q.A + b * M * N; a.Alb = q.Alb + b * M; a.Aub = q.Aub + b * M;
+    a.xlb = q.xlb + b * N; a.xub = q.xub + b * N;
+    a.xg = q.xg ? q.xg + b * N : nullptr; a.yg = q.yg ? q.yg + b * n : nullptr;
+    a.x = q.x + b * N; a.y = q.y + b * n; a.info = q.info ? q.info + b : nullptr;
+    a.z = q.z ? q.z + b * M : nullptr; a.q = q.q ? q.q + b * N : nullptr;
+    a.perm = q.perm ? q.perm + b * n : nullptr; a.ctype = q.ctype ? q.ctype + b * n : nullptr; a.nfac = q.nfac ? q.nfac + b : nullptr;
+    return a;
+}
+
+template <int R>
+struct QpBody {
+    static constexpr int THREADS = 32;
+    static constexpr const char* NAME = "qp_box_admm";
+    static constexpr size_t EMU_STACK_BYTES = 1u << 20;
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, QpBatch qb, const int* active)
+    {
+        const int b = active ? active[blk] : blk;
+        const QpArgs a = qp_instance(qb, b);
+        qp_solve_warp<R>(w, st, a, smem);
+    }
+};
+
+// ---- a17: KKT assembly, reference layout (dense (N+M)^2, lower part + diagonal blocks written, rest zero) ------------
+struct KktDenseBody {
+    static constexpr int THREADS = 256;
+    static constexpr const char* NAME = "kkt_assemble_dense";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char*, int N, int M, const double* H, const double* A, const double* rho_box,
+                            const double* rho_inv, double sigma, double* K)
+    {
+        const int n = N + M;
+        const double* Hb = H + (size_t)b * N * N;
+        const double* Ab = A + (size_t)b * M * N;
+        double* Kb = K + (size_t)b * n * n;
+        const int total = n * n;
+        for (int e = w.tid(); e < total; e += w.nthreads()) {
+            const int j = e / n, i = e - j * n;
+            double v = 0.0;
+            if (j < N) {
+                if (i < N) { v = Hb[i + (size_t)j * N]; if (i == j) { v += sigma; v += rho_box[(size_t)b * N + i]; } }
+                else v = Ab[(i - N) + (size_t)j * M];
+            } else if (i == j) v = -rho_inv[(size_t)b * M + (i - N)];
+            Kb[e] = v;
+        }
+    }
+};
+
+// ---- BFGS operator (C ABI pmb_bfgs_update) -----------------------------------------------------------------------------
+struct BfgsBody {
+    static constexpr int THREADS = 32;
+    static constexpr const char* NAME = "bfgs_update";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, int N, double* B, const double* s, const double* y, int* branch)
+    {
+        double* Bs = reinterpret_cast<double*>(smem);
+        double* r = Bs + N;
+        const int br = bfgs_update_warp(w, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
+        if (branch && w.lane() == 0) branch[b] = br;
+    }
+};
+
+// ---- SQP pipeline ---------------------------------------------------------------------------------------------------
+struct SqpWs {
+    double *x, *lam, *lam_k, *H, *A, *h, *al, *au, *lx, *ux, *lbx, *ubx, *lbg, *ubg, *d, *lag_grad, *step_prev, *p, *plam, *stats;
+    pmb_sqp_info_t* info;
+    pmb_qp_info_t* qp_info;
+    int* qp_nfac;
+    int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
+    double* tr_alpha;
+    int trace_rows;
+    int *active, *next_active, *next_count;
+};
+
+template <class O>
+PMB_DEV SqpInst sqp_instance(const SqpWs& ws, int b)
+{
+    const size_t N = O::N, M = O::M, DUAL = O::DUAL, NI = O::NUM_INEQ, ND = O::ND, T = (size_t)ws.trace_rows;
+    SqpInst s;
+    s.x = ws.x + b * N; s.lam = ws.lam + b * DUAL; s.lam_k = ws.lam_k + b * DUAL; s.H = ws.H + b * N * N; s.A = ws.A + b * M * N;
+    s.h = ws.h + b * N; s.al = ws.al + b * M; s.au = ws.au + b * M; s.lx = ws.lx + b * N; s.ux = ws.ux + b * N;
+    s.lag_grad = ws.lag_grad + b * N; s.step_prev = ws.step_prev + b * N; s.p = ws.p + b * N; s.plam = ws.plam + b * DUAL;
+    s.stats = ws.stats + b * 4;
+    s.lbx = ws.lbx + b * N; s.ubx = ws.ubx + b * N; s.lbg = ws.lbg + b * NI; s.ubg = ws.ubg + b * NI; s.d = ws.d + b * ND;
+    s.info = ws.info + b; s.qp_info = ws.qp_info + b; s.qp_nfac = ws.qp_nfac + b;
+    s.tr_qp_iter = ws.tr_qp_iter ? ws.tr_qp_iter + b * T : nullptr; s.tr_bfgs = ws.tr_bfgs ? ws.tr_bfgs + b * T : nullptr;
+    s.tr_ls = ws.tr_ls ? ws.tr_ls + b * T : nullptr; s.tr_qp_factor = ws.tr_qp_factor ? ws.tr_qp_factor + b * T : nullptr;
+    s.tr_alpha = ws.tr_alpha ? ws.tr_alpha + b * T : nullptr;
+    return s;
+}
+
+template <class O>
+struct SqpLineariseBody {
+    static constexpr int THREADS = 32;
+    static constexpr const char* NAME = "sqp_linearise";
+    static constexpr size_t EMU_STACK_BYTES = 4u << 20;
+    static constexpr size_t SMEM = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, int first)
+    {
+        const int b = ws.active[blk];
+        const SqpInst s = sqp_instance<O>(ws, b);
+        const int row = s.info->iter - 1;
+        SqpDev<O>::linearise(w, o, s, first != 0, row, reinterpret_cast<double*>(smem));
+    }
+};
+
+template <class O>
+struct SqpStepBody {
+    static constexpr int THREADS = 32;
+    static constexpr const char* NAME = "sqp_linesearch_step";
+    static constexpr size_t EMU_STACK_BYTES = 4u << 20;
+    static constexpr size_t SMEM = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st)
+    {
+        const int b = ws.active[blk];
+        const SqpInst s = sqp_instance<O>(ws, b);
+        const int row = s.info->iter - 1;
+        const bool done = SqpDev<O>::step(w, o, s, st, row, reinterpret_cast<double*>(smem));
+        if (w.lane() == 0) {
+            if (done) s.info->status = PMB_SQP_SOLVED;
+            else if (s.info->iter < st.max_iter) {
+                s.info->iter += 1;
+                const int slot = atomic_add(ws.next_count, 1);
+                ws.next_active[slot] = b;
+            }
+        }
+    }
+};
+
+} // namespace pmb

@@ -1,0 +1,372 @@
+// pmb_ocp.hpp — batched transcription of a Chebyshev-collocated OCP: one warp per instance, lane k <-> collocation node k.
+//
+// Reference (dense path of src/control/continuous_ocp.hpp; line numbers of the reference):
+//   sizes / layout 69-98, time nodes 45-66 & 147-159, seeding 690-735, equalities 738-766, inequalities 769-782,
+//   equalities_linearised 794-878, inequalities_linearised 546-575, cost 1180-1207, cost_gradient 1209-1249,
+//   cost_gradient_hessian 1253-1367, lagrangian_gradient 1957-1975, lagrangian_gradient_hessian 2097-2174.
+// Layout: var = [X (NX*NN) | U (NU*NN) | P (NP)], node k at k*NX / VARX + k*NU; node 0 is the FINAL time (time nodes
+// descend); lam = [lam_eq | lam_ineq | lam_box].  Matrices are column-major.
+//
+// Mapping: every node's functor evaluation (plain, first-order dual, second-order dual) is independent, so lane k owns
+// node k: its NX collocation rows of the Jacobian, its gradient entries and its (NX+NU)^2 diagonal Hessian block.
+// Junction nodes of the spline are counted twice in the quadrature, in segment order, exactly like the reference loop.
+// The only cross-lane steps are the cost sum (a fixed sequential order, done with shuffles) and the A^T*lam product.
+#pragma once
+#include "pmb_warp.hpp"
+#include "pmb_dual.hpp"
+#include "pmb_cheb.hpp"
+
+namespace pmb {
+
+template <class Model_, int P_, int S_>
+struct Ocp {
+    using Model = Model_;
+    static constexpr int NX = Model::NX, NU = Model::NU, NP = Model::NP, ND = Model::ND, NG = Model::NG;
+    static constexpr int P = P_, S = S_, NN = P_ * S_ + 1;
+    static constexpr int VARX = NX * NN, VARU = NU * NN, N = VARX + VARU + NP;
+    static constexpr int NUM_EQ = VARX, NUM_INEQ = NG * NN, M = NUM_EQ + NUM_INEQ, DUAL = M + N;
+    static constexpr int NDIR = NX + NU + NP;
+    static_assert(NN <= 32, "one warp per instance: at most 32 collocation nodes");
+    static_assert(NP == 0, "optimised parameters (NP > 0) are not on the GPU path yet");
+    using ad1 = Dual<double, NDIR>;
+    using ad2 = Dual<ad1, NDIR>;
+
+    Model model;
+    double D[(P + 1) * (P + 1)];   // column-major
+    double w[P + 1];
+    double nodes[P + 1];
+    double time_nodes[NN];
+    double t_start, t_stop, ts;
+
+    void init()
+    {
+        model.defaults();
+        cheb_tables(P, nodes, D, w);
+        set_time_limits(0.0, 1.0);
+    }
+    /** continuous_ocp.hpp:45-55, 147-159 */
+    void set_time_limits(double t0, double tf)
+    {
+        t_start = t0; t_stop = tf;
+        const double t_length = (t_stop - t_start) / (double)S;
+        const double t_shift = t_length / 2;
+        for (int i = 0; i < S; ++i)
+            for (int k = 0; k <= P; ++k)
+                time_nodes[i * P + k] = (t_length / 2) * nodes[P - k] + (t_start + t_shift + (double)i * t_length) * 1.0;
+        for (int a = 0, b = NN - 1; a < b; ++a, --b) { const double t = time_nodes[a]; time_nodes[a] = time_nodes[b]; time_nodes[b] = t; }
+        ts = (t_stop - t_start) / (double)(2 * S);
+    }
+    PMB_HD double d_(int i, int j) const { return D[i + j * (P + 1)]; }
+};
+
+/** index of direction a of node k inside var */
+template <class O> PMB_HD int var_index(int k, int a)
+{ return a < O::NX ? k * O::NX + a : (a < O::NX + O::NU ? O::VARX + k * O::NU + (a - O::NX) : O::VARX + O::VARU + (a - O::NX - O::NU)); }
+
+template <class O>
+struct OcpEval {
+    static constexpr int NX = O::NX, NU = O::NU, NP = O::NP, NG = O::NG, P = O::P, S = O::S, NN = O::NN;
+    static constexpr int VARX = O::VARX, VARU = O::VARU, N = O::N, NUM_EQ = O::NUM_EQ, NUM_INEQ = O::NUM_INEQ, M = O::M, NDIR = O::NDIR;
+    using ad1 = typename O::ad1;
+    using ad2 = typename O::ad2;
+
+    /** segment and row of node k for the collocation rows: the later segment owns a junction node */
+    PMB_DEV static void seg_of(int k, int& s, int& i) { s = k / P; if (s > S - 1) s = S - 1; i = k - s * P; }
+
+    /** (D * X_seg)(row of node k): sequential ascending fused chain (continuous_ocp.hpp:747-751) */
+    PMB_DEV static void diff_row(const O& o, const double* var, int k, double* DXk)
+    {
+        int s, i; seg_of(k, s, i);
+        for (int n = 0; n < NX; ++n) {
+            double acc = 0.0;
+            for (int j = 0; j <= P; ++j) acc = dm::fma(o.d_(i, j), var[(s * P + j) * NX + n], acc);
+            DXk[n] = acc;
+        }
+    }
+
+    /** sequential quadrature sum in the reference's loop order; val = this lane's node value. All lanes return the sum. */
+    PMB_DEV static double quadrature_sum(const Warp& w, const O& o, double val, double mayer_val)
+    {
+        double c = 0.0;
+        for (int s = 0; s < S; ++s)
+            for (int k = 0; k <= P; ++k) {
+                const double v = w.shfl(val, s * P + k);
+                c += (o.ts * o.w[k]) * v;
+            }
+        c += w.shfl(mayer_val, 0);
+        return c;
+    }
+
+    /** quadrature coefficients of node k in loop order: c1 always, c2 only for spline junctions */
+    PMB_DEV static void node_coeffs(const O& o, int k, double& c1, double& c2, bool& two)
+    {
+        two = false; c2 = 0.0;
+        if (k == 0) c1 = o.ts * o.w[0];
+        else if (k == NN - 1) c1 = o.ts * o.w[P];
+        else if (k % P == 0) { c1 = o.ts * o.w[P]; c2 = o.ts * o.w[0]; two = true; }
+        else c1 = o.ts * o.w[k % P];
+    }
+
+    template <class T>
+    PMB_DEV static void load_plain(const double* var, int k, T* x, T* u)
+    {
+        for (int i = 0; i < NX; ++i) x[i] = T(var[k * NX + i]);
+        for (int i = 0; i < NU; ++i) u[i] = T(var[VARX + k * NU + i]);
+    }
+    PMB_DEV static void seed1(const double* var, int k, ad1* x, ad1* u)
+    {
+        for (int i = 0; i < NX; ++i) { x[i] = ad1(var[k * NX + i]); x[i].d[i] = 1.0; }
+        for (int i = 0; i < NU; ++i) { u[i] = ad1(var[VARX + k * NU + i]); u[i].d[NX + i] = 1.0; }
+    }
+    /** continuous_ocp.hpp:690-735 */
+    PMB_DEV static void seed2_one(ad2& a, double val, int idx)
+    {
+        a.v = ad1(val); a.v.d[idx] = 1.0;
+        for (int j = 0; j < NDIR; ++j) a.d[j] = ad1(0.0);
+        a.d[idx].v = 1.0;
+    }
+    PMB_DEV static void seed2(const double* var, int k, ad2* x, ad2* u)
+    {
+        for (int i = 0; i < NX; ++i) seed2_one(x[i], var[k * NX + i], i);
+        for (int i = 0; i < NU; ++i) seed2_one(u[i], var[VARX + k * NU + i], NX + i);
+    }
+
+    // ---- a3: cost (continuous_ocp.hpp:1180-1207) -----------------------------------------------------------------
+    PMB_DEV static double cost(const Warp& w, const O& o, const double* var, const double* d)
+    {
+        const int k = w.lane();
+        double ci = 0.0, mv = 0.0;
+        if (k < NN) {
+            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0};
+            load_plain<double>(var, k, x, u);
+            o.model.template lagrange<double>(x, u, p, d, o.time_nodes[k], ci);
+            if (k == 0) o.model.template mayer<double>(x, u, p, d, o.time_nodes[0], mv);
+        }
+        return quadrature_sum(w, o, ci, mv);
+    }
+
+    // ---- a4: equalities (continuous_ocp.hpp:738-766); lane k writes c[k*NX .. k*NX+NX) -----------------------------
+    PMB_DEV static void equalities(const Warp& w, const O& o, const double* var, const double* d, double* c)
+    {
+        const int k = w.lane();
+        if (k < NN) {
+            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, f[NX], DXk[NX];
+            load_plain<double>(var, k, x, u);
+            for (int i = 0; i < NX; ++i) f[i] = 0.0;
+            const double tk = o.time_nodes[k];
+            o.model.template dynamics<double>(x, u, p, d, tk, f);
+            diff_row(o, var, k, DXk);
+            for (int i = 0; i < NX; ++i) c[k * NX + i] = DXk[i] - o.ts * f[i];
+        }
+    }
+
+    // ---- a5: inequalities (continuous_ocp.hpp:769-782) ------------------------------------------------------------
+    PMB_DEV static void inequalities(const Warp& w, const O& o, const double* var, const double* d, double* g)
+    {
+        if (NG == 0) return;
+        const int k = w.lane();
+        if (k < NN) {
+            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, gr[NG > 0 ? NG : 1];
+            load_plain<double>(var, k, x, u);
+            for (int i = 0; i < NG; ++i) gr[i] = 0.0;
+            o.model.template ineq<double>(x, u, p, d, o.time_nodes[k], gr);
+            for (int i = 0; i < NG; ++i) g[k * NG + i] = gr[i];
+        }
+    }
+
+    // ---- a6: constraint linearisation (continuous_ocp.hpp:794-878, 546-575) ----------------------------------------
+    /** writes c[NUM_EQ] (+ g[NUM_INEQ] behind it when NG > 0) and the rows x N Jacobian A (column-major, leading
+     *  dimension ldA; rows = NUM_EQ or M).  A is zero-filled first like the reference (802). */
+    PMB_DEV static void constraints_linearised(const Warp& w, const O& o, const double* var, const double* d, double* c, double* A,
+                                               int ldA, bool with_ineq)
+    {
+        const int lane = w.lane();
+        const int rows = with_ineq ? M : NUM_EQ;
+        for (int j = 0; j < N; ++j)
+            for (int i = lane; i < rows; i += 32) A[i + j * ldA] = 0.0;
+        w.sync();
+        const int k = lane;
+        if (k < NN) {
+            // D (x) I block row of this node
+            if (k < NN - 1) {
+                int s, i; seg_of(k, s, i);
+                const int shift = s * P * NX;
+                for (int j = 0; j <= P; ++j) {
+                    const double dij = o.d_(i, j);
+                    for (int r = 0; r < NX; ++r)
+                        for (int q = 0; q < NX; ++q)
+                            A[(shift + i * NX + r) + (shift + j * NX + q) * ldA] = dij * (r == q ? 1.0 : 0.0);
+                }
+            } else {
+                // last block row = -reverse(first block row) (845-846)
+                const int W = NX * (P + 1);
+                for (int jp = 0; jp <= P; ++jp) {
+                    const double d0 = o.d_(0, P - jp);
+                    for (int r = 0; r < NX; ++r)
+                        for (int q = 0; q < NX; ++q)
+                            A[(VARX - NX + r) + (VARX - W + jp * NX + q) * ldA] = -(d0 * (r == q ? 1.0 : 0.0));
+                }
+            }
+            ad1 x[NX], u[NU > 0 ? NU : 1], p[1], y[NX];
+            seed1(var, k, x, u);
+            for (int i = 0; i < NX; ++i) y[i] = ad1(0.0);
+            const ad1 tk = ad1(o.time_nodes[k]);
+            o.model.template dynamics<ad1>(x, u, p, d, tk, y);
+            double DXk[NX];
+            diff_row(o, var, k, DXk);
+            for (int i = 0; i < NX; ++i) {
+                double cv = -o.ts * y[i].v;
+                cv += DXk[i];
+                c[k * NX + i] = cv;
+            }
+            for (int i = 0; i < NX; ++i) {
+                for (int j = 0; j < NX; ++j) A[(k * NX + i) + (k * NX + j) * ldA] -= o.ts * y[i].d[j];
+                for (int j = 0; j < NU; ++j) A[(k * NX + i) + (VARX + k * NU + j) * ldA] -= o.ts * y[i].d[NX + j];
+            }
+            if (NG > 0 && with_ineq) {
+                ad1 gv[NG > 0 ? NG : 1];
+                for (int i = 0; i < NG; ++i) gv[i] = ad1(0.0);
+                o.model.template ineq<ad1>(x, u, p, d, o.time_nodes[k], gv);
+                for (int i = 0; i < NG; ++i) {
+                    c[NUM_EQ + k * NG + i] = gv[i].v;
+                    const int row = NUM_EQ + k * NG + i;
+                    for (int j = 0; j < NX; ++j) A[row + (k * NX + j) * ldA] = gv[i].d[j];
+                    for (int j = 0; j < NU; ++j) A[row + (VARX + k * NU + j) * ldA] = gv[i].d[NX + j];
+                }
+            }
+        }
+        w.sync();
+    }
+
+    // ---- a7: cost gradient (continuous_ocp.hpp:1209-1249) ----------------------------------------------------------
+    PMB_DEV static double cost_gradient(const Warp& w, const O& o, const double* var, const double* d, double* grad)
+    {
+        const int k = w.lane();
+        double lv = 0.0, mv = 0.0;
+        if (k < NN) {
+            ad1 x[NX], u[NU > 0 ? NU : 1], p[1], L;
+            seed1(var, k, x, u);
+            o.model.template lagrange<ad1>(x, u, p, d, o.time_nodes[k], L);
+            lv = L.v;
+            double c1, c2; bool two;
+            node_coeffs(o, k, c1, c2, two);
+            double g[NDIR];
+            for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.d[i]; if (two) g[i] += c2 * L.d[i]; }
+            if (k == 0) {
+                L = ad1(0.0);
+                o.model.template mayer<ad1>(x, u, p, d, o.time_nodes[0], L);
+                mv = L.v;
+                for (int i = 0; i < NDIR; ++i) g[i] += L.d[i];
+            }
+            for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
+        }
+        return quadrature_sum(w, o, lv, mv);
+    }
+
+    // ---- a8 / a10: cost gradient + Hessian, optionally plus the constraint curvature of the Lagrangian ---------------
+    /** cost_gradient_hessian (1253-1367); with lam != nullptr also adds, per node,
+     *  sum_n (-lam_eq[k*NX+n]*ts) * Hess f_n + sum_n lam_ineq[k*NG+n] * Hess g_n  (2128-2173).  H is N x N, zero-filled first. */
+    PMB_DEV static double cost_gradient_hessian(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
+                                                double* grad, double* H)
+    {
+        const int lane = w.lane();
+        for (int i = lane; i < N * N; i += 32) H[i] = 0.0;
+        w.sync();
+        const int k = lane;
+        double lv = 0.0, mv = 0.0;
+        if (k < NN) {
+            ad2 x[NX], u[NU > 0 ? NU : 1], p[1];
+            double Hl[NDIR * NDIR];   // Hl[r + c*NDIR]
+            double g[NDIR];
+            seed2(var, k, x, u);
+            {
+                ad2 L;
+                o.model.template lagrange<ad2>(x, u, p, d, o.time_nodes[k], L);
+                lv = L.v.v;
+                double c1, c2; bool two;
+                node_coeffs(o, k, c1, c2, two);
+                for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
+                for (int c = 0; c < NDIR; ++c)
+                    for (int r = 0; r < NDIR; ++r) {
+                        double h = 0.0;
+                        h += c1 * L.d[c].d[r];
+                        if (two) h += c2 * L.d[c].d[r];
+                        Hl[r + c * NDIR] = h;
+                    }
+            }
+            if (k == 0) {
+                ad2 Mv(0.0);
+                o.model.template mayer<ad2>(x, u, p, d, o.time_nodes[0], Mv);
+                mv = Mv.v.v;
+                for (int i = 0; i < NDIR; ++i) g[i] += Mv.v.d[i];
+                for (int c = 0; c < NDIR; ++c)
+                    for (int r = 0; r < NDIR; ++r) Hl[r + c * NDIR] += Mv.d[c].d[r];
+            }
+            if (lam != nullptr) {
+                double hes[NDIR * NDIR];
+                for (int i = 0; i < NDIR * NDIR; ++i) hes[i] = 0.0;
+                {
+                    ad2 xdot[NX];
+                    const ad2 tk(o.time_nodes[k]);
+                    o.model.template dynamics<ad2>(x, u, p, d, tk, xdot);
+                    for (int n = 0; n < NX; ++n) {
+                        const double coeff = -lam[n + k * NX] * o.ts;
+                        for (int c = 0; c < NDIR; ++c)
+                            for (int r = 0; r < NDIR; ++r) hes[r + c * NDIR] += coeff * xdot[n].d[c].d[r];
+                    }
+                }
+                if (NG > 0) {
+                    ad2 gv[NG > 0 ? NG : 1];
+                    o.model.template ineq<ad2>(x, u, p, d, o.time_nodes[k], gv);
+                    for (int n = 0; n < NG; ++n) {
+                        const double coeff = lam[n + k * NG + NUM_EQ];
+                        for (int c = 0; c < NDIR; ++c)
+                            for (int r = 0; r < NDIR; ++r) hes[r + c * NDIR] += coeff * gv[n].d[c].d[r];
+                    }
+                }
+                for (int i = 0; i < NDIR * NDIR; ++i) Hl[i] += hes[i];
+            }
+            for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
+            for (int c = 0; c < NDIR; ++c)
+                for (int r = 0; r < NDIR; ++r) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hl[r + c * NDIR];
+        }
+        w.sync();
+        return quadrature_sum(w, o, lv, mv);
+    }
+
+    /** lag_grad = A^T lam_head + cost_grad + lam_box (continuous_ocp.hpp:1970-1974, 2112-2114); A is M x N, ld M */
+    PMB_DEV static void lag_grad_from(const Warp& w, const double* A, const double* lam, const double* cost_grad, double* lag_grad)
+    {
+        for (int j = w.lane(); j < N; j += 32) {
+            double acc = 0.0;
+            const double* col = A + (size_t)j * M;
+            for (int i = 0; i < M; ++i) acc = dm::fma(col[i], lam[i], acc);
+            double v = acc;
+            v += cost_grad[j];
+            v += lam[M + j];
+            lag_grad[j] = v;
+        }
+        w.sync();
+    }
+
+    /** a9: lagrangian_gradient (1957-1975) */
+    PMB_DEV static double lagrangian_gradient(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
+                                              double* lag_grad, double* cost_grad, double* g, double* A)
+    {
+        const double c = cost_gradient(w, o, var, d, cost_grad);
+        constraints_linearised(w, o, var, d, g, A, M, true);
+        lag_grad_from(w, A, lam, cost_grad, lag_grad);
+        return c;
+    }
+    /** a10: lagrangian_gradient_hessian (2097-2174) */
+    PMB_DEV static double lagrangian_gradient_hessian(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
+                                                      double* lag_grad, double* H, double* cost_grad, double* g, double* A)
+    {
+        const double c = cost_gradient_hessian(w, o, var, d, lam, cost_grad, H);
+        constraints_linearised(w, o, var, d, g, A, M, true);
+        lag_grad_from(w, A, lam, cost_grad, lag_grad);
+        return c;
+    }
+};
+
+} // namespace pmb

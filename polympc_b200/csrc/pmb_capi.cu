@@ -6,9 +6,7 @@
 #include "emu_names.h"
 #endif
 #include "../../include/polympc_b200.h"
-#include "pmb_rt.hpp"
-#include "pmb_problems.hpp"
-#include "pmb_kernels.hpp"
+#include "pmb_registry.hpp"
 
 #include <cmath>
 #include <cstring>
@@ -17,70 +15,27 @@
 #include <string>
 #include <vector>
 
-using namespace pmb;
+PMB_DECLARE_PROBLEM(mobile_robot_6x2)
+PMB_DECLARE_PROBLEM(mobile_robot_5x2)
+PMB_DECLARE_PROBLEM(mobile_robot_5x3)
+PMB_DECLARE_PROBLEM(cstr_5x2)
+PMB_DECLARE_PROBLEM(kite_12x1)
+PMB_DECLARE_PROBLEM(kite_4x2)
 
+namespace pmb {
 namespace {
 
 #define PMB_FAIL(code, msg) do { last_error_string() = (msg); return (code); } while (0)
 
-// ---- type-erased problem -----------------------------------------------------------------------------------------
-struct IProblem {
-    pmb_dims_t dims{};
-    int device = 0;
-    virtual ~IProblem() {}
-    virtual void set_params(const double*) = 0;
-    virtual void get_params(double*) const = 0;
-    virtual void set_time_limits(double, double) = 0;
-    virtual void time_nodes(double*) const = 0;
-    virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
-    virtual bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const = 0;
-    virtual bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const = 0;
-};
-
-template <class O>
-struct ProblemImpl : IProblem {
-    O o;
-    ProblemImpl()
-    {
-        o.init();
-        dims.NX = O::NX; dims.NU = O::NU; dims.NP = O::NP; dims.ND = O::ND; dims.NG = O::NG; dims.P = O::P; dims.S = O::S; dims.NN = O::NN;
-        dims.N = O::N; dims.M = O::M; dims.DUAL = O::DUAL; dims.NPARAM = O::Model::NPARAM;
-    }
-    void set_params(const double* v) override { o.model.set_params(v); }
-    void get_params(double* v) const override { o.model.get_params(v); }
-    void set_time_limits(double a, double b) override { o.set_time_limits(a, b); }
-    void time_nodes(double* t) const override { for (int i = 0; i < O::NN; ++i) t[i] = o.time_nodes[i]; }
-    template <int MODE> bool ev(int batch, const OcpIo& io, stream_t s) const { return rt_launch<OcpEvalBody<O, MODE>>(batch, 0, s, o, io); }
-    bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const override
-    {
-        switch (mode) {
-        case OCP_COST: return ev<OCP_COST>(batch, io, s);
-        case OCP_EQ: return ev<OCP_EQ>(batch, io, s);
-        case OCP_INEQ: return ev<OCP_INEQ>(batch, io, s);
-        case OCP_EQ_LIN: return ev<OCP_EQ_LIN>(batch, io, s);
-        case OCP_COST_GRAD: return ev<OCP_COST_GRAD>(batch, io, s);
-        case OCP_COST_GRAD_HESS: return ev<OCP_COST_GRAD_HESS>(batch, io, s);
-        case OCP_LAG_GRAD: return ev<OCP_LAG_GRAD>(batch, io, s);
-        case OCP_LAG_GRAD_HESS: return ev<OCP_LAG_GRAD_HESS>(batch, io, s);
-        }
-        return false;
-    }
-    bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const override
-    { return rt_launch<SqpLineariseBody<O>>(n_active, SqpLineariseBody<O>::SMEM, s, o, ws, first); }
-    bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const override
-    { return rt_launch<SqpStepBody<O>>(n_active, SqpStepBody<O>::SMEM, s, o, ws, st); }
-};
-
 struct Registry { const char* name; IProblem* (*make)(); };
-template <class O> IProblem* mk() { return new ProblemImpl<O>(); }
-#define PMB_REG(NAME, MODEL, P, S) { NAME, &mk<Ocp<MODEL, P, S>> }
+#define PMB_REG(NAME, ID) { NAME, &pmb_make_##ID }
 const Registry g_registry[] = {
-    PMB_REG("mobile_robot_6x2", MobileRobot, 6, 2),   // BASELINE.json configs 1, 2, 5
-    PMB_REG("mobile_robot_5x2", MobileRobot, 5, 2),   // reference CasADi fixture / continuous_ocp_test.cpp
-    PMB_REG("mobile_robot_5x3", MobileRobot, 5, 3),   // reference mpc_wrapper_test.cpp
-    PMB_REG("cstr_5x2", Cstr, 5, 2),                  // reference cstr_control_test.cpp, BASELINE.json config 3
-    PMB_REG("kite_12x1", Kite, 12, 1),                // BASELINE.json config 4 (our model)
-    PMB_REG("kite_4x2", Kite, 4, 2),                  // small kite variant for fast parity tests
+    PMB_REG("mobile_robot_6x2", mobile_robot_6x2),   // BASELINE.json configs 1, 2, 5
+    PMB_REG("mobile_robot_5x2", mobile_robot_5x2),   // reference CasADi fixture / continuous_ocp_test.cpp
+    PMB_REG("mobile_robot_5x3", mobile_robot_5x3),   // reference mpc_wrapper_test.cpp
+    PMB_REG("cstr_5x2", cstr_5x2),                   // reference cstr_control_test.cpp, BASELINE.json config 3
+    PMB_REG("kite_12x1", kite_12x1),                 // BASELINE.json config 4 (our model)
+    PMB_REG("kite_4x2", kite_4x2),                   // small kite variant for fast parity tests
 };
 const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
 const Registry* find_problem(const char* name)
@@ -150,34 +105,36 @@ void qp_defaults(pmb_qp_settings_t* s)
 }
 
 } // namespace
+} // namespace pmb
 
-struct pmb_ocp { IProblem* impl = nullptr; bool owned = true; };
+struct pmb_ocp { pmb::IProblem* impl = nullptr; bool owned = true; };
 
 struct pmb_sqp {
     pmb_ocp ocp;
     int batch = 0, device = 0;
     pmb_sqp_settings_t settings;
     pmb_qp_settings_t qp_settings;
-    stream_t own_stream = nullptr, stream = nullptr;
-    event_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf<double> x, lam, lam_k, H, A, h, al, au, lx, ux, lbx, ubx, lbg, ubg, d, lag_grad, step_prev, p, plam, stats, tr_alpha;
-    DevBuf<pmb_sqp_info_t> info;
-    DevBuf<pmb_qp_info_t> qp_info;
-    DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, active, next_active, next_count;
+    pmb::stream_t own_stream = nullptr, stream = nullptr;
+    pmb::event_t ev0 = nullptr, ev1 = nullptr;
+    pmb::DevBuf<double> x, lam, lam_k, H, A, h, al, au, lx, ux, lbx, ubx, lbg, ubg, d, lag_grad, step_prev, p, plam, stats, tr_alpha;
+    pmb::DevBuf<pmb_sqp_info_t> info;
+    pmb::DevBuf<pmb_qp_info_t> qp_info;
+    pmb::DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, active, next_active, next_count;
     int trace_rows = 0;
     int* h_count = nullptr;   // pinned
     double last_ms = 0;
     long long last_launches = 0;
     ~pmb_sqp()
     {
-        rt_set_device(device);
-        rt_host_free(h_count);
-        rt_event_destroy(ev0); rt_event_destroy(ev1);
-        rt_stream_destroy(own_stream);
+        pmb::rt_set_device(device);
+        pmb::rt_host_free(h_count);
+        pmb::rt_event_destroy(ev0); pmb::rt_event_destroy(ev1);
+        pmb::rt_stream_destroy(own_stream);
         delete ocp.impl;
     }
 };
 
+namespace pmb {
 extern "C" {
 
 const char* pmb_version(void)
@@ -572,3 +529,4 @@ int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream)
 }
 
 } // extern "C"
+} // namespace pmb

@@ -29,7 +29,8 @@ struct Ocp {
     static_assert(NN <= 32, "one warp per instance: at most 32 collocation nodes");
     static_assert(NP == 0, "optimised parameters (NP > 0) are not on the GPU path yet");
     using ad1 = Dual<double, NDIR>;
-    using ad2 = Dual<ad1, NDIR>;
+    using ad2 = Dual<ad1, NDIR>;   // the reference's ad2_scalar_t (full nesting)
+    using ad2d = Dual<ad1, 1>;     // one Hessian column at a time (OcpEval::cost_gradient_hessian)
 
     Model model;
     double D[(P + 1) * (P + 1)];   // column-major
@@ -69,6 +70,7 @@ struct OcpEval {
     static constexpr int VARX = O::VARX, VARU = O::VARU, N = O::N, NUM_EQ = O::NUM_EQ, NUM_INEQ = O::NUM_INEQ, M = O::M, NDIR = O::NDIR;
     using ad1 = typename O::ad1;
     using ad2 = typename O::ad2;
+    using ad2d = typename O::ad2d;
 
     /** segment and row of node k for the collocation rows: the later segment owns a junction node */
     PMB_DEV static void seg_of(int k, int& s, int& i) { s = k / P; if (s > S - 1) s = S - 1; i = k - s * P; }
@@ -118,19 +120,6 @@ struct OcpEval {
         for (int i = 0; i < NX; ++i) { x[i] = ad1(var[k * NX + i]); x[i].d[i] = 1.0; }
         for (int i = 0; i < NU; ++i) { u[i] = ad1(var[VARX + k * NU + i]); u[i].d[NX + i] = 1.0; }
     }
-    /** continuous_ocp.hpp:690-735 */
-    PMB_DEV static void seed2_one(ad2& a, double val, int idx)
-    {
-        a.v = ad1(val); a.v.d[idx] = 1.0;
-        for (int j = 0; j < NDIR; ++j) a.d[j] = ad1(0.0);
-        a.d[idx].v = 1.0;
-    }
-    PMB_DEV static void seed2(const double* var, int k, ad2* x, ad2* u)
-    {
-        for (int i = 0; i < NX; ++i) seed2_one(x[i], var[k * NX + i], i);
-        for (int i = 0; i < NU; ++i) seed2_one(u[i], var[VARX + k * NU + i], NX + i);
-    }
-
     // ---- a3: cost (continuous_ocp.hpp:1180-1207) -----------------------------------------------------------------
     PMB_DEV static double cost(const Warp& w, const O& o, const double* var, const double* d)
     {
@@ -264,71 +253,100 @@ struct OcpEval {
     }
 
     // ---- a8 / a10: cost gradient + Hessian, optionally plus the constraint curvature of the Lagrangian ---------------
+    /** seed node k for ONE outer direction j: value part = first-order dual seeded in all NDIR directions, the single
+     *  outer partial = derivative along direction j (continuous_ocp.hpp:690-735 restricted to one Hessian column). */
+    PMB_DEV static void seed2_dir(const double* var, int k, int j, ad2d* x, ad2d* u)
+    {
+        for (int i = 0; i < NX; ++i) {
+            x[i].v = ad1(var[k * NX + i]); x[i].v.d[i] = 1.0;
+            x[i].d[0] = ad1(0.0); if (j == i) x[i].d[0].v = 1.0;
+        }
+        for (int i = 0; i < NU; ++i) {
+            u[i].v = ad1(var[VARX + k * NU + i]); u[i].v.d[NX + i] = 1.0;
+            u[i].d[0] = ad1(0.0); if (j == NX + i) u[i].d[0].v = 1.0;
+        }
+    }
+
     /** cost_gradient_hessian (1253-1367); with lam != nullptr also adds, per node,
-     *  sum_n (-lam_eq[k*NX+n]*ts) * Hess f_n + sum_n lam_ineq[k*NG+n] * Hess g_n  (2128-2173).  H is N x N, zero-filled first. */
+     *  sum_n (-lam_eq[k*NX+n]*ts) * Hess f_n + sum_n lam_ineq[k*NG+n] * Hess g_n  (2128-2173).  H is N x N, zero-filled first.
+     *
+     *  Mapping: the reference evaluates a nested dual with NDIR outer partials per node.  Every outer partial of a
+     *  nested dual is computed independently of the others, so the warp instead spreads the NN*NDIR (node, Hessian
+     *  column) pairs over its 32 lanes and evaluates the functors on Dual<ad1,1>: identical arithmetic per entry,
+     *  (NX+NU)x less live state per lane, and all lanes busy even when NN < 32. */
     PMB_DEV static double cost_gradient_hessian(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
                                                 double* grad, double* H)
     {
         const int lane = w.lane();
         for (int i = lane; i < N * N; i += 32) H[i] = 0.0;
         w.sync();
-        const int k = lane;
         double lv = 0.0, mv = 0.0;
-        if (k < NN) {
-            ad2 x[NX], u[NU > 0 ? NU : 1], p[1];
-            double Hl[NDIR * NDIR];   // Hl[r + c*NDIR]
-            double g[NDIR];
-            seed2(var, k, x, u);
-            {
-                ad2 L;
-                o.model.template lagrange<ad2>(x, u, p, d, o.time_nodes[k], L);
-                lv = L.v.v;
-                double c1, c2; bool two;
-                node_coeffs(o, k, c1, c2, two);
-                for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
-                for (int c = 0; c < NDIR; ++c)
+        constexpr int ITEMS = NN * NDIR;
+        constexpr int PASSES = (ITEMS + 31) / 32;
+        PMB_NOUNROLL
+        for (int pass = 0; pass < PASSES; ++pass) {
+            const int item = pass * 32 + lane;
+            double lv_item = 0.0, mv_item = 0.0;
+            if (item < ITEMS) {
+                const int k = item / NDIR, c = item - k * NDIR;
+                ad2d x[NX], u[NU > 0 ? NU : 1], p[1];
+                double Hc[NDIR];   // column c of the node's (NDIR x NDIR) block
+                double g[NDIR];
+                seed2_dir(var, k, c, x, u);
+                {
+                    ad2d L;
+                    o.model.template lagrange<ad2d>(x, u, p, d, o.time_nodes[k], L);
+                    lv_item = L.v.v;
+                    double c1, c2; bool two;
+                    node_coeffs(o, k, c1, c2, two);
+                    for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
                     for (int r = 0; r < NDIR; ++r) {
                         double h = 0.0;
-                        h += c1 * L.d[c].d[r];
-                        if (two) h += c2 * L.d[c].d[r];
-                        Hl[r + c * NDIR] = h;
-                    }
-            }
-            if (k == 0) {
-                ad2 Mv(0.0);
-                o.model.template mayer<ad2>(x, u, p, d, o.time_nodes[0], Mv);
-                mv = Mv.v.v;
-                for (int i = 0; i < NDIR; ++i) g[i] += Mv.v.d[i];
-                for (int c = 0; c < NDIR; ++c)
-                    for (int r = 0; r < NDIR; ++r) Hl[r + c * NDIR] += Mv.d[c].d[r];
-            }
-            if (lam != nullptr) {
-                double hes[NDIR * NDIR];
-                for (int i = 0; i < NDIR * NDIR; ++i) hes[i] = 0.0;
-                {
-                    ad2 xdot[NX];
-                    const ad2 tk(o.time_nodes[k]);
-                    o.model.template dynamics<ad2>(x, u, p, d, tk, xdot);
-                    for (int n = 0; n < NX; ++n) {
-                        const double coeff = -lam[n + k * NX] * o.ts;
-                        for (int c = 0; c < NDIR; ++c)
-                            for (int r = 0; r < NDIR; ++r) hes[r + c * NDIR] += coeff * xdot[n].d[c].d[r];
+                        h += c1 * L.d[0].d[r];
+                        if (two) h += c2 * L.d[0].d[r];
+                        Hc[r] = h;
                     }
                 }
-                if (NG > 0) {
-                    ad2 gv[NG > 0 ? NG : 1];
-                    o.model.template ineq<ad2>(x, u, p, d, o.time_nodes[k], gv);
-                    for (int n = 0; n < NG; ++n) {
-                        const double coeff = lam[n + k * NG + NUM_EQ];
-                        for (int c = 0; c < NDIR; ++c)
-                            for (int r = 0; r < NDIR; ++r) hes[r + c * NDIR] += coeff * gv[n].d[c].d[r];
-                    }
+                if (k == 0) {
+                    ad2d Mv(0.0);
+                    o.model.template mayer<ad2d>(x, u, p, d, o.time_nodes[0], Mv);
+                    mv_item = Mv.v.v;
+                    for (int i = 0; i < NDIR; ++i) g[i] += Mv.v.d[i];
+                    for (int r = 0; r < NDIR; ++r) Hc[r] += Mv.d[0].d[r];
                 }
-                for (int i = 0; i < NDIR * NDIR; ++i) Hl[i] += hes[i];
+                if (lam != nullptr) {
+                    double hes[NDIR];
+                    for (int i = 0; i < NDIR; ++i) hes[i] = 0.0;
+                    {
+                        ad2d xdot[NX];
+                        const ad2d tk(o.time_nodes[k]);
+                        o.model.template dynamics<ad2d>(x, u, p, d, tk, xdot);
+                        for (int n = 0; n < NX; ++n) {
+                            const double coeff = -lam[n + k * NX] * o.ts;
+                            for (int r = 0; r < NDIR; ++r) hes[r] += coeff * xdot[n].d[0].d[r];
+                        }
+                    }
+                    if (NG > 0) {
+                        ad2d gv[NG > 0 ? NG : 1];
+                        o.model.template ineq<ad2d>(x, u, p, d, o.time_nodes[k], gv);
+                        for (int n = 0; n < NG; ++n) {
+                            const double coeff = lam[n + k * NG + NUM_EQ];
+                            for (int r = 0; r < NDIR; ++r) hes[r] += coeff * gv[n].d[0].d[r];
+                        }
+                    }
+                    for (int i = 0; i < NDIR; ++i) Hc[i] += hes[i];
+                }
+                if (c == 0) for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
+                for (int r = 0; r < NDIR; ++r) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hc[r];
             }
-            for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
-            for (int c = 0; c < NDIR; ++c)
-                for (int r = 0; r < NDIR; ++r) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hl[r + c * NDIR];
+            // hand node k's Lagrange value to lane k (quadrature_sum expects lane k <-> node k)
+            for (int k = 0; k < NN; ++k) {
+                if ((k * NDIR) / 32 == pass) {
+                    const double v = w.shfl(lv_item, (k * NDIR) & 31);
+                    if (lane == k) lv = v;
+                }
+            }
+            if (pass == 0) mv = w.shfl(mv_item, 0);
         }
         w.sync();
         return quadrature_sum(w, o, lv, mv);

@@ -1,0 +1,66 @@
+// pmb_registry.hpp — type-erased problem interface between the C ABI (pmb_capi.cu) and the per-problem translation
+// units (problems/*.cu).  Each problem class x collocation grid is compiled by nvcc in its own TU (the user functors are
+// templates, so every kernel that touches them is stamped out per problem; separate TUs keep ptxas time bounded and let
+// the build run in parallel).  A TU exports one factory through PMB_DEFINE_PROBLEM.
+#pragma once
+#include "../../include/polympc_b200.h"
+#include "pmb_rt.hpp"
+#include "pmb_problems.hpp"
+#include "pmb_kernels.hpp"
+
+namespace pmb {
+
+struct IProblem {
+    pmb_dims_t dims{};
+    int device = 0;
+    virtual ~IProblem() {}
+    virtual void set_params(const double*) = 0;
+    virtual void get_params(double*) const = 0;
+    virtual void set_time_limits(double, double) = 0;
+    virtual void time_nodes(double*) const = 0;
+    virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
+    virtual bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const = 0;
+    virtual bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const = 0;
+};
+
+template <class O>
+struct ProblemImpl : IProblem {
+    O o;
+    ProblemImpl()
+    {
+        o.init();
+        dims.NX = O::NX; dims.NU = O::NU; dims.NP = O::NP; dims.ND = O::ND; dims.NG = O::NG; dims.P = O::P; dims.S = O::S; dims.NN = O::NN;
+        dims.N = O::N; dims.M = O::M; dims.DUAL = O::DUAL; dims.NPARAM = O::Model::NPARAM;
+    }
+    void set_params(const double* v) override { o.model.set_params(v); }
+    void get_params(double* v) const override { o.model.get_params(v); }
+    void set_time_limits(double a, double b) override { o.set_time_limits(a, b); }
+    void time_nodes(double* t) const override { for (int i = 0; i < O::NN; ++i) t[i] = o.time_nodes[i]; }
+    template <int MODE> bool ev(int batch, const OcpIo& io, stream_t s) const { return rt_launch<OcpEvalBody<O, MODE>>(batch, 0, s, o, io); }
+    bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const override
+    {
+        switch (mode) {
+        case OCP_COST: return ev<OCP_COST>(batch, io, s);
+        case OCP_EQ: return ev<OCP_EQ>(batch, io, s);
+        case OCP_INEQ: return ev<OCP_INEQ>(batch, io, s);
+        case OCP_EQ_LIN: return ev<OCP_EQ_LIN>(batch, io, s);
+        case OCP_COST_GRAD: return ev<OCP_COST_GRAD>(batch, io, s);
+        case OCP_COST_GRAD_HESS: return ev<OCP_COST_GRAD_HESS>(batch, io, s);
+        case OCP_LAG_GRAD: return ev<OCP_LAG_GRAD>(batch, io, s);
+        case OCP_LAG_GRAD_HESS: return ev<OCP_LAG_GRAD_HESS>(batch, io, s);
+        }
+        return false;
+    }
+    bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const override
+    { return rt_launch<SqpLineariseBody<O>>(n_active, SqpLineariseBody<O>::SMEM, s, o, ws, first); }
+    bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const override
+    { return rt_launch<SqpStepBody<O>>(n_active, SqpStepBody<O>::SMEM, s, o, ws, st); }
+};
+
+
+} // namespace pmb
+
+/** defines the factory `pmb::IProblem* pmb_make_<ID>()` for Ocp<MODEL, P, S> */
+#define PMB_DEFINE_PROBLEM(ID, MODEL, P, S) \
+    namespace pmb { IProblem* pmb_make_##ID() { return new ProblemImpl<Ocp<MODEL, P, S>>(); } }
+#define PMB_DECLARE_PROBLEM(ID) namespace pmb { IProblem* pmb_make_##ID(); }

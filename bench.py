@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — SQP iterations/sec (batched) of the collocated-NLP hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mobile_robot|cstr|kite] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm: the reference algorithm on the box's host cores
+
+One "step" = one pmb_sqp_solve() of the whole batch: every instance runs SQPBase::solve to convergence (or max_iter) from
+the same initial guess.  metric = sum over instances of sqp_info.iter / time.
+
+  value : inputs resident in HBM when the timed region starts (bounds, x0 rows, guesses already on the device; the
+          iterates are restored on the device by pmb_sqp_reset_guess) — K solves between two CUDA events.
+  e2e   : the same solves through the C ABI with HOST buffers: every step copies x0 / guesses host->device
+          (pmb_sqp_set_initial_conditions, pmb_sqp_set_primal, pmb_sqp_set_dual) and reads iterates and info back
+          (pmb_sqp_get_primal, pmb_sqp_get_info) inside the timed region.
+  roofline     : the dominant kernel of the step (qp_box_admm), CUDA-event time per launch (pmb_sqp_set_profiling).
+  kkt_kernel   : the materialising KKT kernel of the metric's second half (pmb_kkt_assemble_dev, box_admm.hpp:207-223),
+                 B_KKT = 8 (N^2 + M N + (N+M)^2) bytes per instance, device-resident inputs larger than L2.
+  cpu_baseline : the CPU restatement of the reference algorithm (oracle/, Eigen is not available so the reference itself
+                 cannot be built) on a bounded sample of the same workload, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from polympc_b200 import workloads as W  # noqa: E402
+
+METRIC = "sqp_iterations_per_sec"
+UNIT = "SQP iterations/s"
+DEFAULT_BATCH = {"mobile_robot": 8192, "cstr": 4096, "kite": 1024}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def hbm_peak():
+    p = measured_peaks()
+    if p and p.get("hbm_gbs"):
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args, n_inst: int, offset_seed: int = 0):
+    fn = W.WORKLOADS[args.workload]
+    w = fn(n_inst, sqp_max_iter=args.sqp_max_iter, ls_max_iter=args.ls_max_iter)
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the CPU restatement of the reference algorithm (oracle/), timed on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int):
+    from oracle import pyoracle   # the one place bench.py executes oracle/: as the timed CPU arm
+    orc = pyoracle.load()
+    cores = os.cpu_count() or 1
+    pyoracle.set_num_threads(cores)
+    w = build_workload(args, n_inst)
+    s = orc.sqp(w.name, n_inst)
+    W.configure(s, w)
+    total_it, total_t = 0, 0.0
+    for k in range(warmup + steps):
+        s.reset_guess()
+        t0 = time.perf_counter()
+        s.solve()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            total_it += int(s.info()["iter"].sum()); total_t += dt
+    s.close()
+    return total_it / total_t, total_t / max(steps, 1), cores, total_it
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_inst = args.cpu_sample
+    rate, t_step, cores, _ = cpu_solve_rate(args, n_inst, args.steps, min(args.warmup, 1))
+    sample = f"{n_inst} instances of the {args.workload} workload per step (same seeds/inputs as the GPU arm's first rows), solved to convergence"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, args.batch, max(1, args.gpus)),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of PolyMPC's algorithm (oracle/): Eigen is absent, the reference itself cannot be built"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, batch_per_gpu, n_gpus, cpu=False):
+    sizes = {"mobile_robot": "NX=3,NU=2, Chebyshev order 6 x 2 segments (13 nodes), N=65, M=39",
+             "cstr": "NX=4,NU=2, order 5 x 2 (11 nodes), N=66, M=44",
+             "kite": "NX=13,NU=3, order 12 x 1 (13 nodes), N=208, M=169"}[args.workload]
+    return {"workload": f"{args.workload} OCP batch={batch_per_gpu}{'' if cpu else ' per GPU'} random x0 sweep, fp64, SQP to convergence "
+                        f"(max_iter {args.sqp_max_iter}, line search {args.ls_max_iter}), boxADMM + dense pivoted LDLT",
+            "problem": sizes, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus,
+            "parallelism": "cpu-threads" if cpu else f"instances sharded over {n_gpus} GPU(s), no data-path collective",
+            "l2": "inputs larger than L2 (H + A + state of one batch = %.0f MB)" % (batch_per_gpu * 8 * (65 * 65 + 39 * 65 + 6 * 65) / 1e6)
+            if args.workload == "mobile_robot" else "inputs larger than L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import polympc_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    api = polympc_b200.load()
+    if api.device_count() < 1:
+        raise SystemExit("bench.py: libpolympc_b200 sees no device")
+
+    B = args.batch                                   # per GPU (weak scaling)
+    w_all = build_workload(args, B * world)
+    lo, hi = W.shard_bounds(B * world, world, rank)
+
+    # shared Chebyshev tables: computed on rank 0, broadcast once at init, checked against the local tables (north_star)
+    dims = api.dims(w_all.name)
+    nodes, Dm, wts = api.cheb_tables(dims["P"])
+    tab = torch.tensor(np.concatenate([nodes, Dm.ravel(), wts]), device=dev)
+    if world > 1:
+        ref_tab = tab.clone()
+        dist.broadcast(ref_tab, src=0)
+        assert torch.equal(ref_tab, tab), "Chebyshev tables differ across ranks"
+
+    stream = torch.cuda.Stream(device=dev)     # the engine launches on this stream, the events below are recorded on it
+    torch.cuda.set_stream(stream)
+    s = api.sqp(w_all.name, hi - lo, device=local_rank)
+    s.set_stream(stream.cuda_stream)
+    W.configure(s, w_all, lo, hi)
+    x0 = np.ascontiguousarray(w_all.x0[lo:hi])
+    guess_x = np.zeros(dims["N"]); guess_l = np.zeros(dims["DUAL"])
+    if w_all.x_guess is not None:
+        guess_x[:dims["NX"] * dims["NN"]] = np.tile(w_all.x_guess, dims["NN"])
+    if w_all.u_guess is not None:
+        guess_x[dims["NX"] * dims["NN"]:dims["NX"] * dims["NN"] + dims["NU"] * dims["NN"]] = np.tile(w_all.u_guess, dims["NN"])
+    guess_x_b = np.ascontiguousarray(np.tile(guess_x, (hi - lo, 1)))
+    guess_l_b = np.zeros((hi - lo, dims["DUAL"]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        s.reset_guess(); s.solve()
+    iters_per_solve = int(s.info()["iter"].sum())
+    launches = 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        s.reset_guess()
+        s.solve()
+        launches += s.last_solve_launches()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    total_iters = sum_over_ranks(float(iters_per_solve)) * args.steps
+    value = total_iters / (ms_total * 1e-3)
+    info = s.info()
+    solved_frac = float((info["status"] == 0).mean())
+
+    # ---- end to end through the C ABI with host buffers ("e2e") -----------------------------------------------------------
+    h2d = x0.nbytes * 2 + guess_x_b.nbytes + guess_l_b.nbytes
+    d2h = (hi - lo) * dims["N"] * 8 + (hi - lo) * 12
+    for _ in range(max(1, args.warmup // 2)):
+        s.set_initial_conditions(x0); s.set_primal(guess_x_b); s.set_dual(guess_l_b); s.solve(); s.primal(); s.info()
+    barrier()
+    e0.record(stream)
+    e2e_iters = 0
+    for _ in range(args.steps):
+        s.set_initial_conditions(x0)
+        s.set_primal(guess_x_b)
+        s.set_dual(guess_l_b)
+        s.solve()
+        xs = s.primal()
+        e2e_iters += int(s.info()["iter"].sum())
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = sum_over_ranks(float(e2e_iters)) / (ms_e2e * 1e-3)
+
+    # ---- per-kernel device time (roofline of the dominant kernel) --------------------------------------------------------------
+    s.set_profiling(True)
+    kt = {}
+    for _ in range(2):
+        s.reset_guess(); s.solve()
+        for k, (ms, n) in s.kernel_times().items():
+            a = kt.setdefault(k, [0.0, 0]); a[0] += ms; a[1] += n
+    s.set_profiling(False)
+    qp_info = None
+    N, M = dims["N"], dims["M"]
+    peak, peak_src = hbm_peak()
+    tot_ms = sum(v[0] for v in kt.values())
+    dom = max(kt, key=lambda k: kt[k][0])
+    # algorithmic bytes of one qp_box_admm launch per instance: read H (8N^2), A (8MN), h/Alb/Aub/xlb/xub, write x (N), y (N+M), info
+    qp_bytes_inst = 8 * (N * N + M * N + 3 * N + 2 * M + N + (N + M)) + 40
+    lin_bytes_inst = 8 * (2 * N * N + M * N + 8 * N + 3 * M)     # BFGS update reads+writes H, writes A, vectors
+    step_bytes_inst = 8 * (6 * N + 4 * (N + M))
+    per_inst = {"qp_box_admm": qp_bytes_inst, "sqp_linearise": lin_bytes_inst, "sqp_linesearch_step": step_bytes_inst}[dom]
+    # active instances per launch vary (converged instances leave the batch): bytes per launch = mean active * bytes/instance
+    mean_active = iters_per_solve / max(1, kt[dom][1] // 2)
+    dom_ms = kt[dom][0] / max(1, kt[dom][1])
+    achieved = mean_active * per_inst / (dom_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": dom_ms, "bytes_per_instance": per_inst, "mean_instances_per_launch": mean_active,
+                "kernel_share_of_step": {k: v[0] / tot_ms for k, v in kt.items()},
+                "note": "fused design: K is built, factored and used in shared memory and never written to HBM, so the kernel is "
+                        "fp64-latency bound, not HBM bound; the HBM-bound materialising KKT kernel is reported under kkt_kernel"}
+
+    # ---- the materialising KKT kernel (a17), device-resident, B_KKT bytes per instance ----------------------------------------------
+    kkt = None
+    try:
+        nb = hi - lo
+        H_d = torch.randn(nb, N * N, device=dev, dtype=torch.float64)
+        A_d = torch.randn(nb, M * N, device=dev, dtype=torch.float64)
+        rb_d = torch.rand(nb, N, device=dev, dtype=torch.float64) + 0.1
+        ri_d = torch.rand(nb, M, device=dev, dtype=torch.float64) + 0.1
+        K_d = torch.empty(nb, (N + M) * (N + M), device=dev, dtype=torch.float64)
+        fn = api._fn("kkt_assemble_dev")
+        def kkt_launch():
+            rc = fn(N, M, nb, H_d.data_ptr(), A_d.data_ptr(), rb_d.data_ptr(), ri_d.data_ptr(), 1e-6, K_d.data_ptr(), stream.cuda_stream)
+            assert rc == 0
+        for _ in range(3):
+            kkt_launch()
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record(stream)
+        for _ in range(reps):
+            kkt_launch()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / reps
+        bk = 8 * (N * N + M * N + (N + M) * (N + M))
+        gbs = nb * bk / (kms * 1e-3) / 1e9
+        kkt = {"kernel": "kkt_assemble_dense", "bytes_per_instance": bk, "batch": nb, "avg_launch_ms": kms, "achieved": gbs, "peak": peak,
+               "unit": "GB/s", "frac": gbs / peak, "working_set_mb": nb * bk / 1e6}
+        launches_kkt = reps
+        del H_d, A_d, K_d
+    except Exception as e:   # never let the auxiliary measurement kill the bench line
+        kkt = {"error": str(e)}
+
+    # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, t_step, cores, _ = cpu_solve_rate(args, args.cpu_sample, 1, 0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {args.cpu_sample} instances of the same workload, one solve to convergence ({t_step:.1f} s), all host cores",
+               "note": "CPU restatement of PolyMPC's algorithm (oracle/); Eigen is absent so the reference itself cannot be built"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, B, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kkt_kernel": kkt, "cpu_baseline": cpu,
+            "sqp_iterations_per_step": total_iters / args.steps, "solved_fraction": solved_frac,
+            "mean_sqp_iter_per_instance": iters_per_solve / (hi - lo),
+        }
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mobile_robot", choices=sorted(W.WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU")
+    ap.add_argument("--sqp-max-iter", type=int, default=100)
+    ap.add_argument("--ls-max-iter", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=None, help="instances solved by the CPU arm per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.workload]
+    if args.cpu_sample is None:
+        args.cpu_sample = {"mobile_robot": 2048, "cstr": 1024, "kite": 64}[args.workload]
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

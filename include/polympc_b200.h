@@ -134,6 +134,10 @@ int pmb_qp_solve(int N, int M, int batch,
  * only the lower triangle and the diagonal blocks are written (upper-right block is zero). */
 int pmb_kkt_assemble(int N, int M, int batch, const double* H, const double* A, const double* rho_box,
                      const double* rho_inv, double sigma, double* K);
+/* same operator on DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream): no copies, no
+ * synchronisation — the form a device-resident caller (or a bandwidth measurement) uses */
+int pmb_kkt_assemble_dev(int N, int M, int batch, const double* H_dev, const double* A_dev, const double* rho_box_dev,
+                         const double* rho_inv_dev, double sigma, double* K_dev, void* cuda_stream);
 
 /* a12: BFGS_update (src/solvers/bfgs.hpp:23-52). B[batch*N*N] in/out, s,y[batch*N]; branch[batch]: 0 plain, 1 damped, 2 skipped */
 int pmb_bfgs_update(int N, int batch, double* B, const double* s, const double* y, int* branch);
@@ -157,6 +161,9 @@ int pmb_sqp_set_dual(pmb_sqp_t* s, const double* lam, int stride);              
 /* MPC::initial_conditions(x0) (src/control/mpc_wrapper.hpp:89-99): box equality on the LAST NX entries of the X block.
  * x0_lb/x0_ub[batch*NX] */
 int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const double* x0_ub);
+/* MPC::x_guess()/u_guess()/lam_guess() kept on the device: restores the iterates to the values last given to
+ * pmb_sqp_set_primal / pmb_sqp_set_dual (zeros after create, like the SQPBase ctor) without a host copy */
+int pmb_sqp_reset_guess(pmb_sqp_t* s);
 int pmb_sqp_solve(pmb_sqp_t* s);                                            /* SQPBase::solve(), whole batch */
 int pmb_sqp_get_primal(const pmb_sqp_t* s, double* x);                      /* [batch*N]    */
 int pmb_sqp_get_dual(const pmb_sqp_t* s, double* lam);                      /* [batch*DUAL] */
@@ -170,6 +177,10 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qp_iter, double* alpha,
 /* device time of the last pmb_sqp_solve in milliseconds (CUDA events on the engine's stream) and launches it issued */
 double pmb_sqp_last_solve_ms(const pmb_sqp_t* s);
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s);
+/* per-kernel device time: with profiling on, every launch of pmb_sqp_solve is bracketed by CUDA events on the engine's
+ * stream; ms[3] / launches[3] = {sqp_linearise, qp_box_admm, sqp_linesearch_step} of the last solve */
+int pmb_sqp_set_profiling(pmb_sqp_t* s, int on);
+int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the engine's own stream */
 int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream);
 

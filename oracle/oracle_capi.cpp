@@ -177,6 +177,7 @@ struct pmb_sqp {
     const Registry* reg = nullptr;
     int batch = 0;
     std::vector<std::unique_ptr<ISqpInst>> inst;
+    std::vector<std::vector<double>> x_guess, lam_guess;   // values last given to set_primal / set_dual (reset_guess)
     double last_ms = 0;
 };
 
@@ -415,9 +416,19 @@ int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lb, const double* ub, int s
 int pmb_sqp_set_parameters(pmb_sqp_t* s, const double* d, int stride)
 { if (!s) return PMB_ERR_BAD_ARGUMENT; const int n = s->ocp.impl->dims.ND; return n == 0 ? PMB_OK : set_vec(s, d, stride, n, &ISqpInst::d); }
 int pmb_sqp_set_primal(pmb_sqp_t* s, const double* x, int stride)
-{ if (!s) return PMB_ERR_BAD_ARGUMENT; return set_vec(s, x, stride, s->ocp.impl->dims.N, &ISqpInst::x); }
+{
+    if (!s) return PMB_ERR_BAD_ARGUMENT;
+    const int r = set_vec(s, x, stride, s->ocp.impl->dims.N, &ISqpInst::x);
+    if (r == PMB_OK) { s->x_guess.resize(s->batch); for (int b = 0; b < s->batch; ++b) s->x_guess[b] = s->inst[b]->x(); }
+    return r;
+}
 int pmb_sqp_set_dual(pmb_sqp_t* s, const double* l, int stride)
-{ if (!s) return PMB_ERR_BAD_ARGUMENT; return set_vec(s, l, stride, s->ocp.impl->dims.DUAL, &ISqpInst::lam); }
+{
+    if (!s) return PMB_ERR_BAD_ARGUMENT;
+    const int r = set_vec(s, l, stride, s->ocp.impl->dims.DUAL, &ISqpInst::lam);
+    if (r == PMB_OK) { s->lam_guess.resize(s->batch); for (int b = 0; b < s->batch; ++b) s->lam_guess[b] = s->inst[b]->lam(); }
+    return r;
+}
 int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const double* x0_ub)
 {
     if (!s || !x0_lb || !x0_ub) return PMB_ERR_BAD_ARGUMENT;
@@ -474,5 +485,19 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf
 double pmb_sqp_last_solve_ms(const pmb_sqp_t*) { return 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t*) { return 0; }
 int pmb_sqp_set_stream(pmb_sqp_t*, void*) { return PMB_OK; }
+int pmb_sqp_set_profiling(pmb_sqp_t*, int) { return PMB_OK; }
+int pmb_sqp_get_kernel_times(const pmb_sqp_t*, double* ms, long long* n) { for (int k = 0; k < 3; ++k) { if (ms) ms[k] = 0; if (n) n[k] = 0; } return PMB_OK; }
+int pmb_sqp_reset_guess(pmb_sqp_t* s)
+{
+    if (!s) return PMB_ERR_BAD_ARGUMENT;
+    for (int b = 0; b < s->batch; ++b) {
+        if (!s->x_guess.empty()) s->inst[b]->x() = s->x_guess[b]; else std::fill(s->inst[b]->x().begin(), s->inst[b]->x().end(), 0.0);
+        if (!s->lam_guess.empty()) s->inst[b]->lam() = s->lam_guess[b]; else std::fill(s->inst[b]->lam().begin(), s->inst[b]->lam().end(), 0.0);
+    }
+    return PMB_OK;
+}
+int pmb_kkt_assemble_dev(int N, int M, int batch, const double* H, const double* A, const double* rho_box, const double* rho_inv, double sigma,
+                         double* K, void*)
+{ return pmb_kkt_assemble(N, M, batch, H, A, rho_box, rho_inv, sigma, K); }   /* the oracle's "device" is the host */
 
 } // extern "C"

@@ -56,11 +56,12 @@ ABI_FUNCTIONS = [
     "ocp_create", "ocp_destroy", "ocp_dims", "ocp_set_params", "ocp_get_params", "ocp_set_time_limits", "ocp_time_nodes",
     "ocp_cost", "ocp_equalities", "ocp_inequalities", "ocp_equalities_linearised", "ocp_cost_gradient",
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian",
-    "qp_solve", "kkt_assemble", "bfgs_update",
+    "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
-    "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_solve", "sqp_get_primal", "sqp_get_dual",
-    "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_stream",
+    "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_get_primal", "sqp_get_dual",
+    "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
+    "sqp_get_kernel_times", "sqp_set_stream",
 ]
 
 
@@ -141,6 +142,10 @@ class CApi:
         g("sqp_last_solve_launches").restype = C.c_longlong
         g("sqp_last_solve_launches").argtypes = [C.c_void_p]
         g("sqp_set_stream").argtypes = [C.c_void_p, C.c_void_p]
+        g("sqp_reset_guess").argtypes = [C.c_void_p]
+        g("sqp_set_profiling").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_get_kernel_times").argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
+        g("kkt_assemble_dev").argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_void_p]
         g("qp_default_settings").argtypes = [C.POINTER(QpSettings)]
         g("qp_default_settings").restype = None
         g("sqp_default_settings").argtypes = [C.POINTER(SqpSettings)]
@@ -426,6 +431,19 @@ class Sqp:
 
     def solve(self):
         self.api._chk(self.api._fn("sqp_solve")(self.h), "sqp_solve")
+
+    def reset_guess(self):
+        self.api._chk(self.api._fn("sqp_reset_guess")(self.h), "sqp_reset_guess")
+
+    def set_profiling(self, on: bool):
+        self.api._chk(self.api._fn("sqp_set_profiling")(self.h, int(bool(on))), "sqp_set_profiling")
+
+    def kernel_times(self):
+        """{kernel name: (milliseconds, launches)} of the last solve (profiling must be on)"""
+        ms = np.zeros(3)
+        n = np.zeros(3, dtype=np.int64)
+        self.api._chk(self.api._fn("sqp_get_kernel_times")(self.h, _p(ms), n.ctypes.data_as(C.POINTER(C.c_longlong))), "sqp_get_kernel_times")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("sqp_linearise", "qp_box_admm", "sqp_linesearch_step"))}
 
     def primal(self):
         x = np.zeros((self.batch, self.d["N"]))

@@ -116,6 +116,7 @@ struct pmb_sqp {
     pmb_qp_settings_t qp_settings;
     pmb::stream_t own_stream = nullptr, stream = nullptr;
     pmb::event_t ev0 = nullptr, ev1 = nullptr;
+    pmb::DevBuf<double> x_guess, lam_guess;   // device copies of the initial guess (pmb_sqp_reset_guess)
     pmb::DevBuf<double> x, lam, lam_k, H, A, h, al, au, lx, ux, lbx, ubx, lbg, ubg, d, lag_grad, step_prev, p, plam, stats, tr_alpha;
     pmb::DevBuf<pmb_sqp_info_t> info;
     pmb::DevBuf<pmb_qp_info_t> qp_info;
@@ -124,11 +125,16 @@ struct pmb_sqp {
     int* h_count = nullptr;   // pinned
     double last_ms = 0;
     long long last_launches = 0;
+    bool profiling = false;
+    pmb::event_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double k_ms[3] = {0, 0, 0};
+    long long k_launches[3] = {0, 0, 0};
     ~pmb_sqp()
     {
         pmb::rt_set_device(device);
         pmb::rt_host_free(h_count);
         pmb::rt_event_destroy(ev0); pmb::rt_event_destroy(ev1);
+        for (int i = 0; i < 4; ++i) pmb::rt_event_destroy(pev[i]);
         pmb::rt_stream_destroy(own_stream);
         delete ocp.impl;
     }
@@ -295,6 +301,15 @@ int pmb_kkt_assemble(int N, int M, int batch, const double* H, const double* A, 
     return PMB_OK;
 }
 
+int pmb_kkt_assemble_dev(int N, int M, int batch, const double* H, const double* A, const double* rho_box, const double* rho_inv,
+                         double sigma, double* K, void* cuda_stream)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !A || !rho_box || !rho_inv || !K) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "kkt_assemble_dev: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    return rt_launch<KktDenseBody>(batch, 0, (stream_t)cuda_stream, N, M, H, A, rho_box, rho_inv, sigma, K) ? PMB_OK : PMB_ERR_CUDA;
+}
+
 int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double* y, int* branch)
 {
     if (N <= 0 || batch < 0 || !Bm || !s || !y) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "bfgs_update: bad argument");
@@ -326,7 +341,7 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
     pmb_sqp_default_qp_settings(&s->qp_settings);
     const pmb_dims_t& D = s->ocp.impl->dims;
     const size_t B = batch, N = D.N, M = D.M, DU = D.DUAL, NI = (size_t)D.NG * D.NN, ND = D.ND;
-    bool ok = s->x.resize(B * N) && s->lam.resize(B * DU) && s->lam_k.resize(B * DU) && s->H.resize(B * N * N) && s->A.resize(B * M * N) &&
+    bool ok = s->x.resize(B * N) && s->lam.resize(B * DU) && s->x_guess.resize(B * N) && s->lam_guess.resize(B * DU) && s->lam_k.resize(B * DU) && s->H.resize(B * N * N) && s->A.resize(B * M * N) &&
               s->h.resize(B * N) && s->al.resize(B * M) && s->au.resize(B * M) && s->lx.resize(B * N) && s->ux.resize(B * N) &&
               s->lbx.resize(B * N) && s->ubx.resize(B * N) && s->lbg.resize(B * NI + 1) && s->ubg.resize(B * NI + 1) && s->d.resize(B * ND + 1) &&
               s->lag_grad.resize(B * N) && s->step_prev.resize(B * N) && s->p.resize(B * N) && s->plam.resize(B * DU) && s->stats.resize(B * 4) &&
@@ -341,6 +356,7 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
     const double INF = std::numeric_limits<double>::infinity();
     std::vector<double> lo(B * N, -INF), hi(B * N, INF);
     ok = rt_memset(s->x.p, 0, s->x.bytes(), s->stream) && rt_memset(s->lam.p, 0, s->lam.bytes(), s->stream) &&
+         rt_memset(s->x_guess.p, 0, s->x_guess.bytes(), s->stream) && rt_memset(s->lam_guess.p, 0, s->lam_guess.bytes(), s->stream) &&
          rt_memset(s->d.p, 0, s->d.bytes(), s->stream) && rt_memset(s->stats.p, 0, s->stats.bytes(), s->stream) &&
          rt_memset(s->info.p, 0, s->info.bytes(), s->stream) &&
          rt_h2d(s->lbx.p, lo.data(), B * N * sizeof(double), s->stream) && rt_h2d(s->ubx.p, hi.data(), B * N * sizeof(double), s->stream);
@@ -390,9 +406,28 @@ int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lb, const double* ub, int s
 int pmb_sqp_set_parameters(pmb_sqp_t* s, const double* d, int stride)
 { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->d.p, d, stride, s->ocp.impl->dims.ND); }
 int pmb_sqp_set_primal(pmb_sqp_t* s, const double* x, int stride)
-{ if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->x.p, x, stride, s->ocp.impl->dims.N); }
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    const int r = sqp_set_vec(s, s->x.p, x, stride, s->ocp.impl->dims.N);
+    if (r) return r;
+    return (rt_d2d(s->x_guess.p, s->x.p, (size_t)s->batch * s->ocp.impl->dims.N * sizeof(double), s->stream) && rt_sync(s->stream)) ? PMB_OK : PMB_ERR_CUDA;
+}
 int pmb_sqp_set_dual(pmb_sqp_t* s, const double* l, int stride)
-{ if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); return sqp_set_vec(s, s->lam.p, l, stride, s->ocp.impl->dims.DUAL); }
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    const int r = sqp_set_vec(s, s->lam.p, l, stride, s->ocp.impl->dims.DUAL);
+    if (r) return r;
+    return (rt_d2d(s->lam_guess.p, s->lam.p, (size_t)s->batch * s->ocp.impl->dims.DUAL * sizeof(double), s->stream) && rt_sync(s->stream)) ? PMB_OK : PMB_ERR_CUDA;
+}
+int pmb_sqp_reset_guess(pmb_sqp_t* s)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const pmb_dims_t& D = s->ocp.impl->dims;
+    const bool ok = rt_d2d(s->x.p, s->x_guess.p, (size_t)s->batch * D.N * sizeof(double), s->stream) &&
+                    rt_d2d(s->lam.p, s->lam_guess.p, (size_t)s->batch * D.DUAL * sizeof(double), s->stream);
+    return ok ? PMB_OK : PMB_ERR_CUDA;
+}
 
 /** strided 2-D copy helper for the initial-condition rows: dst[b*N + off + i] = src[b*NX + i] */
 struct ScatterRowsBody {
@@ -463,6 +498,8 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     ws.active = s->active.p; ws.next_active = s->next_active.p; ws.next_count = s->next_count.p;
 
     long long launches = 0;
+    for (int k = 0; k < 3; ++k) { s->k_ms[k] = 0; s->k_launches[k] = 0; }
+    if (s->profiling) for (int k = 0; k < 4; ++k) if (!s->pev[k]) ok = ok && rt_event_create(&s->pev[k]);
     ok = ok && rt_launch<IotaBody>((B + IotaBody::THREADS - 1) / IotaBody::THREADS, 0, st, B, ws.active, ws.info);
     ++launches;
     const IProblem& P = *s->ocp.impl;
@@ -473,13 +510,19 @@ int pmb_sqp_solve(pmb_sqp_t* s)
 
     int n_active = B;
     for (int it = 1; ok && n_active > 0 && it <= s->settings.max_iter; ++it) {
+        const bool prof = s->profiling;
         ok = ok && rt_memset(ws.next_count, 0, sizeof(int), st);
+        if (prof) ok = ok && rt_event_record(s->pev[0], st);
         ok = ok && P.launch_linearise(n_active, ws, it == 1 ? 1 : 0, st);
+        if (prof) ok = ok && rt_event_record(s->pev[1], st);
         ok = ok && launch_qp(n_active, st, s->qp_settings, qb, ws.active);
+        if (prof) ok = ok && rt_event_record(s->pev[2], st);
         ok = ok && P.launch_step(n_active, ws, s->settings, st);
+        if (prof) ok = ok && rt_event_record(s->pev[3], st);
         launches += 3;
         ok = ok && rt_d2h(s->h_count, ws.next_count, sizeof(int), st) && rt_sync(st);
         if (!ok) break;
+        if (prof) for (int k = 0; k < 3; ++k) { s->k_ms[k] += rt_event_ms(s->pev[k], s->pev[k + 1]); s->k_launches[k] += 1; }
         n_active = *s->h_count;
         int* t = ws.active; ws.active = ws.next_active; ws.next_active = t;
     }
@@ -521,6 +564,13 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf
 }
 double pmb_sqp_last_solve_ms(const pmb_sqp_t* s) { return s ? s->last_ms : 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s) { return s ? s->last_launches : 0; }
+int pmb_sqp_set_profiling(pmb_sqp_t* s, int on) { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->profiling = on != 0; return PMB_OK; }
+int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches)
+{
+    if (!s || !ms || !launches) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    for (int k = 0; k < 3; ++k) { ms[k] = s->k_ms[k]; launches[k] = s->k_launches[k]; }
+    return PMB_OK;
+}
 int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream)
 {
     if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");

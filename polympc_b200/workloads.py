@@ -1,0 +1,106 @@
+"""Synthetic workloads of BASELINE.json: problem data and seeded initial-state sweeps.
+
+Host-side product code (numpy only).  Each workload returns everything a batched solver needs; `configure()` applies it to
+any object with the Sqp interface of capi.py (the CUDA engine — or, in tests and the CPU-baseline leg, the oracle).
+Reference setups: tests/control/mpc_wrapper_test.cpp:120-140 (robot), tests/control/cstr_control_test.cpp:137-177 (CSTR);
+the kite is our own model (the reference ships none).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class Workload:
+    name: str                 # registry name of the problem (pmb_problem_name)
+    t0: float
+    tf: float
+    d: np.ndarray | None      # static parameters (ND,) or None
+    u_lb: np.ndarray
+    u_ub: np.ndarray
+    x0: np.ndarray            # (batch, NX) initial states
+    x_guess: np.ndarray | None = None    # (NX,) constant state guess (None: zeros, like the reference SQPBase ctor)
+    u_guess: np.ndarray | None = None
+    sqp_max_iter: int = 100
+    ls_max_iter: int = 100
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def batch(self) -> int:
+        return self.x0.shape[0]
+
+
+def mobile_robot(batch: int, seed: int = 20260117 + 2, grid: str = "6x2", sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
+    rng = np.random.default_rng(seed)
+    x0 = np.column_stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch), rng.uniform(-np.pi / 4, np.pi / 4, batch)])
+    return Workload(f"mobile_robot_{grid}", 0.0, 2.0, np.array([2.0]), np.array([-1.5, -0.75]), np.array([1.5, 0.75]), x0,
+                    sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
+                    meta={"x0": "U([-1,1]^2 x [-pi/4,pi/4])", "seed": seed})
+
+
+def cstr(batch: int, seed: int = 20260117 + 3, sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
+    rng = np.random.default_rng(seed)
+    nominal = np.array([1.0, 0.5, 100.0, 100.0])
+    spread = np.array([0.1, 0.05, 1.0, 1.0])
+    x0 = nominal + rng.uniform(-1, 1, (batch, 4)) * spread
+    return Workload("cstr_5x2", 0.0, 100.0, None, np.array([3.0, -9000.0]), np.array([35.0, 0.0]), x0,
+                    sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
+                    meta={"x0": "(1,0.5,100,100) + U(+-(0.1,0.05,1,1))", "seed": seed})
+
+
+KITE_NOMINAL = np.array([12.0, 0.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, -50.0, 1.0, 0.0, 0.0, 0.0])
+
+
+def kite(batch: int, seed: int = 20260117 + 4, grid: str = "12x1", sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
+    rng = np.random.default_rng(seed)
+    x0 = KITE_NOMINAL * (1.0 + 0.05 * rng.uniform(-1, 1, (batch, 13)))
+    x0[:, [1, 3, 4, 5, 6, 7, 10, 11, 12]] += 0.05 * rng.uniform(-1, 1, (batch, 9))   # entries whose nominal value is 0
+    return Workload(f"kite_{grid}", 0.0, 1.0, np.array([4.0]), np.array([0.0, -0.3, -0.3]), np.array([5.0, 0.3, 0.3]), x0,
+                    x_guess=KITE_NOMINAL, u_guess=np.array([1.5, 0.0, 0.0]),
+                    sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
+                    meta={"x0": "nominal +- 5 %", "seed": seed})
+
+
+WORKLOADS = {"mobile_robot": mobile_robot, "cstr": cstr, "kite": kite}
+
+
+def bounds_x(dims: dict, w: Workload):
+    """Box bounds of the NLP variable [X | U]: states free, controls boxed (MPC::control_bounds, mpc_wrapper.hpp:120-135)."""
+    N, NX, NU, NN = dims["N"], dims["NX"], dims["NU"], dims["NN"]
+    lbx = np.full(N, -np.inf)
+    ubx = np.full(N, np.inf)
+    lbx[NX * NN:NX * NN + NU * NN] = np.tile(w.u_lb, NN)
+    ubx[NX * NN:NX * NN + NU * NN] = np.tile(w.u_ub, NN)
+    return lbx, ubx
+
+
+def configure(solver, w: Workload, lo: int = 0, hi: int | None = None) -> None:
+    """Apply workload rows [lo, hi) to `solver` (an Sqp of capi.py with batch == hi - lo)."""
+    hi = w.batch if hi is None else hi
+    d = solver.d
+    solver.problem.set_time_limits(w.t0, w.tf)
+    st = solver.settings()
+    st.max_iter = w.sqp_max_iter
+    st.line_search_max_iter = w.ls_max_iter
+    solver.set_settings(st)
+    lbx, ubx = bounds_x(d, w)
+    solver.set_bounds_x(lbx, ubx)
+    if d["ND"] > 0:
+        solver.set_parameters(np.asarray(w.d, dtype=np.float64))
+    guess = np.zeros(d["N"])
+    if w.x_guess is not None:
+        guess[:d["NX"] * d["NN"]] = np.tile(w.x_guess, d["NN"])
+    if w.u_guess is not None:
+        guess[d["NX"] * d["NN"]:d["NX"] * d["NN"] + d["NU"] * d["NN"]] = np.tile(w.u_guess, d["NN"])
+    solver.set_primal(guess)
+    solver.set_dual(np.zeros(d["DUAL"]))
+    solver.set_initial_conditions(w.x0[lo:hi])
+
+
+def shard_bounds(batch: int, world_size: int, rank: int):
+    """Contiguous block of ceil(batch / world_size) instances per rank; the last ranks may get less."""
+    per = -(-batch // world_size)
+    lo = min(batch, rank * per)
+    return lo, min(batch, lo + per)

@@ -1,0 +1,160 @@
+"""Parity cases shared by the CPU suite (warp-emulator build of the kernels) and the GPU suite (the CUDA library).
+Every case drives `api` and the oracle `orc` through the same C ABI on the same seeded inputs and demands BIT-EXACT
+equality: integer decisions (pivot permutations, classifications, iteration counts, branches) and fp64 values alike —
+both sides use the same deterministic elementary functions and the same summation orders (oracle/canon.hpp)."""
+import numpy as np
+
+from polympc_b200 import workloads as W
+
+PROBLEM_SETUP = {
+    "mobile_robot_6x2": dict(t=(0.0, 2.0), d=2.0),
+    "mobile_robot_5x2": dict(t=(0.0, 1.0), d=1.0),
+    "mobile_robot_5x3": dict(t=(0.0, 2.0), d=2.0),
+    "cstr_5x2": dict(t=(0.0, 100.0), d=None),
+    "kite_4x2": dict(t=(0.0, 1.0), d=4.0),
+    "kite_12x1": dict(t=(0.0, 1.0), d=4.0),
+}
+
+
+def sample_var(name, dims, B, rng):
+    N, NX, NU, NN = dims["N"], dims["NX"], dims["NU"], dims["NN"]
+    if name.startswith("mobile_robot"):
+        var = rng.uniform(-1.0, 1.0, (B, N))
+    elif name.startswith("cstr"):
+        x = np.array([2.0, 1.0, 110.0, 108.0]) + rng.uniform(-1, 1, (B, NN, NX)) * np.array([0.5, 0.3, 5.0, 5.0])
+        u = np.array([14.0, -1100.0]) + rng.uniform(-1, 1, (B, NN, NU)) * np.array([5.0, 500.0])
+        var = np.concatenate([x.reshape(B, -1), u.reshape(B, -1)], axis=1)
+    else:
+        x = W.KITE_NOMINAL + rng.uniform(-1, 1, (B, NN, NX)) * 0.2
+        u = np.array([1.5, 0.0, 0.0]) + rng.uniform(-1, 1, (B, NN, NU)) * 0.2
+        var = np.concatenate([x.reshape(B, -1), u.reshape(B, -1)], axis=1)
+    return var
+
+
+def assert_same(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, what
+    if a.dtype.kind == "f":
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), f"{what}: {np.count_nonzero(~same)} of {a.size} entries differ, max abs diff {np.nanmax(np.abs(a - b))}"
+    else:
+        assert np.array_equal(a, b), f"{what}: integer arrays differ"
+
+
+def ocp_case(api, orc, name, B=3, seed=0):
+    """a3-a10: every transcription operator"""
+    su = PROBLEM_SETUP[name]
+    rng = np.random.default_rng(seed)
+    oa, ob = api.ocp(name), orc.ocp(name)
+    oa.set_time_limits(*su["t"]); ob.set_time_limits(*su["t"])
+    assert_same(oa.time_nodes(), ob.time_nodes(), "time_nodes")
+    D = oa.d
+    var = sample_var(name, D, B, rng)
+    d = None if su["d"] is None else np.full((B, D["ND"]), su["d"])
+    lam = rng.uniform(-2, 2, (B, D["DUAL"]))
+    assert_same(oa.cost(var, d), ob.cost(var, d), "cost")
+    assert_same(oa.equalities(var, d), ob.equalities(var, d), "equalities")
+    for x, y, n in zip(oa.equalities_linearised(var, d), ob.equalities_linearised(var, d), ("c", "jac")):
+        assert_same(x, y, "equalities_linearised." + n)
+    for x, y, n in zip(oa.cost_gradient(var, d), ob.cost_gradient(var, d), ("cost", "grad")):
+        assert_same(x, y, "cost_gradient." + n)
+    for x, y, n in zip(oa.cost_gradient_hessian(var, d), ob.cost_gradient_hessian(var, d), ("cost", "grad", "hess")):
+        assert_same(x, y, "cost_gradient_hessian." + n)
+    ra, rb = oa.lagrangian_gradient(var, lam, d), ob.lagrangian_gradient(var, lam, d)
+    for k in rb:
+        assert_same(ra[k], rb[k], "lagrangian_gradient." + k)
+    ra, rb = oa.lagrangian_gradient_hessian(var, lam, d), ob.lagrangian_gradient_hessian(var, lam, d)
+    for k in rb:
+        assert_same(ra[k], rb[k], "lagrangian_gradient_hessian." + k)
+    return rb
+
+
+def random_qp(rng, B, N, M, n_eq=None, box=True, loose_rows=0):
+    """strictly convex H, rows of A split into equalities / two-sided inequalities / loose rows; boxes partly infinite"""
+    n_eq = M // 2 if n_eq is None else n_eq
+    G = rng.standard_normal((B, N, N))
+    H = G @ np.transpose(G, (0, 2, 1)) / N + np.eye(N)
+    h = rng.standard_normal((B, N))
+    A = rng.standard_normal((B, M, N))
+    xf = rng.uniform(-0.5, 0.5, (B, N))
+    Ax = np.einsum("bmn,bn->bm", A, xf)
+    Alb = Ax - rng.uniform(0.1, 1.0, (B, M)); Aub = Ax + rng.uniform(0.1, 1.0, (B, M))
+    Alb[:, :n_eq] = Ax[:, :n_eq]; Aub[:, :n_eq] = Ax[:, :n_eq]
+    if loose_rows:
+        Alb[:, M - loose_rows:] = -np.inf; Aub[:, M - loose_rows:] = np.inf
+    if box:
+        xlb = np.where(rng.uniform(size=(B, N)) < 0.5, -0.6, -np.inf); xub = np.where(rng.uniform(size=(B, N)) < 0.5, 0.6, np.inf)
+    else:
+        xlb = np.full((B, N), -np.inf); xub = np.full((B, N), np.inf)
+    return H, h, A, Alb, Aub, xlb, xub
+
+
+def qp_case(api, orc, N, M, B=3, seed=0, settings=None, warm=False, **kw):
+    """a15-a21: boxADMM + pivoted LDLT; iterates, multipliers, active set, classification, pivot order, trip counts"""
+    rng = np.random.default_rng(seed)
+    H, h, A, Alb, Aub, xlb, xub = random_qp(rng, B, N, M, **kw)
+    st = settings if settings is not None else orc.sqp_default_qp_settings()
+    xg = rng.uniform(-0.1, 0.1, (B, N)) if warm else None
+    yg = rng.uniform(-0.1, 0.1, (B, N + M)) if warm else None
+    ra = api.qp_solve(H, h, A, Alb, Aub, xlb, xub, st, x_guess=xg, y_guess=yg)
+    rb = orc.qp_solve(H, h, A, Alb, Aub, xlb, xub, st, x_guess=xg, y_guess=yg)
+    for k in ("perm", "ctype", "n_factor"):
+        assert_same(ra[k], rb[k], "qp." + k)
+    for f in ("status", "iter", "rho_updates"):
+        assert_same(ra["info"][f], rb["info"][f], "qp.info." + f)
+    for f in ("rho_estimate", "res_prim", "res_dual"):
+        assert_same(ra["info"][f], rb["info"][f], "qp.info." + f)
+    for k in ("x", "y", "z", "q"):
+        assert_same(ra[k], rb[k], "qp." + k)
+    # active set: exact equality with the bounds on both sides
+    act_a = np.concatenate([(ra["z"] == Alb) | (ra["z"] == Aub), (ra["q"] == xlb) | (ra["q"] == xub)], axis=1)
+    act_b = np.concatenate([(rb["z"] == Alb) | (rb["z"] == Aub), (rb["q"] == xlb) | (rb["q"] == xub)], axis=1)
+    assert np.array_equal(act_a, act_b)
+    return rb
+
+
+def bfgs_case(api, orc, N, B=4, seed=0):
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((B, N, N))
+    Bm = G @ np.transpose(G, (0, 2, 1)) / N + np.eye(N)
+    s = rng.standard_normal((B, N)); y = rng.standard_normal((B, N))
+    y[0] = np.einsum("ij,j->i", Bm[0], s[0])             # plain branch
+    y[1] = -y[1]                                           # likely damped
+    if B > 2:
+        s[2] = 0.0                                         # skipped (sr < eps)
+    Ba, bra = api.bfgs_update(Bm, s, y)
+    Bb, brb = orc.bfgs_update(Bm, s, y)
+    assert_same(bra, brb, "bfgs.branch")
+    assert_same(Ba, Bb, "bfgs.B")
+    return brb
+
+
+def kkt_case(api, orc, N, M, B=3, seed=0):
+    rng = np.random.default_rng(seed)
+    H = rng.standard_normal((B, N, N)); A = rng.standard_normal((B, M, N))
+    rb = rng.uniform(0.1, 1, (B, N)); ri = rng.uniform(0.1, 1, (B, M))
+    assert_same(api.kkt_assemble(H, A, rb, ri, 1e-6), orc.kkt_assemble(H, A, rb, ri, 1e-6), "kkt")
+
+
+def solve_workload(api, w, lo=0, hi=None):
+    hi = w.batch if hi is None else hi
+    s = api.sqp(w.name, hi - lo)
+    W.configure(s, w, lo, hi)
+    s.solve()
+    out = dict(x=s.primal(), lam=s.dual(), info=s.info(), stats=s.stats(), trace=s.trace(w.sqp_max_iter),
+               ms=s.last_solve_ms(), launches=s.last_solve_launches())
+    s.close()
+    return out
+
+
+def sqp_case(api, orc, w):
+    """a11-a14, a22: whole SQP solves; iterates, multipliers, info and the per-iteration decision trace"""
+    ra, rb = solve_workload(api, w), solve_workload(orc, w)
+    for f in ("iter", "qp_solver_iter", "status"):
+        assert_same(ra["info"][f], rb["info"][f], "sqp.info." + f)
+    for k in ("qp_iter", "bfgs", "ls_trials", "qp_factor", "alpha"):
+        assert_same(ra["trace"][k], rb["trace"][k], "sqp.trace." + k)
+    assert_same(ra["x"], rb["x"], "sqp.x")
+    assert_same(ra["lam"], rb["lam"], "sqp.lam")
+    assert_same(ra["stats"], rb["stats"], "sqp.stats")
+    return ra, rb

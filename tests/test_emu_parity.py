@@ -1,0 +1,52 @@
+"""CPU suite: the product's kernel bodies, compiled by g++ against the lock-step warp emulator (tests/warp_emu, test
+infrastructure), must reproduce the oracle bit for bit.  Small sizes — the emulator context-switches at every warp
+synchronisation.  The same cases run against the real CUDA library in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from polympc_b200 import workloads as W
+
+
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2"])
+def test_ocp_operators(emu, orc, name):
+    pc.ocp_case(emu, orc, name, B=2, seed=1)
+
+
+@pytest.mark.parametrize("N,M", [(1, 0), (2, 1), (5, 5), (12, 7), (33, 20), (40, 31)])
+def test_qp(emu, orc, N, M):
+    pc.qp_case(emu, orc, N, M, B=2, seed=N)
+
+
+def test_qp_warm_start_and_rho_update(emu, orc):
+    st = orc.qp_default_settings()
+    st.max_iter = 200; st.adaptive_rho = 1; st.adaptive_rho_interval = 25; st.check_termination = 10; st.eps_abs = 1e-7; st.eps_rel = 1e-7
+    r = pc.qp_case(emu, orc, 10, 6, B=3, seed=5, settings=st, warm=True, loose_rows=2)
+    assert r["n_factor"].max() >= 2          # the rho re-factorisation path is exercised
+
+
+def test_qp_max_iter_exceeded(emu, orc):
+    st = orc.sqp_default_qp_settings(); st.max_iter = 7
+    r = pc.qp_case(emu, orc, 6, 3, B=2, seed=9, settings=st)
+    assert (r["info"]["iter"] == 8).all() and (r["info"]["status"] == 1).all()     # box_admm.hpp:199-202
+
+
+@pytest.mark.parametrize("N", [2, 31, 65])
+def test_bfgs(emu, orc, N):
+    br = pc.bfgs_case(emu, orc, N)
+    assert br[0] == 0 and br[2] == 2
+
+
+def test_kkt_assemble(emu, orc):
+    pc.kkt_case(emu, orc, 9, 5)
+
+
+def test_sqp_robot(emu, orc):
+    w = W.mobile_robot(2, seed=7, sqp_max_iter=10, ls_max_iter=10)
+    ra, rb = pc.sqp_case(emu, orc, w)
+    assert (rb["info"]["status"] == 0).any()
+
+
+def test_sqp_cstr(emu, orc):
+    w = W.cstr(1, seed=3, sqp_max_iter=4, ls_max_iter=10)
+    pc.sqp_case(emu, orc, w)

@@ -1,0 +1,172 @@
+"""GPU suite: libpolympc_b200.so (sm_100a kernels) through its C ABI vs the CPU oracle, on a real B200.
+
+Bar (BASELINE.json north_star): iterates within 1e-10 rel-inf of the CPU path and bit-exact active-set indices.  Because both
+sides use the same deterministic elementary functions and summation orders we demand more: BIT-EXACT fp64 iterates,
+multipliers and decision traces (tolerance 0).  Full-size runs (batch 8192) additionally check size-independent properties."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from conftest import rel_inf
+from polympc_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+TOL_REL_INF = 1e-10      # the north_star tolerance; the assertions below are stricter (exact)
+
+
+def test_device_present(pmb):
+    assert pmb.device_count() >= 1
+    assert "sm_100a" in pmb.version()
+
+
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1"])
+def test_ocp_operators(pmb, orc, name):
+    pc.ocp_case(pmb, orc, name, B=37, seed=1)
+
+
+def test_ocp_against_casadi_golden(pmb, golden):
+    """the CUDA transcription directly against the reference's CasADi fixtures (no oracle in between)"""
+    o = pmb.ocp("mobile_robot_5x2")
+    o.set_time_limits(0.0, 1.0)
+    x, lam_eq = golden["x"], golden["lam"]
+    B = x.shape[0]
+    d = np.ones((B, 1))
+    lam = np.concatenate([lam_eq, np.zeros((B, 55))], axis=1)
+    r = o.lagrangian_gradient_hessian(x, lam, d)
+    assert np.abs(r["cost"] - golden["cost"][:, 0]).max() <= 2e-14 * max(1.0, np.abs(golden["cost"]).max())
+    assert np.abs(r["cost_grad"] - golden["cost_gradient"]).max() <= 2e-14
+    assert np.abs(r["g"] - golden["constraints"]).max() <= 5e-14
+    assert np.abs(r["jac"] - golden["constraints_jacobian"]).max() <= 5e-13
+    assert np.abs(r["lag_grad"] - golden["lagrangian_gradient"]).max() <= 5e-13
+    assert np.abs(r["hess"] - golden["lagrangian_hessian"]).max() <= 5e-13
+    c, g, H = o.cost_gradient_hessian(x, d)
+    assert np.abs(H - golden["cost_hessian"]).max() <= 2e-14
+
+
+def test_empty_batch(pmb):
+    o = pmb.ocp("mobile_robot_6x2")
+    assert o.cost(np.zeros((0, 65)), np.zeros((0, 1))).shape == (0,)
+    st = pmb.sqp_default_qp_settings()
+    r = pmb.qp_solve(np.zeros((0, 3, 3)), np.zeros((0, 3)), np.zeros((0, 2, 3)), np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((0, 3)),
+                     np.zeros((0, 3)), st)
+    assert r["x"].shape == (0, 3)
+
+
+@pytest.mark.parametrize("N,M", [(1, 0), (2, 1), (5, 5), (12, 7), (33, 20), (40, 31), (65, 39), (66, 44), (100, 92)])
+def test_qp(pmb, orc, N, M):
+    pc.qp_case(pmb, orc, N, M, B=33, seed=N)
+
+
+def test_qp_reference_known_answers(pmb):
+    st = pmb.qp_default_settings(); st.max_iter = 150        # box_admm_test.cpp:15-45
+    r = pmb.qp_solve([[[4, 1], [1, 2]]], [[1, 1]], [[[1, 1]]], [[1]], [[1]], [[0, 0]], [[0.7, 0.7]], st)
+    assert np.allclose(r["x"][0], [0.3, 0.7], rtol=1e-2) and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 150
+    st = pmb.qp_default_settings(); st.max_iter = 200; st.adaptive_rho = 1; st.check_termination = 10   # :266-298
+    r = pmb.qp_solve(np.zeros((1, 1, 1)), [[1.0]], np.zeros((1, 0, 1)), np.zeros((1, 0)), np.zeros((1, 0)), [[-1e6]], [[1e6]], st)
+    assert np.allclose(r["x"][0], [-1e6], rtol=1e-2) and r["info"]["status"][0] == 0
+    st.rho = 2                                                                                           # :300-334
+    r = pmb.qp_solve(-np.ones((1, 1, 1)), [[0.0]], np.zeros((1, 0, 1)), np.zeros((1, 0)), np.zeros((1, 0)), [[-1.0]], [[2.0]], st,
+                     x_guess=[[0.1]], y_guess=[[0.1]])
+    assert np.allclose(r["x"][0], [2.0], rtol=1e-2) and r["info"]["status"][0] == 0
+
+
+def test_qp_warm_start_and_rho_update(pmb, orc):
+    st = orc.qp_default_settings()
+    st.max_iter = 200; st.adaptive_rho = 1; st.adaptive_rho_interval = 25; st.check_termination = 10; st.eps_abs = 1e-7; st.eps_rel = 1e-7
+    r = pc.qp_case(pmb, orc, 30, 16, B=65, seed=5, settings=st, warm=True, loose_rows=2)
+    assert r["n_factor"].max() >= 2
+
+
+def test_qp_max_iter_exceeded(pmb, orc):
+    st = orc.sqp_default_qp_settings(); st.max_iter = 7
+    r = pc.qp_case(pmb, orc, 6, 3, B=5, seed=9, settings=st)
+    assert (r["info"]["iter"] == 8).all() and (r["info"]["status"] == 1).all()
+
+
+@pytest.mark.parametrize("N", [2, 31, 65, 208])
+def test_bfgs(pmb, orc, N):
+    pc.bfgs_case(pmb, orc, N, B=9)
+
+
+@pytest.mark.parametrize("N,M", [(9, 5), (65, 39)])
+def test_kkt_assemble(pmb, orc, N, M):
+    pc.kkt_case(pmb, orc, N, M, B=17)
+
+
+def test_sqp_robot_vs_oracle(pmb, orc):
+    """BASELINE config 2 inputs at a size the oracle finishes in seconds"""
+    from oracle import pyoracle
+    pyoracle.set_num_threads(8)
+    w = W.mobile_robot(256)
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    assert rel_inf(ra["x"], rb["x"]) <= TOL_REL_INF and rel_inf(ra["lam"], rb["lam"]) <= TOL_REL_INF
+    assert (rb["info"]["status"] == 0).mean() > 0.9
+
+
+def test_sqp_robot_reference_test_setup(pmb, orc):
+    """mpc_wrapper_test.cpp:120-166 — x0 = (0.5, 0.5, 0.5), SQP 10/10: SOLVED (:145)"""
+    w = W.mobile_robot(1, grid="5x3", sqp_max_iter=10, ls_max_iter=10)
+    w.x0[:] = [0.5, 0.5, 0.5]
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    assert ra["info"]["status"][0] == 0 and ra["info"]["iter"][0] <= 10
+
+
+def test_sqp_cstr_vs_oracle(pmb, orc):
+    w = W.cstr(128)
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    assert (ra["info"]["status"] == 0).all()          # cstr_control_test.cpp:177 asserts SOLVED
+
+
+def test_sqp_kite_vs_oracle(pmb, orc):
+    w = W.kite(16, grid="4x2", sqp_max_iter=6, ls_max_iter=10)
+    pc.sqp_case(pmb, orc, w)
+    w = W.kite(8, sqp_max_iter=3, ls_max_iter=10)
+    pc.sqp_case(pmb, orc, w)
+
+
+def test_sqp_full_size_properties(pmb, orc):
+    """BASELINE config 2 at full size (batch 8192): properties that need no oracle run of the whole batch"""
+    B = 8192
+    w = W.mobile_robot(B)
+    r = pc.solve_workload(pmb, w)
+    info = r["info"]
+    assert (info["status"] == 0).mean() > 0.95
+    assert info["iter"].min() >= 1 and info["iter"].max() <= 100
+    x = r["x"]
+    assert np.isfinite(x).all() and np.isfinite(r["lam"]).all()
+    # initial condition = box equality on the last state block (mpc_wrapper.hpp:89-93): satisfied to QP tolerance
+    solved = info["status"] == 0
+    assert np.abs(x[solved, 36:39] - w.x0[solved]).max() < 1e-3
+    # control bounds hold up to the ADMM tolerance
+    u = x[:, 39:].reshape(B, 13, 2)
+    assert (np.abs(u[solved, :, 0]).max() <= 1.5 + 1e-3) and (np.abs(u[solved, :, 1]).max() <= 0.75 + 1e-3)
+    # collocation residuals of converged instances: re-evaluated by the independent equalities operator
+    o = pmb.ocp(w.name); o.set_time_limits(w.t0, w.tf)
+    c = o.equalities(x, np.full((B, 1), 2.0))
+    assert np.abs(c[solved]).max() <= 1e-3 + 1e-12       # termination criterion max_viol <= eps_prim (sqp_base.hpp:524-528)
+    # batch-order independence + determinism: a shuffled sub-batch reproduces the same iterates bit for bit
+    idx = np.random.default_rng(0).permutation(B)[:512]
+    w2 = W.mobile_robot(B); w2.x0 = w.x0[idx]
+    r2 = pc.solve_workload(pmb, w2)
+    pc.assert_same(r2["x"], x[idx], "shuffled sub-batch x")
+    pc.assert_same(r2["info"]["iter"], info["iter"][idx], "shuffled sub-batch iter")
+    # and a random sample of the full batch against the oracle
+    sub = idx[:64]
+    w3 = W.mobile_robot(B); w3.x0 = w.x0[sub]
+    rb = pc.solve_workload(orc, w3)
+    pc.assert_same(x[sub], rb["x"], "sample vs oracle x")
+    pc.assert_same(r["lam"][sub], rb["lam"], "sample vs oracle lam")
+
+
+def test_warm_restart_matches_oracle(pmb, orc):
+    """MPC re-solve: a second solve() warm-starts from the kept (x, lam) (mpc_wrapper.hpp / sqp_base.hpp:568-696)"""
+    w = W.mobile_robot(32, sqp_max_iter=3, ls_max_iter=10)
+    outs = []
+    for api in (pmb, orc):
+        s = api.sqp(w.name, 32); W.configure(s, w); s.solve()
+        s.set_initial_conditions(w.x0 + 0.01); s.solve()
+        outs.append((s.primal(), s.dual(), s.info()))
+        s.close()
+    pc.assert_same(outs[0][0], outs[1][0], "x"); pc.assert_same(outs[0][1], outs[1][1], "lam")
+    pc.assert_same(outs[0][2]["iter"], outs[1][2]["iter"], "iter")

@@ -1,0 +1,42 @@
+"""Behavioural pins of the reference's control tests, checked on the oracle."""
+import numpy as np
+
+import parity_cases as pc
+from polympc_b200 import workloads as W
+
+
+def test_robot_mpc_wrapper_setup_solves(orc):
+    """mpc_wrapper_test.cpp:120-166: 5x3 grid, t in [0,2], d=2, x0=(.5,.5,.5), SQP 10/10 -> SOLVED, iter <= max_iter"""
+    w = W.mobile_robot(1, grid="5x3", sqp_max_iter=10, ls_max_iter=10)
+    w.x0[:] = [0.5, 0.5, 0.5]
+    r = pc.solve_workload(orc, w)
+    assert r["info"]["status"][0] == 0 and 1 <= r["info"]["iter"][0] <= 10
+    x = r["x"][0]
+    assert np.abs(x[45:48] - 0.5).max() < 1e-3                 # initial condition on the LAST state block
+    u = x[48:].reshape(16, 2)
+    assert np.abs(u[:, 0]).max() <= 1.5 + 1e-3 and np.abs(u[:, 1]).max() <= 0.75 + 1e-3
+
+
+def test_cstr_setup_solves(orc):
+    """cstr_control_test.cpp:137-177: SQP 20/20 -> SOLVED"""
+    w = W.cstr(1, sqp_max_iter=20, ls_max_iter=20)
+    w.x0[:] = [1.0, 0.5, 100.0, 100.0]
+    r = pc.solve_workload(orc, w)
+    assert r["info"]["status"][0] == 0 and r["info"]["iter"][0] <= 20
+
+
+def test_admm_trip_counts_are_multiples_of_check_interval(orc):
+    w = W.mobile_robot(8, sqp_max_iter=10, ls_max_iter=10)
+    r = pc.solve_workload(orc, w)
+    q = r["trace"]["qp_iter"]
+    done = q[q > 0]
+    assert ((done % 10 == 0) | (done == 101)).all()
+
+
+def test_info_iter_counts_qps(orc):
+    w = W.mobile_robot(4, sqp_max_iter=3, ls_max_iter=10)
+    r = pc.solve_workload(orc, w)
+    assert (r["info"]["iter"] <= 3).all() and (r["info"]["iter"] >= 1).all()
+    n_qp = (r["trace"]["qp_iter"] > 0).sum(axis=1)
+    assert np.array_equal(n_qp, r["info"]["iter"])
+    assert np.array_equal(r["info"]["qp_solver_iter"], np.where(r["trace"]["qp_iter"] > 0, r["trace"]["qp_iter"], 0).sum(axis=1))

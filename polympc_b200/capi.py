@@ -212,8 +212,9 @@ class CApi:
         """H[b,N,N] (numpy [row,col]), h[b,N], A[b,M,N], bounds; returns dict of numpy arrays."""
         H = np.asarray(H, dtype=np.float64)
         B, N = H.shape[0], H.shape[1]
-        A = np.asarray(A, dtype=np.float64).reshape(B, -1, N)
-        M = A.shape[1]
+        A = np.asarray(A, dtype=np.float64)
+        M = A.shape[1] if A.ndim == 3 else (A.size // max(1, B * N))
+        A = A.reshape(B, M, N)
         Hc = np.ascontiguousarray(np.transpose(H, (0, 2, 1)))  # column-major per instance
         Ac = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
         h = _f64(h, (B, N)); Alb = _f64(Alb, (B, M)); Aub = _f64(Aub, (B, M)); xlb = _f64(xlb, (B, N)); xub = _f64(xub, (B, N))

@@ -177,8 +177,10 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qp_iter, double* alpha,
 /* device time of the last pmb_sqp_solve in milliseconds (CUDA events on the engine's stream) and launches it issued */
 double pmb_sqp_last_solve_ms(const pmb_sqp_t* s);
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s);
-/* per-kernel device time: with profiling on, every launch of pmb_sqp_solve is bracketed by CUDA events on the engine's
- * stream; ms[3] / launches[3] = {sqp_linearise, qp_box_admm, sqp_linesearch_step} of the last solve */
+/* phase breakdown of the fused sqp_solve kernel: with profiling on, every CTA accumulates the SM cycles it spends in the
+ * three phases of an SQP iteration; ms[3] = device time of the kernel (CUDA events on the engine's stream) attributed to
+ * {linearise + BFGS, boxADMM QP, line search + step} in proportion to those cycles, launches[3] = number of SQP
+ * iterations executed (all instances) */
 int pmb_sqp_set_profiling(pmb_sqp_t* s, int on);
 int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the engine's own stream */

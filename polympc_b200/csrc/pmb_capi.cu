@@ -73,25 +73,38 @@ struct Staging {
     template <class T> void back(T* host, const T* dev, size_t count) { if (host && dev) ok = rt_d2h(host, dev, count * sizeof(T), s) && ok; }
 };
 
-template <int R> bool launch_qp_r(int grid, size_t smem, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, const int* active)
-{ return rt_launch<QpBody<R>>(grid, smem, s, st, qb, active); }
+constexpr size_t SMEM_CTA_MAX = 227 * 1024;   // B200: opt-in dynamic shared memory per CTA
 
-bool launch_qp(int grid, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, const int* active)
+/** launches the persistent boxADMM kernel over `batch` instances; `queue` is a zeroed device counter */
+template <int R> bool launch_qp_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int batch,
+                                  int* queue, DevBuf<double>& scratch)
+{
+    const size_t base = Cta::SCRATCH_DOUBLES * sizeof(double) + vec_bytes;
+    const bool in_smem = base + fac_doubles * sizeof(double) <= SMEM_CTA_MAX;
+    const size_t smem = in_smem ? base + fac_doubles * sizeof(double) : base;
+    int grid = resident_ctas<QpBody<R>, pmb_qp_settings_t, QpBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
+    if (grid <= 0) { last_error_string() = "qp_box_admm: kernel does not fit on the device"; return false; }
+    if (!in_smem) grid = grid > 2 * 148 ? 2 * 148 : grid;      // keep the global factor slots L2 resident
+    if (grid > batch) grid = batch;
+    FactorStore fs{nullptr, fac_doubles};
+    if (!in_smem) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
+    return rt_launch<QpBody<R>>(grid, smem, s, st, qb, fs, batch, queue);
+}
+
+bool launch_qp(stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int batch, int* queue, DevBuf<double>& scratch)
 {
     const int n = qb.N + qb.M;
     const int R = (n + 31) / 32;
-    const size_t smem = qp_smem_bytes(qb.N, qb.M);
-    if (smem > 227 * 1024) { last_error_string() = "QP too large for the shared-memory LDLT kernel (needs " + std::to_string(smem) + " bytes)"; return false; }
+    const size_t fd = qp_factor_doubles(qb.N, qb.M), vb = qp_vec_bytes(qb.N, qb.M);
+    if (Cta::SCRATCH_DOUBLES * sizeof(double) + vb > SMEM_CTA_MAX) { last_error_string() = "QP vectors do not fit in shared memory"; return false; }
     switch (R) {
-    case 1: return launch_qp_r<1>(grid, smem, s, st, qb, active);
-    case 2: return launch_qp_r<2>(grid, smem, s, st, qb, active);
-    case 3: return launch_qp_r<3>(grid, smem, s, st, qb, active);
-    case 4: return launch_qp_r<4>(grid, smem, s, st, qb, active);
-    case 5: return launch_qp_r<5>(grid, smem, s, st, qb, active);
-    case 6: return launch_qp_r<6>(grid, smem, s, st, qb, active);
+#define PMB_QP_CASE(r) case r: return launch_qp_r<r>(fd, vb, s, st, qb, batch, queue, scratch);
+    PMB_QP_CASE(1) PMB_QP_CASE(2) PMB_QP_CASE(3) PMB_QP_CASE(4) PMB_QP_CASE(5) PMB_QP_CASE(6) PMB_QP_CASE(7) PMB_QP_CASE(8)
+    PMB_QP_CASE(9) PMB_QP_CASE(10) PMB_QP_CASE(11) PMB_QP_CASE(12)
+#undef PMB_QP_CASE
     default: break;
     }
-    last_error_string() = "QP dimension N+M > 192 not instantiated";
+    last_error_string() = "QP dimension N+M > 384 not instantiated";
     return false;
 }
 
@@ -120,21 +133,24 @@ struct pmb_sqp {
     pmb::DevBuf<double> x, lam, lam_k, H, A, h, al, au, lx, ux, lbx, ubx, lbg, ubg, d, lag_grad, step_prev, p, plam, stats, tr_alpha;
     pmb::DevBuf<pmb_sqp_info_t> info;
     pmb::DevBuf<pmb_qp_info_t> qp_info;
-    pmb::DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, active, next_active, next_count;
+    pmb::DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, queue;
+    pmb::DevBuf<double> factor_scratch;
+    int grid = 0;
+    bool factor_in_smem = true;
     int trace_rows = 0;
-    int* h_count = nullptr;   // pinned
     double last_ms = 0;
     long long last_launches = 0;
     bool profiling = false;
-    pmb::event_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+    pmb::event_t kev0 = nullptr, kev1 = nullptr;
+    pmb::DevBuf<unsigned long long> phase;   // per-phase SM cycles of the fused kernel (profiling)
+    double last_kernel_ms = 0;
     double k_ms[3] = {0, 0, 0};
     long long k_launches[3] = {0, 0, 0};
     ~pmb_sqp()
     {
         pmb::rt_set_device(device);
-        pmb::rt_host_free(h_count);
         pmb::rt_event_destroy(ev0); pmb::rt_event_destroy(ev1);
-        for (int i = 0; i < 4; ++i) pmb::rt_event_destroy(pev[i]);
+        pmb::rt_event_destroy(kev0); pmb::rt_event_destroy(kev1);
         pmb::rt_stream_destroy(own_stream);
         delete ocp.impl;
     }
@@ -275,8 +291,10 @@ int pmb_qp_solve(int N, int M, int batch, const double* H, const double* h, cons
     qb.xlb = st.in(xlb, B * N); qb.xub = st.in(xub, B * N); qb.xg = st.in(x_guess, B * N); qb.yg = st.in(y_guess, B * n);
     qb.x = st.out(x, B * N); qb.y = st.out(y, B * n); qb.info = st.out(info, B); qb.z = st.out(z, B * M); qb.q = st.out(q, B * N);
     qb.perm = st.out(perm, B * n); qb.ctype = st.out(ctype, B * n); qb.nfac = st.out(n_factor, B);
-    if (!st.ok) return PMB_ERR_CUDA;
-    if (!launch_qp(batch, st.s, *settings, qb, nullptr)) return PMB_ERR_CUDA;
+    DevBuf<int> queue;
+    DevBuf<double> scratch;
+    if (!st.ok || !queue.resize(1) || !rt_memset(queue.p, 0, sizeof(int), st.s)) return PMB_ERR_CUDA;
+    if (!launch_qp(st.s, *settings, qb, batch, queue.p, scratch)) return PMB_ERR_CUDA;
     st.back(x, qb.x, B * N); st.back(y, qb.y, B * n); st.back(info, qb.info, B); st.back(z, qb.z, B * M); st.back(q, qb.q, B * N);
     st.back(perm, qb.perm, B * n); st.back(ctype, qb.ctype, B * n); st.back(n_factor, qb.nfac, B);
     if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
@@ -321,7 +339,7 @@ int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double*
     const double* ds = st.in(s, B * N); const double* dy = st.in(y, B * N);
     int* dbr = st.out(branch, B);
     if (!st.ok) return PMB_ERR_CUDA;
-    if (!rt_launch<BfgsBody>(batch, 2 * (size_t)N * sizeof(double), st.s, N, dB, ds, dy, dbr)) return PMB_ERR_CUDA;
+    if (!rt_launch<BfgsBody>(batch, BfgsBody::smem_bytes(N), st.s, N, dB, ds, dy, dbr)) return PMB_ERR_CUDA;
     st.back(Bm, (const double*)dB, B * N * N); st.back(branch, (const int*)dbr, B);
     if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
     return PMB_OK;
@@ -345,13 +363,22 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
               s->h.resize(B * N) && s->al.resize(B * M) && s->au.resize(B * M) && s->lx.resize(B * N) && s->ux.resize(B * N) &&
               s->lbx.resize(B * N) && s->ubx.resize(B * N) && s->lbg.resize(B * NI + 1) && s->ubg.resize(B * NI + 1) && s->d.resize(B * ND + 1) &&
               s->lag_grad.resize(B * N) && s->step_prev.resize(B * N) && s->p.resize(B * N) && s->plam.resize(B * DU) && s->stats.resize(B * 4) &&
-              s->info.resize(B) && s->qp_info.resize(B) && s->qp_nfac.resize(B) && s->active.resize(B) && s->next_active.resize(B) &&
-              s->next_count.resize(1);
-    ok = ok && rt_stream_create(&s->own_stream) && rt_event_create(&s->ev0) && rt_event_create(&s->ev1);
+              s->info.resize(B) && s->qp_info.resize(B) && s->qp_nfac.resize(B) && s->queue.resize(1);
+    ok = ok && rt_stream_create(&s->own_stream) && rt_event_create(&s->ev0) && rt_event_create(&s->ev1) && rt_event_create(&s->kev0) &&
+         rt_event_create(&s->kev1);
     if (!ok) return nullptr;
     s->stream = s->own_stream;
-    s->h_count = (int*)rt_host_alloc(sizeof(int));
-    if (!s->h_count) return nullptr;
+    {   // placement of the LDL^T factor and the persistent grid
+        const IProblem& P = *s->ocp.impl;
+        s->factor_in_smem = P.solve_smem_bytes(true) <= SMEM_CTA_MAX;
+        if (P.solve_smem_bytes(s->factor_in_smem) > SMEM_CTA_MAX) { last_error_string() = "sqp_create: problem too large for shared memory"; return nullptr; }
+        int grid = P.solve_resident_ctas(s->factor_in_smem);
+        if (grid <= 0) { last_error_string() = "sqp_create: sqp_solve kernel does not fit on the device"; return nullptr; }
+        if (!s->factor_in_smem) grid = grid > 2 * 148 ? 2 * 148 : grid;
+        if (grid > batch) grid = batch;
+        s->grid = grid;
+        if (!s->factor_in_smem && !s->factor_scratch.resize((size_t)grid * P.factor_doubles())) return nullptr;
+    }
     // SQPBase constructor state (sqp_base.hpp:72-99): x = 0, lam = 0, bounds +-inf
     const double INF = std::numeric_limits<double>::infinity();
     std::vector<double> lo(B * N, -INF), hi(B * N, INF);
@@ -432,6 +459,7 @@ int pmb_sqp_reset_guess(pmb_sqp_t* s)
 /** strided 2-D copy helper for the initial-condition rows: dst[b*N + off + i] = src[b*NX + i] */
 struct ScatterRowsBody {
     static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr const char* NAME = "scatter_rows";
     static constexpr size_t EMU_STACK_BYTES = 128u << 10;
     PMB_DEV static void run(const Warp& w, int blk, unsigned char*, int batch, int len, int ld, int off, const double* src, double* dst)
@@ -458,17 +486,6 @@ int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const doub
     return ok ? PMB_OK : PMB_ERR_CUDA;
 }
 
-struct IotaBody {
-    static constexpr int THREADS = 256;
-    static constexpr const char* NAME = "sqp_init";
-    static constexpr size_t EMU_STACK_BYTES = 128u << 10;
-    PMB_DEV static void run(const Warp& w, int blk, unsigned char*, int n, int* active, pmb_sqp_info_t* info)
-    {
-        const int e = blk * THREADS + w.tid();
-        if (e < n) { active[e] = e; info[e].iter = 1; info[e].qp_solver_iter = 0; info[e].status = PMB_SQP_MAX_ITER_EXCEEDED; }
-    }
-};
-
 int pmb_sqp_solve(pmb_sqp_t* s)
 {
     if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
@@ -482,11 +499,12 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     }
     stream_t st = s->stream;
     bool ok = rt_event_record(s->ev0, st);
+    long long launches = 0;
     {
         const size_t T = (size_t)B * rows;
         ok = ok && rt_memset(s->tr_qp_iter.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_bfgs.p, 0xFF, T * sizeof(int), st) &&
              rt_memset(s->tr_ls.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_qp_factor.p, 0xFF, T * sizeof(int), st) &&
-             rt_memset(s->tr_alpha.p, 0xFF, T * sizeof(double), st);
+             rt_memset(s->tr_alpha.p, 0xFF, T * sizeof(double), st) && rt_memset(s->queue.p, 0, sizeof(int), st);
     }
     SqpWs ws{};
     ws.x = s->x.p; ws.lam = s->lam.p; ws.lam_k = s->lam_k.p; ws.H = s->H.p; ws.A = s->A.p; ws.h = s->h.p; ws.al = s->al.p; ws.au = s->au.p;
@@ -495,41 +513,28 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     ws.info = s->info.p; ws.qp_info = s->qp_info.p; ws.qp_nfac = s->qp_nfac.p;
     ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p;
     ws.trace_rows = rows;
-    ws.active = s->active.p; ws.next_active = s->next_active.p; ws.next_count = s->next_count.p;
-
-    long long launches = 0;
-    for (int k = 0; k < 3; ++k) { s->k_ms[k] = 0; s->k_launches[k] = 0; }
-    if (s->profiling) for (int k = 0; k < 4; ++k) if (!s->pev[k]) ok = ok && rt_event_create(&s->pev[k]);
-    ok = ok && rt_launch<IotaBody>((B + IotaBody::THREADS - 1) / IotaBody::THREADS, 0, st, B, ws.active, ws.info);
-    ++launches;
-    const IProblem& P = *s->ocp.impl;
-    const pmb_dims_t& D = P.dims;
-    QpBatch qb{};
-    qb.N = D.N; qb.M = D.M; qb.H = ws.H; qb.h = ws.h; qb.A = ws.A; qb.Alb = ws.al; qb.Aub = ws.au; qb.xlb = ws.lx; qb.xub = ws.ux;
-    qb.x = ws.p; qb.y = ws.plam; qb.info = ws.qp_info; qb.nfac = ws.qp_nfac;
-
-    int n_active = B;
-    for (int it = 1; ok && n_active > 0 && it <= s->settings.max_iter; ++it) {
-        const bool prof = s->profiling;
-        ok = ok && rt_memset(ws.next_count, 0, sizeof(int), st);
-        if (prof) ok = ok && rt_event_record(s->pev[0], st);
-        ok = ok && P.launch_linearise(n_active, ws, it == 1 ? 1 : 0, st);
-        if (prof) ok = ok && rt_event_record(s->pev[1], st);
-        ok = ok && launch_qp(n_active, st, s->qp_settings, qb, ws.active);
-        if (prof) ok = ok && rt_event_record(s->pev[2], st);
-        ok = ok && P.launch_step(n_active, ws, s->settings, st);
-        if (prof) ok = ok && rt_event_record(s->pev[3], st);
-        launches += 3;
-        ok = ok && rt_d2h(s->h_count, ws.next_count, sizeof(int), st) && rt_sync(st);
-        if (!ok) break;
-        if (prof) for (int k = 0; k < 3; ++k) { s->k_ms[k] += rt_event_ms(s->pev[k], s->pev[k + 1]); s->k_launches[k] += 1; }
-        n_active = *s->h_count;
-        int* t = ws.active; ws.active = ws.next_active; ws.next_active = t;
+    ws.phase = nullptr;
+    if (s->profiling) {
+        ok = ok && s->phase.resize(8) && rt_memset(s->phase.p, 0, 8 * sizeof(unsigned long long), st);
+        ws.phase = s->phase.p;
     }
+    // one persistent launch: CTAs draw instances from the queue and run their whole SQP loop on the device
+    ok = ok && rt_event_record(s->kev0, st);
+    ok = ok && s->ocp.impl->launch_solve(s->grid, s->factor_in_smem, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
+    ok = ok && rt_event_record(s->kev1, st);
+    ++launches;
     ok = ok && rt_event_record(s->ev1, st) && rt_sync(st);
     if (!ok) return PMB_ERR_CUDA;
     s->last_ms = rt_event_ms(s->ev0, s->ev1);
+    s->last_kernel_ms = rt_event_ms(s->kev0, s->kev1);
     s->last_launches = launches;
+    for (int k = 0; k < 3; ++k) { s->k_ms[k] = 0; s->k_launches[k] = 0; }
+    if (s->profiling) {
+        unsigned long long ph[8];
+        if (!(rt_d2h(ph, s->phase.p, sizeof ph, st) && rt_sync(st))) return PMB_ERR_CUDA;
+        const double tot = (double)ph[0] + (double)ph[1] + (double)ph[2];
+        for (int k = 0; k < 3; ++k) { s->k_ms[k] = tot > 0 ? s->last_kernel_ms * (double)ph[k] / tot : 0.0; s->k_launches[k] = (long long)ph[3]; }
+    }
     return PMB_OK;
 }
 

@@ -17,31 +17,35 @@ struct OcpIo {
 
 template <class O, int MODE>
 struct OcpEvalBody {
-    static constexpr int THREADS = 32;
+    static constexpr int THREADS = 64;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr const char* NAME = "ocp_eval";
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
-    PMB_DEV static void run(const Warp& w, int b, unsigned char*, O o, OcpIo io)
+    static constexpr size_t SMEM = (Cta::SCRATCH_DOUBLES + OcpEval<O>::NV_DOUBLES) * sizeof(double);
+    PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, O o, OcpIo io)
     {
         using E = OcpEval<O>;
+        Cta c(w, reinterpret_cast<double*>(smem));
+        double* nv = reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES;
         const double* var = io.var + (size_t)b * O::N;
         const double* d = io.d ? io.d + (size_t)b * O::ND : nullptr;
         const double* lam = io.lam ? io.lam + (size_t)b * O::DUAL : nullptr;
         double cost = 0.0;
-        if (MODE == OCP_COST) cost = E::cost(w, o, var, d);
-        else if (MODE == OCP_EQ) E::equalities(w, o, var, d, io.c + (size_t)b * O::NUM_EQ);
-        else if (MODE == OCP_INEQ) E::inequalities(w, o, var, d, io.g + (size_t)b * O::NUM_INEQ);
+        if (MODE == OCP_COST) cost = E::cost(c, o, var, d);
+        else if (MODE == OCP_EQ) E::equalities(c, o, var, d, io.c + (size_t)b * O::NUM_EQ);
+        else if (MODE == OCP_INEQ) E::inequalities(c, o, var, d, io.g + (size_t)b * O::NUM_INEQ);
         else if (MODE == OCP_EQ_LIN)
-            E::constraints_linearised(w, o, var, d, io.c + (size_t)b * O::NUM_EQ, io.jac + (size_t)b * O::NUM_EQ * O::N, O::NUM_EQ, false);
-        else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(w, o, var, d, io.grad + (size_t)b * O::N);
+            E::constraints_linearised(c, o, var, d, io.c + (size_t)b * O::NUM_EQ, io.jac + (size_t)b * O::NUM_EQ * O::N, O::NUM_EQ, false);
+        else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(c, o, var, d, io.grad + (size_t)b * O::N);
         else if (MODE == OCP_COST_GRAD_HESS)
-            cost = E::cost_gradient_hessian(w, o, var, d, nullptr, io.grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N);
+            cost = E::cost_gradient_hessian(c, o, var, d, nullptr, io.grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N, nv);
         else if (MODE == OCP_LAG_GRAD)
-            cost = E::lagrangian_gradient(w, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.grad + (size_t)b * O::N,
+            cost = E::lagrangian_gradient(c, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.grad + (size_t)b * O::N,
                                           io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N);
         else if (MODE == OCP_LAG_GRAD_HESS)
-            cost = E::lagrangian_gradient_hessian(w, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N,
-                                                  io.grad + (size_t)b * O::N, io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N);
-        if (io.cost && w.lane() == 0 && MODE != OCP_EQ && MODE != OCP_INEQ && MODE != OCP_EQ_LIN) io.cost[b] = cost;
+            cost = E::lagrangian_gradient_hessian(c, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N,
+                                                  io.grad + (size_t)b * O::N, io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N, nv);
+        if (io.cost && c.tid() == 0 && MODE != OCP_EQ && MODE != OCP_INEQ && MODE != OCP_EQ_LIN) io.cost[b] = cost;
     }
 };
 
@@ -69,22 +73,38 @@ PMB_DEV QpArgs qp_instance(const QpBatch& q, int b)
     return a;
 }
 
+/** where the packed factor of a CTA lives: in shared memory when it fits, else in a per-CTA global scratch slot */
+struct FactorStore {
+    double* global;      // grid * factor_doubles (nullptr: shared memory)
+    size_t doubles;      // n (n + 1) / 2
+};
+
+/** persistent CTA-per-instance boxADMM: CTAs draw instances from an atomic queue */
 template <int R>
 struct QpBody {
-    static constexpr int THREADS = 32;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = R <= 4 ? 4 : (R <= 6 ? 2 : 1);
     static constexpr const char* NAME = "qp_box_admm";
     static constexpr size_t EMU_STACK_BYTES = 1u << 20;
-    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, QpBatch qb, const int* active)
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, QpBatch qb, FactorStore fs, int batch, int* queue)
     {
-        const int b = active ? active[blk] : blk;
-        const QpArgs a = qp_instance(qb, b);
-        qp_solve_warp<R>(w, st, a, smem);
+        Cta c(w, reinterpret_cast<double*>(smem));
+        unsigned char* ws = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
+        double* Lp = fs.global ? fs.global + (size_t)blk * fs.doubles : reinterpret_cast<double*>(ws);
+        unsigned char* vec = fs.global ? ws : ws + fs.doubles * sizeof(double);
+        for (;;) {
+            const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
+            if (b >= batch) break;
+            const QpArgs a = qp_instance(qb, b);
+            qp_solve_cta<R>(c, st, a, Lp, vec);
+        }
     }
 };
 
 // ---- a17: KKT assembly, reference layout (dense (N+M)^2, lower part + diagonal blocks written, rest zero) ------------
 struct KktDenseBody {
     static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr const char* NAME = "kkt_assemble_dense";
     static constexpr size_t EMU_STACK_BYTES = 256u << 10;
     PMB_DEV static void run(const Warp& w, int b, unsigned char*, int N, int M, const double* H, const double* A, const double* rho_box,
@@ -109,15 +129,18 @@ struct KktDenseBody {
 
 // ---- BFGS operator (C ABI pmb_bfgs_update) -----------------------------------------------------------------------------
 struct BfgsBody {
-    static constexpr int THREADS = 32;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    static size_t smem_bytes(int N) { return (Cta::SCRATCH_DOUBLES + 2 * (size_t)N) * sizeof(double); }
     static constexpr const char* NAME = "bfgs_update";
     static constexpr size_t EMU_STACK_BYTES = 256u << 10;
     PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, int N, double* B, const double* s, const double* y, int* branch)
     {
-        double* Bs = reinterpret_cast<double*>(smem);
+        Cta c(w, reinterpret_cast<double*>(smem));
+        double* Bs = reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES;
         double* r = Bs + N;
-        const int br = bfgs_update_warp(w, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
-        if (branch && w.lane() == 0) branch[b] = br;
+        const int br = bfgs_update_cta(c, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
+        if (branch && c.tid() == 0) branch[b] = br;
     }
 };
 
@@ -130,7 +153,7 @@ struct SqpWs {
     int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
     double* tr_alpha;
     int trace_rows;
-    int *active, *next_active, *next_count;
+    unsigned long long* phase;   // profiling: {linearise, qp, step} cycles of thread 0 summed over CTAs, [3] = instance-iterations
 };
 
 template <class O>
@@ -147,43 +170,53 @@ PMB_DEV SqpInst sqp_instance(const SqpWs& ws, int b)
     s.tr_qp_iter = ws.tr_qp_iter ? ws.tr_qp_iter + b * T : nullptr; s.tr_bfgs = ws.tr_bfgs ? ws.tr_bfgs + b * T : nullptr;
     s.tr_ls = ws.tr_ls ? ws.tr_ls + b * T : nullptr; s.tr_qp_factor = ws.tr_qp_factor ? ws.tr_qp_factor + b * T : nullptr;
     s.tr_alpha = ws.tr_alpha ? ws.tr_alpha + b * T : nullptr;
+    s.phase = ws.phase;
     return s;
 }
 
+/** the whole SQPBase::solve of the batch in ONE persistent launch: each CTA draws an instance from the atomic queue and
+ *  iterates linearise -> boxADMM -> line search / step on it until it converges (no host round trip per iteration, no
+ *  wave quantisation: a slow instance only occupies its own CTA). */
 template <class O>
-struct SqpLineariseBody {
-    static constexpr int THREADS = 32;
-    static constexpr const char* NAME = "sqp_linearise";
+struct SqpSolveBody {
+    static constexpr int THREADS = 128;
+    static constexpr const char* NAME = "sqp_solve";
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
-    static constexpr size_t SMEM = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
-    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, int first)
+    static constexpr int R = (O::N + O::M + 31) / 32;
+    static constexpr size_t FACTOR_DOUBLES = (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
+    static constexpr size_t SCRATCH_BYTES = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
+    /** resident CTAs per SM the register allocation is asked to allow: what shared memory permits when the factor lives
+     *  there (mobile robot: 4 x 55 KB), 2 when the factor is in global scratch (large problems, heavy AD code) */
+    static constexpr size_t SMEM_IN = Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
+                                      (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
+    static constexpr int MIN_BLOCKS = SMEM_IN > 227 * 1024 ? 2 : ((228 * 1024) / SMEM_IN > 4 ? 4 : (int)((228 * 1024) / SMEM_IN));
+    /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors      (factor in shared memory)
+     *                 Cta scratch | SQP scratch | QP vectors                              (factor in global scratch) */
+    static size_t smem_bytes(bool factor_in_smem)
     {
-        const int b = ws.active[blk];
-        const SqpInst s = sqp_instance<O>(ws, b);
-        const int row = s.info->iter - 1;
-        SqpDev<O>::linearise(w, o, s, first != 0, row, reinterpret_cast<double*>(smem));
+        const size_t fac = FACTOR_DOUBLES * sizeof(double);
+        const size_t first = factor_in_smem ? (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES) : SCRATCH_BYTES;
+        return Cta::SCRATCH_DOUBLES * sizeof(double) + first + qp_vec_bytes(O::N, O::M);
     }
-};
-
-template <class O>
-struct SqpStepBody {
-    static constexpr int THREADS = 32;
-    static constexpr const char* NAME = "sqp_linesearch_step";
-    static constexpr size_t EMU_STACK_BYTES = 4u << 20;
-    static constexpr size_t SMEM = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
-    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st)
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st, pmb_qp_settings_t qst,
+                            FactorStore fs, int batch, int* queue)
     {
-        const int b = ws.active[blk];
-        const SqpInst s = sqp_instance<O>(ws, b);
-        const int row = s.info->iter - 1;
-        const bool done = SqpDev<O>::step(w, o, s, st, row, reinterpret_cast<double*>(smem));
-        if (w.lane() == 0) {
-            if (done) s.info->status = PMB_SQP_SOLVED;
-            else if (s.info->iter < st.max_iter) {
-                s.info->iter += 1;
-                const int slot = atomic_add(ws.next_count, 1);
-                ws.next_active[slot] = b;
-            }
+        Cta c(w, reinterpret_cast<double*>(smem));
+        unsigned char* base = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
+        double* scratch = reinterpret_cast<double*>(base);
+        double* Lp;
+        unsigned char* vec;
+        if (fs.global) { Lp = fs.global + (size_t)blk * fs.doubles; vec = base + SCRATCH_BYTES; }
+        else {
+            Lp = reinterpret_cast<double*>(base);
+            const size_t fac = FACTOR_DOUBLES * sizeof(double);
+            vec = base + (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES);
+        }
+        for (;;) {
+            const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
+            if (b >= batch) break;
+            const SqpInst s = sqp_instance<O>(ws, b);
+            SqpDev<O>::template solve<R>(c, o, s, st, qst, Lp, vec, scratch);
         }
     }
 };

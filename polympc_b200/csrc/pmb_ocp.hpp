@@ -7,12 +7,14 @@
 // Layout: var = [X (NX*NN) | U (NU*NN) | P (NP)], node k at k*NX / VARX + k*NU; node 0 is the FINAL time (time nodes
 // descend); lam = [lam_eq | lam_ineq | lam_box].  Matrices are column-major.
 //
-// Mapping: every node's functor evaluation (plain, first-order dual, second-order dual) is independent, so lane k owns
-// node k: its NX collocation rows of the Jacobian, its gradient entries and its (NX+NU)^2 diagonal Hessian block.
-// Junction nodes of the spline are counted twice in the quadrature, in segment order, exactly like the reference loop.
-// The only cross-lane steps are the cost sum (a fixed sequential order, done with shuffles) and the A^T*lam product.
+// Mapping: every node's functor evaluation (plain, first-order dual, second-order dual) is independent, so thread k of the
+// CTA owns node k (NN <= 32: they all sit in warp 0): its NX collocation rows of the Jacobian and its gradient entries;
+// Hessian columns are spread over all threads as (node, column) work items.  Zero fills, A^T*lam and other element-wise
+// work are strided over the whole block.  Junction nodes of the spline are counted twice in the quadrature, in segment
+// order, exactly like the reference loop; the cost sum keeps that fixed sequential order (shuffles inside warp 0) and is
+// then broadcast, so every routine returns its scalar in every thread.
 #pragma once
-#include "pmb_warp.hpp"
+#include "pmb_cta.hpp"
 #include "pmb_dual.hpp"
 #include "pmb_cheb.hpp"
 
@@ -86,17 +88,20 @@ struct OcpEval {
         }
     }
 
-    /** sequential quadrature sum in the reference's loop order; val = this lane's node value. All lanes return the sum. */
-    PMB_DEV static double quadrature_sum(const Warp& w, const O& o, double val, double mayer_val)
+    /** sequential quadrature sum in the reference's loop order; val = thread k's node value (k < NN, warp 0).  Every thread
+     *  of the block returns the sum. */
+    PMB_DEV static double quadrature_sum(Cta& c, const O& o, double val, double mayer_val)
     {
-        double c = 0.0;
-        for (int s = 0; s < S; ++s)
-            for (int k = 0; k <= P; ++k) {
-                const double v = w.shfl(val, s * P + k);
-                c += (o.ts * o.w[k]) * v;
-            }
-        c += w.shfl(mayer_val, 0);
-        return c;
+        double acc = 0.0;
+        if (c.warp_id() == 0) {
+            for (int s = 0; s < S; ++s)
+                for (int k = 0; k <= P; ++k) {
+                    const double v = c.w.shfl(val, s * P + k);
+                    acc += (o.ts * o.w[k]) * v;
+                }
+            acc += c.w.shfl(mayer_val, 0);
+        }
+        return c.bcast(acc, 0);
     }
 
     /** quadrature coefficients of node k in loop order: c1 always, c2 only for spline junctions */
@@ -121,9 +126,9 @@ struct OcpEval {
         for (int i = 0; i < NU; ++i) { u[i] = ad1(var[VARX + k * NU + i]); u[i].d[NX + i] = 1.0; }
     }
     // ---- a3: cost (continuous_ocp.hpp:1180-1207) -----------------------------------------------------------------
-    PMB_DEV static double cost(const Warp& w, const O& o, const double* var, const double* d)
+    PMB_DEV static double cost(Cta& c, const O& o, const double* var, const double* d)
     {
-        const int k = w.lane();
+        const int k = c.tid();
         double ci = 0.0, mv = 0.0;
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0};
@@ -131,13 +136,13 @@ struct OcpEval {
             o.model.template lagrange<double>(x, u, p, d, o.time_nodes[k], ci);
             if (k == 0) o.model.template mayer<double>(x, u, p, d, o.time_nodes[0], mv);
         }
-        return quadrature_sum(w, o, ci, mv);
+        return quadrature_sum(c, o, ci, mv);
     }
 
     // ---- a4: equalities (continuous_ocp.hpp:738-766); lane k writes c[k*NX .. k*NX+NX) -----------------------------
-    PMB_DEV static void equalities(const Warp& w, const O& o, const double* var, const double* d, double* c)
+    PMB_DEV static void equalities(Cta& c, const O& o, const double* var, const double* d, double* ce)
     {
-        const int k = w.lane();
+        const int k = c.tid();
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, f[NX], DXk[NX];
             load_plain<double>(var, k, x, u);
@@ -145,15 +150,15 @@ struct OcpEval {
             const double tk = o.time_nodes[k];
             o.model.template dynamics<double>(x, u, p, d, tk, f);
             diff_row(o, var, k, DXk);
-            for (int i = 0; i < NX; ++i) c[k * NX + i] = DXk[i] - o.ts * f[i];
+            for (int i = 0; i < NX; ++i) ce[k * NX + i] = DXk[i] - o.ts * f[i];
         }
     }
 
     // ---- a5: inequalities (continuous_ocp.hpp:769-782) ------------------------------------------------------------
-    PMB_DEV static void inequalities(const Warp& w, const O& o, const double* var, const double* d, double* g)
+    PMB_DEV static void inequalities(Cta& c, const O& o, const double* var, const double* d, double* g)
     {
         if (NG == 0) return;
-        const int k = w.lane();
+        const int k = c.tid();
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, gr[NG > 0 ? NG : 1];
             load_plain<double>(var, k, x, u);
@@ -166,15 +171,14 @@ struct OcpEval {
     // ---- a6: constraint linearisation (continuous_ocp.hpp:794-878, 546-575) ----------------------------------------
     /** writes c[NUM_EQ] (+ g[NUM_INEQ] behind it when NG > 0) and the rows x N Jacobian A (column-major, leading
      *  dimension ldA; rows = NUM_EQ or M).  A is zero-filled first like the reference (802). */
-    PMB_DEV static void constraints_linearised(const Warp& w, const O& o, const double* var, const double* d, double* c, double* A,
+    PMB_DEV static void constraints_linearised(Cta& cta, const O& o, const double* var, const double* d, double* c, double* A,
                                                int ldA, bool with_ineq)
     {
-        const int lane = w.lane();
         const int rows = with_ineq ? M : NUM_EQ;
-        for (int j = 0; j < N; ++j)
-            for (int i = lane; i < rows; i += 32) A[i + j * ldA] = 0.0;
-        w.sync();
-        const int k = lane;
+        if (rows == ldA) { for (int e = cta.tid(); e < rows * N; e += cta.nthreads()) A[e] = 0.0; }
+        else { for (int e = cta.tid(); e < rows * N; e += cta.nthreads()) { const int j = e / rows; A[(e - j * rows) + j * ldA] = 0.0; } }
+        cta.sync();
+        const int k = cta.tid();
         if (k < NN) {
             // D (x) I block row of this node
             if (k < NN - 1) {
@@ -224,13 +228,13 @@ struct OcpEval {
                 }
             }
         }
-        w.sync();
+        cta.sync();
     }
 
     // ---- a7: cost gradient (continuous_ocp.hpp:1209-1249) ----------------------------------------------------------
-    PMB_DEV static double cost_gradient(const Warp& w, const O& o, const double* var, const double* d, double* grad)
+    PMB_DEV static double cost_gradient(Cta& c, const O& o, const double* var, const double* d, double* grad)
     {
-        const int k = w.lane();
+        const int k = c.tid();
         double lv = 0.0, mv = 0.0;
         if (k < NN) {
             ad1 x[NX], u[NU > 0 ? NU : 1], p[1], L;
@@ -249,7 +253,7 @@ struct OcpEval {
             }
             for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
         }
-        return quadrature_sum(w, o, lv, mv);
+        return quadrature_sum(c, o, lv, mv);
     }
 
     // ---- a8 / a10: cost gradient + Hessian, optionally plus the constraint curvature of the Lagrangian ---------------
@@ -271,23 +275,19 @@ struct OcpEval {
      *  sum_n (-lam_eq[k*NX+n]*ts) * Hess f_n + sum_n lam_ineq[k*NG+n] * Hess g_n  (2128-2173).  H is N x N, zero-filled first.
      *
      *  Mapping: the reference evaluates a nested dual with NDIR outer partials per node.  Every outer partial of a
-     *  nested dual is computed independently of the others, so the warp instead spreads the NN*NDIR (node, Hessian
-     *  column) pairs over its 32 lanes and evaluates the functors on Dual<ad1,1>: identical arithmetic per entry,
-     *  (NX+NU)x less live state per lane, and all lanes busy even when NN < 32. */
-    PMB_DEV static double cost_gradient_hessian(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
-                                                double* grad, double* H)
+     *  nested dual is computed independently of the others, so the CTA instead spreads the NN*NDIR (node, Hessian
+     *  column) pairs over all its threads and evaluates the functors on Dual<ad1,1>: identical arithmetic per entry,
+     *  (NX+NU)x less live state per thread, and every thread busy even when NN < 32. */
+    PMB_DEV static double cost_gradient_hessian(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
+                                                double* grad, double* H, double* nv /* shared scratch, NV_DOUBLES */)
     {
-        const int lane = w.lane();
-        for (int i = lane; i < N * N; i += 32) H[i] = 0.0;
-        w.sync();
-        double lv = 0.0, mv = 0.0;
+        const int tid = cta.tid(), nt = cta.nthreads();
+        for (int i = tid; i < N * N; i += nt) H[i] = 0.0;
+        cta.sync();
         constexpr int ITEMS = NN * NDIR;
-        constexpr int PASSES = (ITEMS + 31) / 32;
         PMB_NOUNROLL
-        for (int pass = 0; pass < PASSES; ++pass) {
-            const int item = pass * 32 + lane;
-            double lv_item = 0.0, mv_item = 0.0;
-            if (item < ITEMS) {
+        for (int item = tid; item < ITEMS; item += nt) {
+            {   // one (node k, Hessian column c) work item
                 const int k = item / NDIR, c = item - k * NDIR;
                 ad2d x[NX], u[NU > 0 ? NU : 1], p[1];
                 double Hc[NDIR];   // column c of the node's (NDIR x NDIR) block
@@ -296,7 +296,7 @@ struct OcpEval {
                 {
                     ad2d L;
                     o.model.template lagrange<ad2d>(x, u, p, d, o.time_nodes[k], L);
-                    lv_item = L.v.v;
+                    if (c == 0) nv[k] = L.v.v;
                     double c1, c2; bool two;
                     node_coeffs(o, k, c1, c2, two);
                     for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
@@ -310,7 +310,7 @@ struct OcpEval {
                 if (k == 0) {
                     ad2d Mv(0.0);
                     o.model.template mayer<ad2d>(x, u, p, d, o.time_nodes[0], Mv);
-                    mv_item = Mv.v.v;
+                    if (c == 0) nv[NN] = Mv.v.v;
                     for (int i = 0; i < NDIR; ++i) g[i] += Mv.v.d[i];
                     for (int r = 0; r < NDIR; ++r) Hc[r] += Mv.d[0].d[r];
                 }
@@ -339,23 +339,19 @@ struct OcpEval {
                 if (c == 0) for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
                 for (int r = 0; r < NDIR; ++r) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hc[r];
             }
-            // hand node k's Lagrange value to lane k (quadrature_sum expects lane k <-> node k)
-            for (int k = 0; k < NN; ++k) {
-                if ((k * NDIR) / 32 == pass) {
-                    const double v = w.shfl(lv_item, (k * NDIR) & 31);
-                    if (lane == k) lv = v;
-                }
-            }
-            if (pass == 0) mv = w.shfl(mv_item, 0);
         }
-        w.sync();
-        return quadrature_sum(w, o, lv, mv);
+        cta.sync();
+        // node values -> thread k (quadrature_sum expects thread k <-> node k)
+        const double lv = tid < NN ? nv[tid] : 0.0;
+        const double mv = tid == 0 ? nv[NN] : 0.0;
+        return quadrature_sum(cta, o, lv, mv);
     }
+    static constexpr int NV_DOUBLES = NN + 1;
 
     /** lag_grad = A^T lam_head + cost_grad + lam_box (continuous_ocp.hpp:1970-1974, 2112-2114); A is M x N, ld M */
-    PMB_DEV static void lag_grad_from(const Warp& w, const double* A, const double* lam, const double* cost_grad, double* lag_grad)
+    PMB_DEV static void lag_grad_from(Cta& c, const double* A, const double* lam, const double* cost_grad, double* lag_grad)
     {
-        for (int j = w.lane(); j < N; j += 32) {
+        for (int j = c.tid(); j < N; j += c.nthreads()) {
             double acc = 0.0;
             const double* col = A + (size_t)j * M;
             for (int i = 0; i < M; ++i) acc = dm::fma(col[i], lam[i], acc);
@@ -364,25 +360,25 @@ struct OcpEval {
             v += lam[M + j];
             lag_grad[j] = v;
         }
-        w.sync();
+        c.sync();
     }
 
     /** a9: lagrangian_gradient (1957-1975) */
-    PMB_DEV static double lagrangian_gradient(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
+    PMB_DEV static double lagrangian_gradient(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
                                               double* lag_grad, double* cost_grad, double* g, double* A)
     {
-        const double c = cost_gradient(w, o, var, d, cost_grad);
-        constraints_linearised(w, o, var, d, g, A, M, true);
-        lag_grad_from(w, A, lam, cost_grad, lag_grad);
+        const double c = cost_gradient(cta, o, var, d, cost_grad);
+        constraints_linearised(cta, o, var, d, g, A, M, true);
+        lag_grad_from(cta, A, lam, cost_grad, lag_grad);
         return c;
     }
     /** a10: lagrangian_gradient_hessian (2097-2174) */
-    PMB_DEV static double lagrangian_gradient_hessian(const Warp& w, const O& o, const double* var, const double* d, const double* lam,
-                                                      double* lag_grad, double* H, double* cost_grad, double* g, double* A)
+    PMB_DEV static double lagrangian_gradient_hessian(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
+                                                      double* lag_grad, double* H, double* cost_grad, double* g, double* A, double* nv)
     {
-        const double c = cost_gradient_hessian(w, o, var, d, lam, cost_grad, H);
-        constraints_linearised(w, o, var, d, g, A, M, true);
-        lag_grad_from(w, A, lam, cost_grad, lag_grad);
+        const double c = cost_gradient_hessian(cta, o, var, d, lam, cost_grad, H, nv);
+        constraints_linearised(cta, o, var, d, g, A, M, true);
+        lag_grad_from(cta, A, lam, cost_grad, lag_grad);
         return c;
     }
 };

@@ -1,4 +1,4 @@
-// pmb_qp.hpp — batched boxADMM with a dense pivoted LDL^T: one warp per QP instance, KKT factor in shared memory.
+// pmb_qp.hpp — batched boxADMM with a dense pivoted LDL^T: one CTA per QP instance, KKT factor in shared memory.
 //
 // Reference: src/solvers/box_admm.hpp (solve_impl 88-205, construct_kkt_matrix 207-223, factorise 335-341, compute_kkt_rhs
 // 351-355, rho_vec_update 357-396, residuals_update 398-415, termination 417-431, estimate_rho 433-445, update_kkt_rho
@@ -6,17 +6,21 @@
 // (src/utils/helpers.hpp:38-43 selects it; Eigen itself is not in the reference tree).
 //
 // B200 mapping.  K = [[H + sigma I + diag(rho_box), .],[A, -diag(1/rho_A)]] is (N+M)^2; only its lower triangle is
-// ever read, so the warp keeps the packed lower triangle (n(n+1)/2 doubles: 43.7 KB for the mobile robot) in shared
-// memory and factors it in place.  Eigen's LDLT picks, at step k, the largest |diagonal| of the *not yet updated*
-// trailing diagonal (its in-place algorithm is left-looking), i.e. the pivot order depends only on diag(K): the warp
-// first replays that selection on the diagonal alone, gathers P K P^T straight into the packed layout, and then runs an
-// unpivoted right-looking LDL^T whose per-element update order (ascending elimination step, fused multiply-add) is
-// identical to the left-looking inner products.  Triangular solves keep the right-hand side in registers (lane l owns
-// rows l, l+32, ...) and broadcast each finished component with one shuffle.  ADMM vectors live in shared memory and
-// every lane owns a strided slice; residual mat-vecs stream H and A from global memory (L2 resident) every
-// check_termination trips.
+// ever read, so the CTA keeps the packed lower triangle (n(n+1)/2 doubles: 43.7 KB for the mobile robot) in shared
+// memory and factors it in place; K is never written to HBM.  Problems whose factor does not fit (kite 12x1: 570 KB)
+// keep it in a per-CTA global scratch slot that stays L2 resident.
+//   * Pivoting.  Eigen's LDLT picks, at step k, the largest |diagonal| of the *not yet updated* trailing diagonal (its
+//     in-place algorithm is left-looking), i.e. the pivot order depends only on diag(K): warp 0 replays that selection on
+//     the diagonal alone, the block gathers P K P^T straight into the packed layout, and then runs an unpivoted
+//     right-looking LDL^T whose per-element update order (ascending elimination step, fused multiply-add) is identical
+//     to the left-looking inner products.
+//   * Factorisation: columns of the trailing matrix are dealt round-robin to the warps, rows to the lanes.
+//   * Triangular solves are a dependent chain of n steps: warp 0 keeps the right-hand side in registers (lane l owns
+//     rows l, l+32, ...) and broadcasts each finished component with one shuffle; the other warps wait at the barrier.
+//   * ADMM vector updates are strided over the block; the residual mat-vecs (every check_termination trips) give every
+//     thread one row of A x, H x or A^T y and stream H and A from global memory (L2 resident).
 #pragma once
-#include "pmb_warp.hpp"
+#include "pmb_cta.hpp"
 #include "../../include/polympc_b200.h"
 #include <cfloat>
 
@@ -36,60 +40,82 @@ constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e+6, RHO_EQ_FACTOR = 1e+3;
 constexpr double LOOSE_BOUNDS_THRESH = 1e+10, EQ_TOL = 1e-4, DIV_BY_ZERO_REGUL = 10e-10;
 }
 
-/** shared-memory bytes one QP instance needs */
-inline size_t qp_smem_bytes(int N, int M)
+/** doubles of the packed factor */
+inline size_t qp_factor_doubles(int N, int M) { const size_t n = (size_t)N + M; return n * (n + 1) / 2; }
+/** shared-memory bytes of the vector workspace of one QP instance (everything except the packed factor) */
+inline size_t qp_vec_bytes(int N, int M)
 {
     const size_t n = (size_t)N + M;
-    const size_t doubles = n * (n + 1) / 2 + 3 * n + 8 * (size_t)N + 6 * (size_t)M;
+    const size_t doubles = 3 * n + 6 * (size_t)N + 4 * (size_t)M;
     return doubles * sizeof(double) + 2 * n * sizeof(int) + 16;
 }
 
+PMB_DEV double fmax_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (a < b) ? b : a; }
+PMB_DEV double fmin_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (b < a) ? b : a; }
 PMB_DEV double warp_max(const Warp& w, double m)
 {
     for (int off = 16; off >= 1; off >>= 1) { const double o = w.shfl_xor(m, off); if (o > m) m = o; }
     return m;
 }
-PMB_DEV double fmax_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (a < b) ? b : a; }
-PMB_DEV double fmin_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (b < a) ? b : a; }
 
 PMB_DEV int packed_off(int j, int n) { return j * n - (j * (j - 1)) / 2; }
 
-/** replay Eigen's diagonal pivot selection on |dd| (a scratch copy of diag(K)); perm[a] = original index at position a */
-PMB_DEV void ldlt_pivot_order(const Warp& w, int n, double* dd, int* perm)
+/** sum_j a[j*ld] * x[j], sequential ascending fused chain; loads are issued eight at a time ahead of the chain */
+PMB_DEV double dot_chain(const double* a, size_t ld, const double* x, int n)
 {
-    const int lane = w.lane();
-    for (int i = lane; i < n; i += 32) perm[i] = i;
-    w.sync();
-    for (int k = 0; k < n - 1; ++k) {
-        double bv = -1.0; int bi = 0x7fffffff;
-        for (int i = k + ((lane - k) & 31); i < n; i += 32) {   // positions >= k owned by this lane, ascending
-            const double v = dm::fabs(dd[i]);
-            if (v > bv) { bv = v; bi = i; }
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double ov = w.shfl_xor(bv, off);
-            const int oi = w.shfl_xor(bi, off);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0 && bi != k && bi < n) {
-            const double t = dd[k]; dd[k] = dd[bi]; dd[bi] = t;
-            const int p = perm[k]; perm[k] = perm[bi]; perm[bi] = p;
-        }
-        w.sync();
+    double acc = 0.0;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+        double v[8];
+        PMB_UNROLL
+        for (int u = 0; u < 8; ++u) v[u] = a[(size_t)(j + u) * ld];
+        PMB_UNROLL
+        for (int u = 0; u < 8; ++u) acc = dm::fma(v[u], x[j + u], acc);
     }
+    for (; j < n; ++j) acc = dm::fma(a[(size_t)j * ld], x[j], acc);
+    return acc;
 }
 
-/** gather P K P^T into the packed lower triangle */
-PMB_DEV void kkt_gather_permuted(const Warp& w, int N, int M, const double* H, const double* A, const double* dK, const int* perm,
-                                 double* Lp)
+/** replay Eigen's diagonal pivot selection on |dd| (a scratch copy of diag(K)); perm[a] = original index at position a.
+ *  Executed by warp 0; ends with a block barrier. */
+PMB_DEV void ldlt_pivot_order(Cta& c, int n, double* dd, int* perm)
 {
-    const int n = N + M, lane = w.lane();
-    for (int b = 0; b < n; ++b) {
-        const int c = perm[b];
+    if (c.warp_id() == 0) {
+        const Warp& w = c.w;
+        const int lane = w.lane();
+        for (int i = lane; i < n; i += 32) perm[i] = i;
+        w.sync();
+        for (int k = 0; k < n - 1; ++k) {
+            double bv = -1.0; int bi = 0x7fffffff;
+            for (int i = k + ((lane - k) & 31); i < n; i += 32) {   // positions >= k owned by this lane, ascending
+                const double v = dm::fabs(dd[i]);
+                if (v > bv) { bv = v; bi = i; }
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                const double ov = w.shfl_xor(bv, off);
+                const int oi = w.shfl_xor(bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0 && bi != k && bi < n) {
+                const double t = dd[k]; dd[k] = dd[bi]; dd[bi] = t;
+                const int p = perm[k]; perm[k] = perm[bi]; perm[bi] = p;
+            }
+            w.sync();
+        }
+    }
+    c.sync();
+}
+
+/** gather P K P^T into the packed lower triangle: columns round-robin over warps, rows over lanes */
+PMB_DEV void kkt_gather_permuted(Cta& c, int N, int M, const double* H, const double* A, const double* dK, const int* perm, double* Lp)
+{
+    const int n = N + M, lane = c.lane(), nw = c.nwarps();
+    for (int b = c.warp_id(); b < n; b += nw) {
+        const int cc = perm[b];
         double* col = Lp + packed_off(b, n) - b;
         for (int a = b + lane; a < n; a += 32) {
             const int r = perm[a];
-            const int hi = r > c ? r : c, lo = r > c ? c : r;
+            const int hi = r > cc ? r : cc, lo = r > cc ? cc : r;
             double v;
             if (hi == lo) v = dK[hi];
             else if (hi < N) v = H[hi + (size_t)lo * N];
@@ -98,224 +124,230 @@ PMB_DEV void kkt_gather_permuted(const Warp& w, int N, int M, const double* H, c
             col[a] = v;
         }
     }
-    w.sync();
+    c.sync();
 }
 
-/** unpivoted right-looking LDL^T on the packed lower triangle; tmp[n] scratch */
-PMB_DEV void ldlt_factor_packed(const Warp& w, int n, double* Lp, double* tmp)
+/** unpivoted right-looking LDL^T on the packed lower triangle; tmp[n] scratch.  R = ceil(n / 32). */
+template <int R>
+PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp, double* tmp)
 {
-    const int lane = w.lane();
+    const int tid = c.tid(), nt = c.nthreads(), lane = c.lane(), wid = c.warp_id(), nw = c.nwarps();
     for (int j = 0; j < n; ++j) {
         double* cj = Lp + packed_off(j, n) - j;   // cj[i] = L(i,j), i >= j
         const double dj = cj[j];
         const bool scale = dm::fabs(dj) > 0.0;
-        for (int i = j + 1 + lane; i < n; i += 32) {
+        for (int i = j + 1 + tid; i < n; i += nt) {
             double v = cj[i];
             if (scale) { v = v / dj; cj[i] = v; }
             tmp[i] = dj * v;
         }
-        w.sync();
-        for (int i = j + 1 + lane; i < n; i += 32) {
-            const double nl = -cj[i];
-            double* p = Lp + packed_off(j + 1, n) - (j + 1) + i;   // a(i, j+1)
-            int stride = n - (j + 1) - 1;
-            for (int k = j + 1; k <= i; ++k) {
-                *p = dm::fma(nl, tmp[k], *p);
-                p += stride; --stride;
+        c.sync();
+        // a(i,k) = fma(-L(i,j), tmp[k], a(i,k)) for j < k <= i < n
+        for (int k = j + 1 + wid; k < n; k += nw) {
+            const double tk = tmp[k];
+            double* ck = Lp + packed_off(k, n) - k;
+            double av[R], lv[R];
+            PMB_UNROLL
+            for (int r = 0; r < R; ++r) {
+                const int i = k + lane + 32 * r;
+                if (i < n) { av[r] = ck[i]; lv[r] = cj[i]; }
+            }
+            PMB_UNROLL
+            for (int r = 0; r < R; ++r) {
+                const int i = k + lane + 32 * r;
+                if (i < n) ck[i] = dm::fma(-lv[r], tk, av[r]);
             }
         }
-        w.sync();
+        c.sync();
     }
 }
 
-/** solve (P^T L D L^T P) s = rhs; `sol` holds rhs on entry and the solution on exit (unpermuted indexing) */
+/** solve (P^T L D L^T P) s = rhs; `sol` holds rhs on entry and the solution on exit (unpermuted indexing).
+ *  Executed by warp 0; ends with a block barrier. */
 template <int R>
-PMB_DEV void ldlt_solve_packed(const Warp& w, int n, const double* Lp, const int* perm, double* sol)
+PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol)
 {
-    const int lane = w.lane();
-    double y[R];
-    int offr[R];
-    PMB_UNROLL
-    for (int r = 0; r < R; ++r) {
-        const int i = lane + 32 * r;
-        y[r] = i < n ? sol[perm[i]] : 0.0;
-        offr[r] = i < n ? packed_off(i, n) - i : 0;
-    }
-    // unit lower: ascending columns
-    PMB_UNROLL
-    for (int jb = 0; jb < R; ++jb) {
-        const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
-        PMB_NOUNROLL
-        for (int jj = 0; jj < jend; ++jj) {
-            const int j = jb * 32 + jj;
-            const double yj = w.shfl(y[jb], jj);
-            const double* col = Lp + packed_off(j, n) - j;
-            PMB_UNROLL
-            for (int r = jb; r < R; ++r) {
-                const int i = lane + 32 * r;
-                if (i > j && i < n) y[r] = dm::fma(-col[i], yj, y[r]);
+    if (c.warp_id() == 0) {
+        const Warp& w = c.w;
+        const int lane = w.lane();
+        double y[R];
+        int offr[R];
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            y[r] = i < n ? sol[perm[i]] : 0.0;
+            offr[r] = i < n ? packed_off(i, n) - i : 0;
+        }
+        // unit lower: ascending columns
+        PMB_UNROLL
+        for (int jb = 0; jb < R; ++jb) {
+            const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
+            PMB_NOUNROLL
+            for (int jj = 0; jj < jend; ++jj) {
+                const int j = jb * 32 + jj;
+                const double yj = w.shfl(y[jb], jj);
+                const double* col = Lp + packed_off(j, n) - j;
+                PMB_UNROLL
+                for (int r = jb; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i > j && i < n) y[r] = dm::fma(-col[i], yj, y[r]);
+                }
             }
         }
-    }
-    PMB_UNROLL
-    for (int r = 0; r < R; ++r) {
-        const int i = lane + 32 * r;
-        if (i < n) {
-            const double di = Lp[offr[r] + i];
-            y[r] = (dm::fabs(di) > DBL_MIN) ? (y[r] / di) : 0.0;
-        }
-    }
-    // unit upper (L^T): descending columns
-    PMB_UNROLL
-    for (int jb = R - 1; jb >= 0; --jb) {
-        const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
-        PMB_NOUNROLL
-        for (int jj = jend - 1; jj >= 0; --jj) {
-            const int j = jb * 32 + jj;
-            const double yj = w.shfl(y[jb], jj);
-            PMB_UNROLL
-            for (int r = 0; r <= jb; ++r) {
-                const int i = lane + 32 * r;
-                if (i < j) y[r] = dm::fma(-Lp[offr[r] + j], yj, y[r]);
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) {
+                const double di = Lp[offr[r] + i];
+                y[r] = (dm::fabs(di) > DBL_MIN) ? (y[r] / di) : 0.0;
             }
         }
+        // unit upper (L^T): descending columns
+        PMB_UNROLL
+        for (int jb = R - 1; jb >= 0; --jb) {
+            const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
+            PMB_NOUNROLL
+            for (int jj = jend - 1; jj >= 0; --jj) {
+                const int j = jb * 32 + jj;
+                const double yj = w.shfl(y[jb], jj);
+                PMB_UNROLL
+                for (int r = 0; r <= jb; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i < j) y[r] = dm::fma(-Lp[offr[r] + j], yj, y[r]);
+                }
+            }
+        }
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) sol[perm[i]] = y[r];
+        }
     }
-    w.sync();
-    PMB_UNROLL
-    for (int r = 0; r < R; ++r) {
-        const int i = lane + 32 * r;
-        if (i < n) sol[perm[i]] = y[r];
-    }
-    w.sync();
+    c.sync();
 }
 
-/** the whole boxADMM solve of one instance by one warp */
+/** the whole boxADMM solve of one instance by one CTA.  Lp: n(n+1)/2 doubles (shared or global), vec: qp_vec_bytes() of
+ *  shared memory. */
 template <int R>
-PMB_DEV void qp_solve_warp(const Warp& w, const pmb_qp_settings_t& st, const QpArgs& a, unsigned char* smem)
+PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec)
 {
-    const int N = a.N, M = a.M, n = N + M, lane = w.lane();
-    double* Lp = reinterpret_cast<double*>(smem);
-    double* dK = Lp + (size_t)n * (n + 1) / 2;
+    const int N = a.N, M = a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
+    double* dK = reinterpret_cast<double*>(vec);
     double* tmp = dK + n;
     double* sol = tmp + n;
     double* x = sol + n;
     double* q = x + N;
     double* yb = q + N;
     double* h = yb + N;
-    double* xlb = h + N;
-    double* xub = xlb + N;
-    double* rb = xub + N;
+    double* rb = h + N;
     double* rbi = rb + N;
     double* z = rbi + N;
     double* ya = z + M;
-    double* alb = ya + M;
-    double* aub = alb + M;
-    double* rv = aub + M;
+    double* rv = ya + M;
     double* rvi = rv + M;
     int* perm = reinterpret_cast<int*>(rvi + M);
     int* ctype = perm + n;     // [constr_type (M) ; box_constr_type (N)]
+    const double *alb = a.Alb, *aub = a.Aub, *xlb = a.xlb, *xub = a.xub;   // bounds stay in global memory (read-only here)
 
     // ---- load, initial iterates (box_admm.hpp:97-100) -----------------------------------------------------------
-    for (int i = lane; i < N; i += 32) {
-        h[i] = a.h[i]; xlb[i] = a.xlb[i]; xub[i] = a.xub[i];
+    for (int i = tid; i < N; i += nt) {
+        h[i] = a.h[i];
         x[i] = a.xg ? a.xg[i] : 0.0;
         q[i] = x[i];
         yb[i] = a.yg ? a.yg[M + i] : 0.0;
     }
-    for (int i = lane; i < M; i += 32) { alb[i] = a.Alb[i]; aub[i] = a.Aub[i]; ya[i] = a.yg ? a.yg[i] : 0.0; }
-    w.sync();
-    for (int i = lane; i < M; i += 32) {
-        double acc = 0.0;
-        if (a.xg) for (int j = 0; j < N; ++j) acc = dm::fma(a.A[i + (size_t)j * M], x[j], acc);
-        z[i] = acc;
-    }
+    for (int i = tid; i < M; i += nt) ya[i] = a.yg ? a.yg[i] : 0.0;
+    c.sync();
+    for (int i = tid; i < M; i += nt) z[i] = a.xg ? dot_chain(a.A + i, (size_t)M, x, N) : 0.0;
 
     // ---- parse_constraints_bounds (qp_base.hpp:195-222) ------------------------------------------------------------
-    for (int i = lane; i < M; i += 32)
+    for (int i = tid; i < M; i += nt)
         ctype[i] = (alb[i] < -qpc::LOOSE_BOUNDS_THRESH && aub[i] > qpc::LOOSE_BOUNDS_THRESH) ? PMB_LOOSE_BOUNDS
                    : ((aub[i] - alb[i] < qpc::EQ_TOL) ? PMB_EQUALITY_CONSTRAINT : PMB_INEQUALITY_CONSTRAINT);
-    for (int i = lane; i < N; i += 32)
+    for (int i = tid; i < N; i += nt)
         ctype[M + i] = (xlb[i] < -qpc::LOOSE_BOUNDS_THRESH && xub[i] > qpc::LOOSE_BOUNDS_THRESH) ? PMB_LOOSE_BOUNDS
                        : ((xub[i] - xlb[i] < qpc::EQ_TOL) ? PMB_EQUALITY_CONSTRAINT : PMB_INEQUALITY_CONSTRAINT);
-    w.sync();
+    c.sync();
 
     int rho_updates = 0, n_factor = 0;
     double rho = 0.0;
     auto rho_vec_update = [&](double rho0) {   // box_admm.hpp:357-396
-        for (int i = lane; i < M; i += 32) {
+        for (int i = tid; i < M; i += nt) {
             const int t = ctype[i];
             const double r = t == PMB_LOOSE_BOUNDS ? qpc::RHO_MIN : (t == PMB_EQUALITY_CONSTRAINT ? qpc::RHO_EQ_FACTOR * rho0 : rho0);
             rv[i] = r; rvi[i] = 1.0 / r;
         }
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += nt) {
             const int t = ctype[M + i];
             const double r = t == PMB_LOOSE_BOUNDS ? qpc::RHO_MIN : (t == PMB_EQUALITY_CONSTRAINT ? qpc::RHO_EQ_FACTOR * rho0 : rho0);
             rb[i] = r; rbi[i] = 1.0 / r;
         }
         rho = rho0;
         rho_updates += 1;
-        w.sync();
+        c.sync();
     };
     auto factorise = [&]() {
-        for (int i = lane; i < n; i += 32) tmp[i] = dK[i];
-        w.sync();
-        ldlt_pivot_order(w, n, tmp, perm);
-        if (n_factor == 0 && a.perm) { for (int i = lane; i < n; i += 32) a.perm[i] = perm[i]; }
-        kkt_gather_permuted(w, N, M, a.H, a.A, dK, perm, Lp);
-        ldlt_factor_packed(w, n, Lp, tmp);
+        for (int i = tid; i < n; i += nt) tmp[i] = dK[i];
+        c.sync();
+        ldlt_pivot_order(c, n, tmp, perm);
+        if (n_factor == 0 && a.perm) { for (int i = tid; i < n; i += nt) a.perm[i] = perm[i]; }
+        kkt_gather_permuted(c, N, M, a.H, a.A, dK, perm, Lp);
+        ldlt_factor_packed<R>(c, n, Lp, tmp);
         ++n_factor;
     };
 
     rho_vec_update(st.rho);
     // diag of construct_kkt_matrix (box_admm.hpp:207-223): (H_ii + sigma) + rho_box_i ; -1/rho_A
-    for (int i = lane; i < N; i += 32) { double v = a.H[i + (size_t)i * N]; v += st.sigma; v += rb[i]; dK[i] = v; }
-    for (int i = lane; i < M; i += 32) dK[N + i] = -rvi[i];
-    w.sync();
+    for (int i = tid; i < N; i += nt) { double v = a.H[i + (size_t)i * N]; v += st.sigma; v += rb[i]; dK[i] = v; }
+    for (int i = tid; i < M; i += nt) dK[N + i] = -rvi[i];
+    c.sync();
     factorise();
 
     int status = PMB_QP_UNSOLVED;
     double res_prim = 1.0, res_dual = 1.0, rho_estimate = 0.0, max_Ax_z = 0.0, max_Hx_ATy_h = 0.0;
     const double alpha = st.alpha, sigma = st.sigma;
 
-    auto residuals_update = [&]() {   // box_admm.hpp:398-415
-        double nAx = 0.0, nz = 0.0, nx = 0.0, nHx = 0.0, nATy = 0.0, nh = 0.0, nyb = 0.0, rp = 0.0, rq = 0.0, rd = 0.0;
-        for (int i = lane; i < M; i += 32) {
-            double acc = 0.0;
-            for (int j = 0; j < N; ++j) acc = dm::fma(a.A[i + (size_t)j * M], x[j], acc);
-            double v = dm::fabs(acc); if (v > nAx) nAx = v;
-            v = dm::fabs(z[i]); if (v > nz) nz = v;
-            v = dm::fabs(acc - z[i]); if (v > rp) rp = v;
+    auto residuals_update = [&]() {   // box_admm.hpp:398-415; task t < M: row t of A x, task M + i: row i of H x and A^T y
+        enum { nAx = 0, nz, nx, nHx, nATy, nh, nyb, rp, rq, rd, NRED };
+        double m[NRED];
+        PMB_UNROLL
+        for (int k = 0; k < NRED; ++k) m[k] = 0.0;
+        for (int t = tid; t < M + N; t += nt) {
+            if (t < M) {
+                const int i = t;
+                const double acc = dot_chain(a.A + i, (size_t)M, x, N);
+                double v = dm::fabs(acc); if (v > m[nAx]) m[nAx] = v;
+                v = dm::fabs(z[i]); if (v > m[nz]) m[nz] = v;
+                v = dm::fabs(acc - z[i]); if (v > m[rp]) m[rp] = v;
+            } else {
+                const int i = t - M;
+                const double hx = dot_chain(a.H + i, (size_t)N, x, N);
+                const double aty = dot_chain(a.A + (size_t)i * M, 1, ya, M);
+                double v = dm::fabs(x[i]); if (v > m[nx]) m[nx] = v;
+                v = dm::fabs(hx); if (v > m[nHx]) m[nHx] = v;
+                v = dm::fabs(aty); if (v > m[nATy]) m[nATy] = v;
+                v = dm::fabs(h[i]); if (v > m[nh]) m[nh] = v;
+                v = dm::fabs(yb[i]); if (v > m[nyb]) m[nyb] = v;
+                v = dm::fabs(x[i] - q[i]); if (v > m[rq]) m[rq] = v;
+                v = dm::fabs(((hx + h[i]) + aty) + yb[i]); if (v > m[rd]) m[rd] = v;
+            }
         }
-        for (int i = lane; i < N; i += 32) {
-            double hx = 0.0, aty = 0.0;
-            for (int j = 0; j < N; ++j) hx = dm::fma(a.H[i + (size_t)j * N], x[j], hx);
-            const double* col = a.A + (size_t)i * M;
-            for (int r = 0; r < M; ++r) aty = dm::fma(col[r], ya[r], aty);
-            double v = dm::fabs(x[i]); if (v > nx) nx = v;
-            v = dm::fabs(hx); if (v > nHx) nHx = v;
-            v = dm::fabs(aty); if (v > nATy) nATy = v;
-            v = dm::fabs(h[i]); if (v > nh) nh = v;
-            v = dm::fabs(yb[i]); if (v > nyb) nyb = v;
-            v = dm::fabs(x[i] - q[i]); if (v > rq) rq = v;
-            v = dm::fabs(((hx + h[i]) + aty) + yb[i]); if (v > rd) rd = v;
-        }
-        nAx = warp_max(w, nAx); nz = warp_max(w, nz); nx = warp_max(w, nx); nHx = warp_max(w, nHx); nATy = warp_max(w, nATy);
-        nh = warp_max(w, nh); nyb = warp_max(w, nyb); rp = warp_max(w, rp); rq = warp_max(w, rq); rd = warp_max(w, rd);
-        max_Ax_z = fmax_nan(nAx, fmax_nan(nz, nx));
-        max_Hx_ATy_h = fmax_nan(nHx, fmax_nan(nATy, fmax_nan(nh, nyb)));
-        res_prim = rp + rq;
-        res_dual = rd;
+        c.max_all<NRED>(m);
+        max_Ax_z = fmax_nan(m[nAx], fmax_nan(m[nz], m[nx]));
+        max_Hx_ATy_h = fmax_nan(m[nHx], fmax_nan(m[nATy], fmax_nan(m[nh], m[nyb])));
+        res_prim = m[rp] + m[rq];
+        res_dual = m[rd];
     };
 
     int iter;
     for (iter = 1; iter <= st.max_iter; ++iter) {
         // compute_kkt_rhs (351-355)
-        for (int i = lane; i < N; i += 32) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
-        for (int i = lane; i < M; i += 32) sol[N + i] = z[i] - rvi[i] * ya[i];
-        w.sync();
-        ldlt_solve_packed<R>(w, n, Lp, perm, sol);
+        for (int i = tid; i < N; i += nt) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
+        for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
+        c.sync();
+        ldlt_solve_packed<R>(c, n, Lp, perm, sol);
         // z, y_A (126, 133-135, 142-144)
-        for (int i = lane; i < M; i += 32) {
+        for (int i = tid; i < M; i += nt) {
             const double zp = z[i];
             const double zt = zp + rvi[i] * (sol[N + i] - ya[i]);
             double v = alpha * zt;
@@ -325,7 +357,7 @@ PMB_DEV void qp_solve_warp(const Warp& w, const pmb_qp_settings_t& st, const QpA
             z[i] = zn;
         }
         // x, q, y_box (129-130, 138-139, 146-147)
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += nt) {
             double xv = alpha * sol[i];
             xv += (1 - alpha) * xv;
             x[i] = xv;
@@ -333,7 +365,7 @@ PMB_DEV void qp_solve_warp(const Warp& w, const pmb_qp_settings_t& st, const QpA
             q[i] = qv;
             yb[i] += rb[i] * (xv - qv);
         }
-        w.sync();
+        c.sync();
 
         const bool check = (st.check_termination != 0) && (iter % st.check_termination == 0);
         if (check) {
@@ -350,30 +382,30 @@ PMB_DEV void qp_solve_warp(const Warp& w, const pmb_qp_settings_t& st, const QpA
             new_rho = fmax_nan(qpc::RHO_MIN, fmin_nan(new_rho, qpc::RHO_MAX));
             rho_estimate = new_rho;
             if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
-                for (int i = lane; i < N; i += 32) tmp[i] = rb[i];   // rho_box_prev
-                w.sync();
+                for (int i = tid; i < N; i += nt) tmp[i] = rb[i];   // rho_box_prev
+                c.sync();
                 rho_vec_update(new_rho);
                 // update_kkt_rho (447-452)
-                for (int i = lane; i < N; i += 32) dK[i] += (rb[i] - tmp[i]);
-                for (int i = lane; i < M; i += 32) dK[N + i] = -rvi[i];
-                w.sync();
+                for (int i = tid; i < N; i += nt) dK[i] += (rb[i] - tmp[i]);
+                for (int i = tid; i < M; i += nt) dK[N + i] = -rvi[i];
+                c.sync();
                 factorise();
             }
         }
     }
     if (iter > st.max_iter) status = PMB_QP_MAX_ITER_EXCEEDED;
 
-    for (int i = lane; i < N; i += 32) { a.x[i] = x[i]; a.y[M + i] = yb[i]; if (a.q) a.q[i] = q[i]; }
-    for (int i = lane; i < M; i += 32) { a.y[i] = ya[i]; if (a.z) a.z[i] = z[i]; }
-    if (a.ctype) for (int i = lane; i < n; i += 32) a.ctype[i] = ctype[i];
-    if (lane == 0) {
+    for (int i = tid; i < N; i += nt) { a.x[i] = x[i]; a.y[M + i] = yb[i]; if (a.q) a.q[i] = q[i]; }
+    for (int i = tid; i < M; i += nt) { a.y[i] = ya[i]; if (a.z) a.z[i] = z[i]; }
+    if (a.ctype) for (int i = tid; i < n; i += nt) a.ctype[i] = ctype[i];
+    if (tid == 0) {
         if (a.info) {
             a.info->status = status; a.info->iter = iter; a.info->rho_updates = rho_updates; a.info->_pad = 0;
             a.info->rho_estimate = rho_estimate; a.info->res_prim = res_prim; a.info->res_dual = res_dual;
         }
         if (a.nfac) *a.nfac = n_factor;
     }
-    w.sync();
+    c.sync();
 }
 
 } // namespace pmb

@@ -19,8 +19,13 @@ struct IProblem {
     virtual void set_time_limits(double, double) = 0;
     virtual void time_nodes(double*) const = 0;
     virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
-    virtual bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const = 0;
-    virtual bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const = 0;
+    /** shared-memory bytes / resident CTAs of the fused SQP kernel for the two placements of the LDL^T factor */
+    virtual size_t solve_smem_bytes(bool factor_in_smem) const = 0;
+    virtual size_t factor_doubles() const = 0;
+    virtual int solve_resident_ctas(bool factor_in_smem) const = 0;
+    /** one persistent launch that solves `batch` instances (grid CTAs draw them from `queue`) */
+    virtual bool launch_solve(int grid, bool factor_in_smem, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
+                              double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
 };
 
 template <class O>
@@ -36,7 +41,7 @@ struct ProblemImpl : IProblem {
     void get_params(double* v) const override { o.model.get_params(v); }
     void set_time_limits(double a, double b) override { o.set_time_limits(a, b); }
     void time_nodes(double* t) const override { for (int i = 0; i < O::NN; ++i) t[i] = o.time_nodes[i]; }
-    template <int MODE> bool ev(int batch, const OcpIo& io, stream_t s) const { return rt_launch<OcpEvalBody<O, MODE>>(batch, 0, s, o, io); }
+    template <int MODE> bool ev(int batch, const OcpIo& io, stream_t s) const { return rt_launch<OcpEvalBody<O, MODE>>(batch, OcpEvalBody<O, MODE>::SMEM, s, o, io); }
     bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const override
     {
         switch (mode) {
@@ -51,10 +56,20 @@ struct ProblemImpl : IProblem {
         }
         return false;
     }
-    bool launch_linearise(int n_active, const SqpWs& ws, int first, stream_t s) const override
-    { return rt_launch<SqpLineariseBody<O>>(n_active, SqpLineariseBody<O>::SMEM, s, o, ws, first); }
-    bool launch_step(int n_active, const SqpWs& ws, const pmb_sqp_settings_t& st, stream_t s) const override
-    { return rt_launch<SqpStepBody<O>>(n_active, SqpStepBody<O>::SMEM, s, o, ws, st); }
+    using Solve = SqpSolveBody<O>;
+    size_t solve_smem_bytes(bool in_smem) const override { return Solve::smem_bytes(in_smem); }
+    size_t factor_doubles() const override { return Solve::FACTOR_DOUBLES; }
+    int solve_resident_ctas(bool in_smem) const override
+    {
+        return resident_ctas<Solve, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
+            Solve::smem_bytes(in_smem), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
+    }
+    bool launch_solve(int grid, bool in_smem, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
+                      int batch, int* queue, stream_t s) const override
+    {
+        FactorStore fs{in_smem ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES};
+        return rt_launch<Solve>(grid, Solve::smem_bytes(in_smem), s, o, ws, st, qst, fs, batch, queue);
+    }
 };
 
 

@@ -8,7 +8,8 @@
 //
 // Rules for kernel bodies (they make both back ends agree):
 //   * every w.sync()/w.shfl*/w.ballot/w.block_sync() is executed by ALL threads of the block, converged;
-//   * a kernel body is a struct with `static constexpr int THREADS` and
+//   * a kernel body is a struct with `static constexpr int THREADS`, `MIN_BLOCKS` (resident CTAs per SM the register
+//     allocation must allow) and
 //       template-free  static PMB_DEV void run(const Warp& w, int block, unsigned char* smem, Args... args);
 #pragma once
 #include <cstdint>
@@ -29,6 +30,7 @@ struct Warp {
     PMB_DEV int lane() const { return (int)(threadIdx.x & 31u); }
     PMB_DEV int tid() const { return (int)threadIdx.x; }
     PMB_DEV int nthreads() const { return (int)blockDim.x; }
+    PMB_DEV int warp_id() const { return (int)(threadIdx.x >> 5); }
     PMB_DEV void sync() const { __syncwarp(); }
     PMB_DEV void block_sync() const { __syncthreads(); }
     PMB_DEV double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
@@ -39,12 +41,14 @@ struct Warp {
     PMB_DEV unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
     PMB_DEV bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
     PMB_DEV bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
+    PMB_DEV unsigned long long clock() const { return (unsigned long long)clock64(); }
 };
 
 PMB_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+PMB_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 
 template <class Body, class... Args>
-__global__ void __launch_bounds__(Body::THREADS) pmb_kernel(Args... args)
+__global__ void __launch_bounds__(Body::THREADS, Body::MIN_BLOCKS) pmb_kernel(Args... args)
 {
     extern __shared__ __align__(16) unsigned char pmb_smem[];
     Warp w;
@@ -64,6 +68,20 @@ inline cudaError_t launch(int grid, size_t smem, cudaStream_t stream, Args... ar
     }
     pmb_kernel<Body, Args...><<<grid, Body::THREADS, smem, stream>>>(args...);
     return cudaGetLastError();
+}
+
+/** number of CTAs of this kernel that are resident at once on the current device (SMs x CTAs per SM): the grid of a
+ *  persistent launch.  0 on error. */
+template <class Body, class... Args>
+inline int resident_ctas(size_t smem, Args...)
+{
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(pmb_kernel<Body, Args...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pmb_kernel<Body, Args...>, Body::THREADS, smem) != cudaSuccess) return 0;
+    return sms * per_sm;
 }
 
 } // namespace pmb
@@ -93,6 +111,9 @@ struct EmuBlock {
     std::vector<char> done;
     std::vector<uint64_t> slot;
     std::vector<unsigned char> pred;
+    struct Bar { int count = 0; int gen = 0; };
+    Bar block_bar;
+    std::vector<Bar> warp_bar;
     char* stacks = nullptr;
     std::function<void(int)> body;
     static EmuBlock*& current() { static thread_local EmuBlock* p = nullptr; return p; }
@@ -105,10 +126,20 @@ struct EmuBlock {
         // returning activates uc_link (main_ctx)
     }
     void yield() { const int t = cur; swapcontext(&ctx[t], &main_ctx); }
+    /** true barrier among `participants` fibers: the last arrival releases the generation, the others yield until then */
+    void barrier(Bar& b, int participants, int t)
+    {
+        const int g = b.gen;
+        if (++b.count == participants) { b.count = 0; ++b.gen; return; }
+        while (b.gen == g) { cur = t; yield(); }
+    }
+    void warp_barrier(int t) { const int wi = t >> 5; const int cnt = (nthreads - (wi << 5)) >= 32 ? 32 : (nthreads - (wi << 5)); barrier(warp_bar[wi], cnt, t); }
+    void block_barrier(int t) { barrier(block_bar, nthreads, t); }
     void run(int n, size_t stack_bytes, std::function<void(int)> f)
     {
         nthreads = n; body = std::move(f);
         ctx.assign(n, ucontext_t()); done.assign(n, 0); slot.assign(n, 0); pred.assign(n, 0);
+        block_bar = Bar(); warp_bar.assign((n + 31) / 32, Bar());
         stacks = (char*)std::malloc(stack_bytes * (size_t)n);
         EmuBlock* prev = current();
         current() = this;
@@ -139,8 +170,9 @@ struct Warp {
     int lane() const { return t & 31; }
     int tid() const { return t; }
     int nthreads() const { return b->nthreads; }
-    void sync() const { b->cur = t; b->yield(); }
-    void block_sync() const { b->cur = t; b->yield(); }
+    int warp_id() const { return t >> 5; }
+    void sync() const { b->warp_barrier(t); }
+    void block_sync() const { b->block_barrier(t); }
     uint64_t xchg(uint64_t bits, int src_lane) const
     {
         b->slot[t] = bits;
@@ -166,11 +198,13 @@ struct Warp {
         sync();
         return m;
     }
+    unsigned long long clock() const { return 0; }
     bool any(bool p) const { return ballot(p) != 0; }
     bool all(bool p) const { const unsigned m = ballot(p); const int cnt = (b->nthreads - (t & ~31)) >= 32 ? 32 : (b->nthreads - (t & ~31)); return m == (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)); }
 };
 
 inline int atomic_add(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 
 typedef void* cudaStream_t_emu;
 
@@ -188,6 +222,10 @@ inline int launch(int grid, size_t smem, void* /*stream*/, Args... args)
     }
     return 0;
 }
+
+/** emulator: a handful of "resident" CTAs (they run one after the other; the first drains the queue) */
+template <class Body, class... Args>
+inline int resident_ctas(size_t, Args...) { return 2; }
 
 } // namespace pmb
 #endif

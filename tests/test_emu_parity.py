@@ -50,3 +50,21 @@ def test_sqp_robot(emu, orc):
 def test_sqp_cstr(emu, orc):
     w = W.cstr(1, seed=3, sqp_max_iter=4, ls_max_iter=10)
     pc.sqp_case(emu, orc, w)
+
+
+def test_sqp_warm_restart_and_reset_guess(emu, orc):
+    """second solve() warm-starts from the kept (x, lam); reset_guess() restores the guess given to set_primal/set_dual"""
+    w = W.mobile_robot(2, seed=11, sqp_max_iter=2, ls_max_iter=10)
+    outs = []
+    for api in (emu, orc):
+        s = api.sqp(w.name, 2); W.configure(s, w); s.solve()
+        x1 = s.primal()
+        s.set_initial_conditions(w.x0 + 0.01); s.solve()
+        x2, l2 = s.primal(), s.dual()
+        s.set_initial_conditions(w.x0); s.reset_guess(); s.solve()
+        x3 = s.primal()
+        outs.append((x1, x2, l2, x3))
+        s.close()
+    for a, b, n in zip(outs[0], outs[1], ("x1", "x2", "lam2", "x3")):
+        pc.assert_same(a, b, n)
+    pc.assert_same(outs[0][0], outs[0][3], "reset_guess reproduces the first solve")

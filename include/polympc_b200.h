@@ -183,6 +183,10 @@ long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s);
  * iterations executed (all instances) */
 int pmb_sqp_set_profiling(pmb_sqp_t* s, int on);
 int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches);
+/* raw counters behind it, cycles16[16]: SM cycles (thread 0 of every CTA, summed) in {linearise, QP, step}, [3] = SQP
+ * iterations, [4..9] = QP split {pivot order, gather, factorisation, triangular solves, ADMM updates, residual checks},
+ * [10] = ADMM trips; the rest is reserved */
+int pmb_sqp_get_phase_cycles(const pmb_sqp_t* s, unsigned long long* cycles16);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the engine's own stream */
 int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream);
 

@@ -486,6 +486,7 @@ double pmb_sqp_last_solve_ms(const pmb_sqp_t*) { return 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t*) { return 0; }
 int pmb_sqp_set_stream(pmb_sqp_t*, void*) { return PMB_OK; }
 int pmb_sqp_set_profiling(pmb_sqp_t*, int) { return PMB_OK; }
+int pmb_sqp_get_phase_cycles(const pmb_sqp_t*, unsigned long long* c) { if (c) for (int k = 0; k < 16; ++k) c[k] = 0; return PMB_OK; }
 int pmb_sqp_get_kernel_times(const pmb_sqp_t*, double* ms, long long* n) { for (int k = 0; k < 3; ++k) { if (ms) ms[k] = 0; if (n) n[k] = 0; } return PMB_OK; }
 int pmb_sqp_reset_guess(pmb_sqp_t* s)
 {

@@ -61,7 +61,7 @@ ABI_FUNCTIONS = [
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
-    "sqp_get_kernel_times", "sqp_set_stream",
+    "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
 ]
 
 
@@ -145,6 +145,7 @@ class CApi:
         g("sqp_reset_guess").argtypes = [C.c_void_p]
         g("sqp_set_profiling").argtypes = [C.c_void_p, C.c_int]
         g("sqp_get_kernel_times").argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
+        g("sqp_get_phase_cycles").argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
         g("kkt_assemble_dev").argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_void_p]
         g("qp_default_settings").argtypes = [C.POINTER(QpSettings)]
         g("qp_default_settings").restype = None
@@ -438,6 +439,13 @@ class Sqp:
 
     def set_profiling(self, on: bool):
         self.api._chk(self.api._fn("sqp_set_profiling")(self.h, int(bool(on))), "sqp_set_profiling")
+
+    def phase_cycles(self):
+        """raw profiling counters of the last solve (see pmb_sqp_get_phase_cycles)"""
+        cyc = np.zeros(16, dtype=np.uint64)
+        self.api._chk(self.api._fn("sqp_get_phase_cycles")(self.h, cyc.ctypes.data_as(C.POINTER(C.c_ulonglong))), "sqp_get_phase_cycles")
+        names = ("linearise", "qp", "step", "sqp_iterations", "qp_pivot", "qp_gather", "qp_factor", "qp_solve", "qp_update", "qp_resid", "admm_trips")
+        return {k: int(cyc[i]) for i, k in enumerate(names)}
 
     def kernel_times(self):
         """{kernel name: (milliseconds, launches)} of the last solve (profiling must be on)"""

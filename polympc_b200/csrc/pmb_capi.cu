@@ -76,19 +76,18 @@ struct Staging {
 constexpr size_t SMEM_CTA_MAX = 227 * 1024;   // B200: opt-in dynamic shared memory per CTA
 
 /** launches the persistent boxADMM kernel over `batch` instances; `queue` is a zeroed device counter */
-template <int R> bool launch_qp_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int batch,
-                                  int* queue, DevBuf<double>& scratch)
+template <int R, bool IN_SMEM> bool launch_qp_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb,
+                                                int batch, int* queue, DevBuf<double>& scratch)
 {
     const size_t base = Cta::SCRATCH_DOUBLES * sizeof(double) + vec_bytes;
-    const bool in_smem = base + fac_doubles * sizeof(double) <= SMEM_CTA_MAX;
-    const size_t smem = in_smem ? base + fac_doubles * sizeof(double) : base;
-    int grid = resident_ctas<QpBody<R>, pmb_qp_settings_t, QpBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
+    const size_t smem = IN_SMEM ? base + fac_doubles * sizeof(double) : base;
+    int grid = resident_ctas<QpBody<R, IN_SMEM>, pmb_qp_settings_t, QpBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
     if (grid <= 0) { last_error_string() = "qp_box_admm: kernel does not fit on the device"; return false; }
-    if (!in_smem) grid = grid > 2 * 148 ? 2 * 148 : grid;      // keep the global factor slots L2 resident
+    if (!IN_SMEM) grid = grid > 2 * 148 ? 2 * 148 : grid;      // keep the global factor slots L2 resident
     if (grid > batch) grid = batch;
     FactorStore fs{nullptr, fac_doubles};
-    if (!in_smem) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
-    return rt_launch<QpBody<R>>(grid, smem, s, st, qb, fs, batch, queue);
+    if (!IN_SMEM) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
+    return rt_launch<QpBody<R, IN_SMEM>>(grid, smem, s, st, qb, fs, batch, queue);
 }
 
 bool launch_qp(stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int batch, int* queue, DevBuf<double>& scratch)
@@ -97,11 +96,16 @@ bool launch_qp(stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int b
     const int R = (n + 31) / 32;
     const size_t fd = qp_factor_doubles(qb.N, qb.M), vb = qp_vec_bytes(qb.N, qb.M);
     if (Cta::SCRATCH_DOUBLES * sizeof(double) + vb > SMEM_CTA_MAX) { last_error_string() = "QP vectors do not fit in shared memory"; return false; }
+    const bool in_smem = Cta::SCRATCH_DOUBLES * sizeof(double) + vb + fd * sizeof(double) <= SMEM_CTA_MAX;
     switch (R) {
-#define PMB_QP_CASE(r) case r: return launch_qp_r<r>(fd, vb, s, st, qb, batch, queue, scratch);
-    PMB_QP_CASE(1) PMB_QP_CASE(2) PMB_QP_CASE(3) PMB_QP_CASE(4) PMB_QP_CASE(5) PMB_QP_CASE(6) PMB_QP_CASE(7) PMB_QP_CASE(8)
-    PMB_QP_CASE(9) PMB_QP_CASE(10) PMB_QP_CASE(11) PMB_QP_CASE(12)
-#undef PMB_QP_CASE
+    // the factor of every QP with n <= 192 fits in shared memory; n in (192, 224] may or may not; beyond that it never does
+#define PMB_QP_SMEM(r) case r: return launch_qp_r<r, true>(fd, vb, s, st, qb, batch, queue, scratch);
+#define PMB_QP_GLOB(r) case r: return launch_qp_r<r, false>(fd, vb, s, st, qb, batch, queue, scratch);
+    PMB_QP_SMEM(1) PMB_QP_SMEM(2) PMB_QP_SMEM(3) PMB_QP_SMEM(4) PMB_QP_SMEM(5) PMB_QP_SMEM(6)
+    case 7: return in_smem ? launch_qp_r<7, true>(fd, vb, s, st, qb, batch, queue, scratch) : launch_qp_r<7, false>(fd, vb, s, st, qb, batch, queue, scratch);
+    PMB_QP_GLOB(8) PMB_QP_GLOB(9) PMB_QP_GLOB(10) PMB_QP_GLOB(11) PMB_QP_GLOB(12)
+#undef PMB_QP_SMEM
+#undef PMB_QP_GLOB
     default: break;
     }
     last_error_string() = "QP dimension N+M > 384 not instantiated";
@@ -144,6 +148,7 @@ struct pmb_sqp {
     pmb::event_t kev0 = nullptr, kev1 = nullptr;
     pmb::DevBuf<unsigned long long> phase;   // per-phase SM cycles of the fused kernel (profiling)
     double last_kernel_ms = 0;
+    unsigned long long phase_host[16] = {0};
     double k_ms[3] = {0, 0, 0};
     long long k_launches[3] = {0, 0, 0};
     ~pmb_sqp()
@@ -370,9 +375,9 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
     s->stream = s->own_stream;
     {   // placement of the LDL^T factor and the persistent grid
         const IProblem& P = *s->ocp.impl;
-        s->factor_in_smem = P.solve_smem_bytes(true) <= SMEM_CTA_MAX;
-        if (P.solve_smem_bytes(s->factor_in_smem) > SMEM_CTA_MAX) { last_error_string() = "sqp_create: problem too large for shared memory"; return nullptr; }
-        int grid = P.solve_resident_ctas(s->factor_in_smem);
+        s->factor_in_smem = P.factor_in_smem();
+        if (P.solve_smem_bytes() > SMEM_CTA_MAX) { last_error_string() = "sqp_create: problem too large for shared memory"; return nullptr; }
+        int grid = P.solve_resident_ctas();
         if (grid <= 0) { last_error_string() = "sqp_create: sqp_solve kernel does not fit on the device"; return nullptr; }
         if (!s->factor_in_smem) grid = grid > 2 * 148 ? 2 * 148 : grid;
         if (grid > batch) grid = batch;
@@ -515,12 +520,12 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     ws.trace_rows = rows;
     ws.phase = nullptr;
     if (s->profiling) {
-        ok = ok && s->phase.resize(8) && rt_memset(s->phase.p, 0, 8 * sizeof(unsigned long long), st);
+        ok = ok && s->phase.resize(16) && rt_memset(s->phase.p, 0, 16 * sizeof(unsigned long long), st);
         ws.phase = s->phase.p;
     }
     // one persistent launch: CTAs draw instances from the queue and run their whole SQP loop on the device
     ok = ok && rt_event_record(s->kev0, st);
-    ok = ok && s->ocp.impl->launch_solve(s->grid, s->factor_in_smem, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
+    ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
     ok = ok && rt_event_record(s->kev1, st);
     ++launches;
     ok = ok && rt_event_record(s->ev1, st) && rt_sync(st);
@@ -530,8 +535,8 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     s->last_launches = launches;
     for (int k = 0; k < 3; ++k) { s->k_ms[k] = 0; s->k_launches[k] = 0; }
     if (s->profiling) {
-        unsigned long long ph[8];
-        if (!(rt_d2h(ph, s->phase.p, sizeof ph, st) && rt_sync(st))) return PMB_ERR_CUDA;
+        unsigned long long* ph = s->phase_host;
+        if (!(rt_d2h(ph, s->phase.p, 16 * sizeof(unsigned long long), st) && rt_sync(st))) return PMB_ERR_CUDA;
         const double tot = (double)ph[0] + (double)ph[1] + (double)ph[2];
         for (int k = 0; k < 3; ++k) { s->k_ms[k] = tot > 0 ? s->last_kernel_ms * (double)ph[k] / tot : 0.0; s->k_launches[k] = (long long)ph[3]; }
     }
@@ -574,6 +579,12 @@ int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches
 {
     if (!s || !ms || !launches) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
     for (int k = 0; k < 3; ++k) { ms[k] = s->k_ms[k]; launches[k] = s->k_launches[k]; }
+    return PMB_OK;
+}
+int pmb_sqp_get_phase_cycles(const pmb_sqp_t* s, unsigned long long* cycles16)
+{
+    if (!s || !cycles16) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    for (int k = 0; k < 16; ++k) cycles16[k] = s->phase_host[k];
     return PMB_OK;
 }
 int pmb_sqp_set_stream(pmb_sqp_t* s, void* cuda_stream)

@@ -70,6 +70,7 @@ PMB_DEV QpArgs qp_instance(const QpBatch& q, int b)
     a.x = q.x + b * N; a.y = q.y + b * n; a.info = q.info ? q.info + b : nullptr;
     a.z = q.z ? q.z + b * M : nullptr; a.q = q.q ? q.q + b * N : nullptr;
     a.perm = q.perm ? q.perm + b * n : nullptr; a.ctype = q.ctype ? q.ctype + b * n : nullptr; a.nfac = q.nfac ? q.nfac + b : nullptr;
+    a.prof = nullptr;
     return a;
 }
 
@@ -80,7 +81,7 @@ struct FactorStore {
 };
 
 /** persistent CTA-per-instance boxADMM: CTAs draw instances from an atomic queue */
-template <int R>
+template <int R, bool IN_SMEM>
 struct QpBody {
     static constexpr int THREADS = 128;
     static constexpr int MIN_BLOCKS = R <= 4 ? 4 : (R <= 6 ? 2 : 1);
@@ -90,8 +91,9 @@ struct QpBody {
     {
         Cta c(w, reinterpret_cast<double*>(smem));
         unsigned char* ws = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
-        double* Lp = fs.global ? fs.global + (size_t)blk * fs.doubles : reinterpret_cast<double*>(ws);
-        unsigned char* vec = fs.global ? ws : ws + fs.doubles * sizeof(double);
+        // IN_SMEM is a template parameter so that the factor pointer is provably a shared-memory address (LDS/STS)
+        double* Lp = IN_SMEM ? reinterpret_cast<double*>(ws) : fs.global + (size_t)blk * fs.doubles;
+        unsigned char* vec = IN_SMEM ? ws + fs.doubles * sizeof(double) : ws;
         for (;;) {
             const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (b >= batch) break;
@@ -153,7 +155,8 @@ struct SqpWs {
     int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
     double* tr_alpha;
     int trace_rows;
-    unsigned long long* phase;   // profiling: {linearise, qp, step} cycles of thread 0 summed over CTAs, [3] = instance-iterations
+    unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
+                                 // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
 };
 
 template <class O>
@@ -189,13 +192,14 @@ struct SqpSolveBody {
      *  there (mobile robot: 4 x 55 KB), 2 when the factor is in global scratch (large problems, heavy AD code) */
     static constexpr size_t SMEM_IN = Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
                                       (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
-    static constexpr int MIN_BLOCKS = SMEM_IN > 227 * 1024 ? 2 : ((228 * 1024) / SMEM_IN > 4 ? 4 : (int)((228 * 1024) / SMEM_IN));
+    static constexpr bool IN_SMEM = SMEM_IN <= 227 * 1024;    // placement of the factor, fixed per problem at compile time
+    static constexpr int MIN_BLOCKS = !IN_SMEM ? 2 : ((228 * 1024) / SMEM_IN > 4 ? 4 : (int)((228 * 1024) / SMEM_IN));
     /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors      (factor in shared memory)
      *                 Cta scratch | SQP scratch | QP vectors                              (factor in global scratch) */
-    static size_t smem_bytes(bool factor_in_smem)
+    static size_t smem_bytes()
     {
         const size_t fac = FACTOR_DOUBLES * sizeof(double);
-        const size_t first = factor_in_smem ? (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES) : SCRATCH_BYTES;
+        const size_t first = IN_SMEM ? (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES) : SCRATCH_BYTES;
         return Cta::SCRATCH_DOUBLES * sizeof(double) + first + qp_vec_bytes(O::N, O::M);
     }
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st, pmb_qp_settings_t qst,
@@ -206,7 +210,7 @@ struct SqpSolveBody {
         double* scratch = reinterpret_cast<double*>(base);
         double* Lp;
         unsigned char* vec;
-        if (fs.global) { Lp = fs.global + (size_t)blk * fs.doubles; vec = base + SCRATCH_BYTES; }
+        if (!IN_SMEM) { Lp = fs.global + (size_t)blk * fs.doubles; vec = base + SCRATCH_BYTES; }
         else {
             Lp = reinterpret_cast<double*>(base);
             const size_t fac = FACTOR_DOUBLES * sizeof(double);

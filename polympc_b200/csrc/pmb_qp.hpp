@@ -26,6 +26,10 @@
 
 namespace pmb {
 
+/** optional cycle counters of one QP solve (thread 0's clock): pivot order, gather, factorisation, triangular solves,
+ *  ADMM vector updates, residual checks */
+struct QpProf { unsigned long long pivot = 0, gather = 0, factor = 0, solve = 0, update = 0, resid = 0; };
+
 struct QpArgs {
     int N, M;
     const double *H, *h, *A, *Alb, *Aub, *xlb, *xub, *xg, *yg;   // this instance
@@ -33,6 +37,7 @@ struct QpArgs {
     pmb_qp_info_t* info;
     double *z, *q;
     int *perm, *ctype, *nfac;
+    QpProf* prof;   // thread-local accumulator or nullptr
 };
 
 namespace qpc {
@@ -76,32 +81,63 @@ PMB_DEV double dot_chain(const double* a, size_t ld, const double* x, int n)
     return acc;
 }
 
-/** replay Eigen's diagonal pivot selection on |dd| (a scratch copy of diag(K)); perm[a] = original index at position a.
- *  Executed by warp 0; ends with a block barrier. */
-PMB_DEV void ldlt_pivot_order(Cta& c, int n, double* dd, int* perm)
+/** replay Eigen's diagonal pivot selection (LDLT.h, ldlt_inplace<Lower>::unblocked: `mat.diagonal().tail(size-k).cwiseAbs()
+ *  .maxCoeff(&idx)` then a symmetric swap k <-> idx) on dd, a scratch copy of diag(K); perm[a] = original index at position a.
+ *  maxCoeff semantics: the candidate at position k is the initial best (even when it is NaN — then nothing replaces it),
+ *  a later position wins only with a strictly larger value (NaN never does).
+ *  Executed by warp 0 on registers (lane l owns positions l, l+32, ...): one step = 3 REDUX + 4 SHFL.  Ends with a block
+ *  barrier. */
+template <int R>
+PMB_DEV void ldlt_pivot_order(Cta& c, int n, const double* dd, int* perm)
 {
     if (c.warp_id() == 0) {
         const Warp& w = c.w;
         const int lane = w.lane();
-        for (int i = lane; i < n; i += 32) perm[i] = i;
-        w.sync();
-        for (int k = 0; k < n - 1; ++k) {
-            double bv = -1.0; int bi = 0x7fffffff;
-            for (int i = k + ((lane - k) & 31); i < n; i += 32) {   // positions >= k owned by this lane, ascending
-                const double v = dm::fabs(dd[i]);
-                if (v > bv) { bv = v; bi = i; }
-            }
-            for (int off = 16; off >= 1; off >>= 1) {
-                const double ov = w.shfl_xor(bv, off);
-                const int oi = w.shfl_xor(bi, off);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0 && bi != k && bi < n) {
-                const double t = dd[k]; dd[k] = dd[bi]; dd[bi] = t;
-                const int p = perm[k]; perm[k] = perm[bi]; perm[bi] = p;
-            }
-            w.sync();
+        // key: 0 = not a candidate (NaN or out of range); otherwise bits(|v|) + 1, order preserving for |v| in [0, inf]
+        unsigned hi[R], lo[R];
+        int pr[R];
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            uint64_t key = 0;
+            if (i < n) { const double v = dm::fabs(dd[i]); key = (v != v) ? 0 : dm::to_bits(v) + 1; }
+            hi[r] = (unsigned)(key >> 32); lo[r] = (unsigned)key; pr[r] = i;
         }
+        for (int k = 0; k < n - 1; ++k) {
+            const int kr = k >> 5, kl = k & 31;
+            // local best over owned positions >= k (ascending positions: first maximum wins)
+            unsigned bh = 0, bl = 0; int bp = 0x7fffffff;
+            PMB_UNROLL
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + 32 * r;
+                const bool cand = i >= k && (hi[r] | lo[r]) != 0;
+                if (cand && (hi[r] > bh || (hi[r] == bh && lo[r] > bl))) { bh = hi[r]; bl = lo[r]; bp = i; }
+            }
+            const unsigned mh = w.reduce_max(bh);
+            const unsigned ml = w.reduce_max(bh == mh ? bl : 0u);
+            const bool mine = (bh == mh) && (bl == ml) && bp != 0x7fffffff;
+            int bi = (int)w.reduce_min(mine ? (unsigned)bp : 0x7fffffffu);
+            // key / perm currently at position k
+            unsigned kh = 0, kw = 0; int kp = 0;
+            PMB_UNROLL
+            for (int r = 0; r < R; ++r) if (r == kr) { kh = hi[r]; kw = lo[r]; kp = pr[r]; }
+            kh = (unsigned)w.shfl((int)kh, kl); kw = (unsigned)w.shfl((int)kw, kl); kp = w.shfl(kp, kl);
+            if ((kh | kw) == 0 || (mh | ml) == 0) bi = k;          // NaN at k stays; nothing selectable: no swap
+            if (bi != k) {
+                const int br = bi >> 5, bl2 = bi & 31;
+                int bperm = 0;
+                PMB_UNROLL
+                for (int r = 0; r < R; ++r) if (r == br) bperm = pr[r];
+                bperm = w.shfl(bperm, bl2);
+                PMB_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    if (r == kr && lane == kl) { hi[r] = mh; lo[r] = ml; pr[r] = bperm; }
+                    if (r == br && lane == bl2) { hi[r] = kh; lo[r] = kw; pr[r] = kp; }
+                }
+            }
+        }
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) { const int i = lane + 32 * r; if (i < n) perm[i] = pr[r]; }
     }
     c.sync();
 }
@@ -127,13 +163,16 @@ PMB_DEV void kkt_gather_permuted(Cta& c, int N, int M, const double* H, const do
     c.sync();
 }
 
-/** unpivoted right-looking LDL^T on the packed lower triangle; tmp[n] scratch.  R = ceil(n / 32). */
+/** unpivoted right-looking LDL^T on the packed lower triangle; tmp[n] scratch.  R = ceil(n / 32).
+ *  Lane l owns rows l, l+32, ... (its multipliers L(i,j) stay in registers for the whole step); the columns k > j of the
+ *  trailing matrix are dealt round-robin to the warps. */
 template <int R>
 PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp, double* tmp)
 {
     const int tid = c.tid(), nt = c.nthreads(), lane = c.lane(), wid = c.warp_id(), nw = c.nwarps();
+    int bj = 0;                                    // packed_off(j, n) - j
     for (int j = 0; j < n; ++j) {
-        double* cj = Lp + packed_off(j, n) - j;   // cj[i] = L(i,j), i >= j
+        double* cj = Lp + bj;                      // cj[i] = L(i,j), i >= j
         const double dj = cj[j];
         const bool scale = dm::fabs(dj) > 0.0;
         for (int i = j + 1 + tid; i < n; i += nt) {
@@ -143,27 +182,33 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp, double* tmp)
         }
         c.sync();
         // a(i,k) = fma(-L(i,j), tmp[k], a(i,k)) for j < k <= i < n
-        for (int k = j + 1 + wid; k < n; k += nw) {
+        double nl[R];
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) { const int i = lane + 32 * r; nl[r] = (i > j && i < n) ? -cj[i] : 0.0; }
+        int k = j + 1 + wid;
+        int bk = k * n - ((k * (k + 1)) >> 1);     // packed_off(k, n) - k
+        for (; k < n; k += nw) {
             const double tk = tmp[k];
-            double* ck = Lp + packed_off(k, n) - k;
-            double av[R], lv[R];
+            double* ck = Lp + bk + lane;
             PMB_UNROLL
             for (int r = 0; r < R; ++r) {
-                const int i = k + lane + 32 * r;
-                if (i < n) { av[r] = ck[i]; lv[r] = cj[i]; }
+                if (32 * r + 31 >= k) {            // warp-uniform: chunk has rows >= k
+                    const int i = lane + 32 * r;
+                    if (i >= k && i < n) ck[32 * r] = dm::fma(nl[r], tk, ck[32 * r]);
+                }
             }
+            // advance nw columns: off(k+1) - off(k) = n - k - 1
             PMB_UNROLL
-            for (int r = 0; r < R; ++r) {
-                const int i = k + lane + 32 * r;
-                if (i < n) ck[i] = dm::fma(-lv[r], tk, av[r]);
-            }
+            for (int q = 0; q < 8; ++q) if (q < nw) bk += n - (k + q) - 1;
         }
         c.sync();
+        bj += n - j - 1;
     }
 }
 
 /** solve (P^T L D L^T P) s = rhs; `sol` holds rhs on entry and the solution on exit (unpermuted indexing).
- *  Executed by warp 0; ends with a block barrier. */
+ *  Executed by warp 0: lane l keeps components l, l+32, ... in registers; step j broadcasts the finished component with
+ *  one shuffle and applies column j (forward) / row j (backward) of L.  Ends with a block barrier. */
 template <int R>
 PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol)
 {
@@ -171,26 +216,29 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
         const Warp& w = c.w;
         const int lane = w.lane();
         double y[R];
-        int offr[R];
+        int offr[R];      // packed_off(i, n) - i of the lane's rows
         PMB_UNROLL
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
             y[r] = i < n ? sol[perm[i]] : 0.0;
-            offr[r] = i < n ? packed_off(i, n) - i : 0;
+            offr[r] = i < n ? i * n - ((i * (i + 1)) >> 1) : 0;
         }
-        // unit lower: ascending columns
-        PMB_UNROLL
-        for (int jb = 0; jb < R; ++jb) {
-            const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
-            PMB_NOUNROLL
-            for (int jj = 0; jj < jend; ++jj) {
-                const int j = jb * 32 + jj;
-                const double yj = w.shfl(y[jb], jj);
-                const double* col = Lp + packed_off(j, n) - j;
-                PMB_UNROLL
-                for (int r = jb; r < R; ++r) {
-                    const int i = lane + 32 * r;
-                    if (i > j && i < n) y[r] = dm::fma(-col[i], yj, y[r]);
+        // unit lower: ascending columns.  col_j[i] = Lp[bj + i], bj = packed_off(j) - j advances by n - j - 1
+        {
+            const double* colp = Lp + lane;
+            PMB_UNROLL
+            for (int jb = 0; jb < R; ++jb) {
+                const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
+                PMB_NOUNROLL
+                for (int jj = 0; jj < jend; ++jj) {
+                    const int j = jb * 32 + jj;
+                    const double yj = w.shfl(y[jb], jj);
+                    if (lane > jj && 32 * jb + lane < n) y[jb] = dm::fma(-colp[32 * jb], yj, y[jb]);
+                    PMB_UNROLL
+                    for (int r = jb + 1; r < R; ++r) {
+                        if (r < R - 1 || lane + 32 * r < n) y[r] = dm::fma(-colp[32 * r], yj, y[r]);
+                    }
+                    colp += n - j - 1;
                 }
             }
         }
@@ -202,7 +250,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 y[r] = (dm::fabs(di) > DBL_MIN) ? (y[r] / di) : 0.0;
             }
         }
-        // unit upper (L^T): descending columns
+        // unit upper (L^T): descending columns; lane's row i reads L(j,i) = Lp[offr + j]
         PMB_UNROLL
         for (int jb = R - 1; jb >= 0; --jb) {
             const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
@@ -211,10 +259,8 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 const int j = jb * 32 + jj;
                 const double yj = w.shfl(y[jb], jj);
                 PMB_UNROLL
-                for (int r = 0; r <= jb; ++r) {
-                    const int i = lane + 32 * r;
-                    if (i < j) y[r] = dm::fma(-Lp[offr[r] + j], yj, y[r]);
-                }
+                for (int r = 0; r < jb; ++r) y[r] = dm::fma(-Lp[offr[r] + j], yj, y[r]);
+                if (lane < jj) y[jb] = dm::fma(-Lp[offr[jb] + j], yj, y[jb]);
             }
         }
         PMB_UNROLL
@@ -286,13 +332,16 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         rho_updates += 1;
         c.sync();
     };
+    QpProf* const prof = a.prof;
     auto factorise = [&]() {
-        for (int i = tid; i < n; i += nt) tmp[i] = dK[i];
-        c.sync();
-        ldlt_pivot_order(c, n, tmp, perm);
+        const unsigned long long t0 = prof ? c.w.clock() : 0;
+        ldlt_pivot_order<R>(c, n, dK, perm);
         if (n_factor == 0 && a.perm) { for (int i = tid; i < n; i += nt) a.perm[i] = perm[i]; }
+        const unsigned long long t1 = prof ? c.w.clock() : 0;
         kkt_gather_permuted(c, N, M, a.H, a.A, dK, perm, Lp);
+        const unsigned long long t2 = prof ? c.w.clock() : 0;
         ldlt_factor_packed<R>(c, n, Lp, tmp);
+        if (prof) { const unsigned long long t3 = c.w.clock(); prof->pivot += t1 - t0; prof->gather += t2 - t1; prof->factor += t3 - t2; }
         ++n_factor;
     };
 
@@ -341,11 +390,14 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
 
     int iter;
     for (iter = 1; iter <= st.max_iter; ++iter) {
+        const unsigned long long ta = prof ? c.w.clock() : 0;
         // compute_kkt_rhs (351-355)
         for (int i = tid; i < N; i += nt) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
         for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
         c.sync();
+        const unsigned long long tb = prof ? c.w.clock() : 0;
         ldlt_solve_packed<R>(c, n, Lp, perm, sol);
+        const unsigned long long tc = prof ? c.w.clock() : 0;
         // z, y_A (126, 133-135, 142-144)
         for (int i = tid; i < M; i += nt) {
             const double zp = z[i];
@@ -366,10 +418,13 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
             yb[i] += rb[i] * (xv - qv);
         }
         c.sync();
+        if (prof) { const unsigned long long td = c.w.clock(); prof->update += (tb - ta) + (td - tc); prof->solve += tc - tb; }
 
         const bool check = (st.check_termination != 0) && (iter % st.check_termination == 0);
         if (check) {
+            const unsigned long long te = prof ? c.w.clock() : 0;
             residuals_update();
+            if (prof) prof->resid += c.w.clock() - te;
             const double eps_prim = st.eps_abs + st.eps_rel * max_Ax_z;
             const double eps_dual = st.eps_abs + st.eps_rel * max_Hx_ATy_h;
             if (res_prim <= eps_prim && res_dual <= eps_dual) { status = PMB_QP_SOLVED; break; }

@@ -19,12 +19,14 @@ struct IProblem {
     virtual void set_time_limits(double, double) = 0;
     virtual void time_nodes(double*) const = 0;
     virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
-    /** shared-memory bytes / resident CTAs of the fused SQP kernel for the two placements of the LDL^T factor */
-    virtual size_t solve_smem_bytes(bool factor_in_smem) const = 0;
+    /** placement of the LDL^T factor (shared memory, or a per-CTA global scratch slot), shared-memory bytes and resident CTAs
+     *  of the fused SQP kernel */
+    virtual bool factor_in_smem() const = 0;
+    virtual size_t solve_smem_bytes() const = 0;
     virtual size_t factor_doubles() const = 0;
-    virtual int solve_resident_ctas(bool factor_in_smem) const = 0;
+    virtual int solve_resident_ctas() const = 0;
     /** one persistent launch that solves `batch` instances (grid CTAs draw them from `queue`) */
-    virtual bool launch_solve(int grid, bool factor_in_smem, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
+    virtual bool launch_solve(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
 };
 
@@ -57,18 +59,19 @@ struct ProblemImpl : IProblem {
         return false;
     }
     using Solve = SqpSolveBody<O>;
-    size_t solve_smem_bytes(bool in_smem) const override { return Solve::smem_bytes(in_smem); }
+    bool factor_in_smem() const override { return Solve::IN_SMEM; }
+    size_t solve_smem_bytes() const override { return Solve::smem_bytes(); }
     size_t factor_doubles() const override { return Solve::FACTOR_DOUBLES; }
-    int solve_resident_ctas(bool in_smem) const override
+    int solve_resident_ctas() const override
     {
         return resident_ctas<Solve, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
-            Solve::smem_bytes(in_smem), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
+            Solve::smem_bytes(), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
     }
-    bool launch_solve(int grid, bool in_smem, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
+    bool launch_solve(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
                       int batch, int* queue, stream_t s) const override
     {
-        FactorStore fs{in_smem ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES};
-        return rt_launch<Solve>(grid, Solve::smem_bytes(in_smem), s, o, ws, st, qst, fs, batch, queue);
+        FactorStore fs{Solve::IN_SMEM ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES};
+        return rt_launch<Solve>(grid, Solve::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
     }
 };
 

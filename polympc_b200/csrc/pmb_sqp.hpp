@@ -221,6 +221,8 @@ struct SqpDev {
         qa.N = N; qa.M = M; qa.H = s.H; qa.h = s.h; qa.A = s.A; qa.Alb = s.al; qa.Aub = s.au; qa.xlb = s.lx; qa.xub = s.ux;
         qa.xg = nullptr; qa.yg = nullptr; qa.x = s.p; qa.y = s.plam; qa.info = s.qp_info; qa.z = nullptr; qa.q = nullptr;
         qa.perm = nullptr; qa.ctype = nullptr; qa.nfac = s.qp_nfac;
+        QpProf qprof;
+        qa.prof = s.phase ? &qprof : nullptr;
         c.sync();
         unsigned long long t_lin = 0, t_qp = 0, t_step = 0, n_it = 0;
         for (int it = 1; it <= st.max_iter; ++it) {
@@ -238,6 +240,9 @@ struct SqpDev {
         }
         if (s.phase && c.tid() == 0) {
             atomic_add_u64(s.phase + 0, t_lin); atomic_add_u64(s.phase + 1, t_qp); atomic_add_u64(s.phase + 2, t_step); atomic_add_u64(s.phase + 3, n_it);
+            atomic_add_u64(s.phase + 4, qprof.pivot); atomic_add_u64(s.phase + 5, qprof.gather); atomic_add_u64(s.phase + 6, qprof.factor);
+            atomic_add_u64(s.phase + 7, qprof.solve); atomic_add_u64(s.phase + 8, qprof.update); atomic_add_u64(s.phase + 9, qprof.resid);
+            atomic_add_u64(s.phase + 10, (unsigned long long)s.info->qp_solver_iter);
         }
         c.sync();
     }

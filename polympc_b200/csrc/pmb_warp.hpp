@@ -42,6 +42,9 @@ struct Warp {
     PMB_DEV bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
     PMB_DEV bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
     PMB_DEV unsigned long long clock() const { return (unsigned long long)clock64(); }
+    /** warp-wide integer reductions (REDUX.SYNC) */
+    PMB_DEV unsigned reduce_max(unsigned v) const { return __reduce_max_sync(0xffffffffu, v); }
+    PMB_DEV unsigned reduce_min(unsigned v) const { return __reduce_min_sync(0xffffffffu, v); }
 };
 
 PMB_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
@@ -199,6 +202,17 @@ struct Warp {
         return m;
     }
     unsigned long long clock() const { return 0; }
+    unsigned reduce_max(unsigned v) const
+    {
+        b->slot[t] = v;
+        sync();
+        unsigned m = 0;
+        const int base = t & ~31;
+        for (int l = 0; l < 32 && base + l < b->nthreads; ++l) { const unsigned o = (unsigned)b->slot[base + l]; if (o > m) m = o; }
+        sync();
+        return m;
+    }
+    unsigned reduce_min(unsigned v) const { return ~reduce_max(~v); }
     bool any(bool p) const { return ballot(p) != 0; }
     bool all(bool p) const { const unsigned m = ballot(p); const int cnt = (b->nthreads - (t & ~31)) >= 32 ? 32 : (b->nthreads - (t & ~31)); return m == (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)); }
 };

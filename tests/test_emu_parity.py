@@ -68,3 +68,20 @@ def test_sqp_warm_restart_and_reset_guess(emu, orc):
     for a, b, n in zip(outs[0], outs[1], ("x1", "x2", "lam2", "x3")):
         pc.assert_same(a, b, n)
     pc.assert_same(outs[0][0], outs[0][3], "reset_guess reproduces the first solve")
+
+
+def test_qp_nan_and_inf_data(emu, orc):
+    """garbage in: NaN / inf entries must flow through both sides identically (Eigen maxCoeff pivot rule with NaN, IEEE inf)"""
+    rng = np.random.default_rng(2)
+    H, h, A, Alb, Aub, xlb, xub = pc.random_qp(rng, 4, 9, 5)
+    H[0, 3, 3] = np.nan                   # NaN on the diagonal, not at the first pivot position
+    H[1, 0, 0] = np.nan                   # NaN at the first position: stays there (maxCoeff starts from it)
+    H[2, :, :] = np.nan                   # everything NaN
+    H[3, 2, 2] = 1e308; h[3, 1] = 1e308   # overflow to inf
+    st = orc.sqp_default_qp_settings(); st.max_iter = 30
+    ra = emu.qp_solve(H, h, A, Alb, Aub, xlb, xub, st)
+    rb = orc.qp_solve(H, h, A, Alb, Aub, xlb, xub, st)
+    for k in ("perm", "ctype", "n_factor", "x", "y", "z", "q"):
+        pc.assert_same(ra[k], rb[k], "qp." + k)
+    for f in ("status", "iter"):
+        pc.assert_same(ra["info"][f], rb["info"][f], "qp.info." + f)

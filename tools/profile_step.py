@@ -13,9 +13,18 @@ api = polympc_b200.load()
 w = W.WORKLOADS[name](batch)
 s = api.sqp(w.name, batch)
 W.configure(s, w)
+import os as _os
+max_iter = int(_os.environ.get("PMB_MAX_ITER", "100"))
+if max_iter != 100:
+    st = s.settings(); st.max_iter = max_iter; s.set_settings(st)
+s.set_profiling(bool(int(_os.environ.get("PMB_PROFILE", "1"))))
 for _ in range(solves):
     s.reset_guess()
     s.solve()
+ph = s.phase_cycles()
+it = max(1, ph["sqp_iterations"])
+print("cycles per SQP iteration:", {k: round(v / it) for k, v in ph.items() if k not in ("sqp_iterations", "admm_trips")},
+      "ADMM trips/iteration %.1f" % (ph["admm_trips"] / it))
 info = s.info()
 print(f"{w.name} batch={batch}: {int(info['iter'].sum())} SQP iterations, {s.last_solve_ms():.2f} ms, {s.last_solve_launches()} launches, "
       f"solved {float((info['status'] == 0).mean()):.4f}")

@@ -24,6 +24,11 @@
 #include "../../include/polympc_b200.h"
 #include <cfloat>
 
+// micro-benchmark hook (tools/ubench): expands to nothing in the product build
+#ifndef PMB_TICK
+#define PMB_TICK(k)
+#endif
+
 namespace pmb {
 
 /** optional cycle counters of one QP solve (thread 0's clock): pivot order, gather, factorisation, triangular solves,
@@ -223,6 +228,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
             y[r] = i < n ? sol[perm[i]] : 0.0;
             offr[r] = i < n ? i * n - ((i * (i + 1)) >> 1) : 0;
         }
+        PMB_TICK(0)
         // unit lower: ascending columns.  col_j[i] = Lp[bj + i], bj = packed_off(j) - j advances by n - j - 1
         {
             const double* colp = Lp + lane;
@@ -242,6 +248,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 }
             }
         }
+        PMB_TICK(1)
         PMB_UNROLL
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
@@ -250,6 +257,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 y[r] = (dm::fabs(di) > DBL_MIN) ? (y[r] / di) : 0.0;
             }
         }
+        PMB_TICK(2)
         // unit upper (L^T): descending columns; lane's row i reads L(j,i) = Lp[offr + j]
         PMB_UNROLL
         for (int jb = R - 1; jb >= 0; --jb) {
@@ -263,6 +271,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 if (lane < jj) y[jb] = dm::fma(-Lp[offr[jb] + j], yj, y[jb]);
             }
         }
+        PMB_TICK(3)
         PMB_UNROLL
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
@@ -270,6 +279,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
         }
     }
     c.sync();
+    PMB_TICK(4)
 }
 
 /** the whole boxADMM solve of one instance by one CTA.  Lp: n(n+1)/2 doubles (shared or global), vec: qp_vec_bytes() of

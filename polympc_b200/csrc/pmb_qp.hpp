@@ -168,116 +168,271 @@ PMB_DEV void kkt_gather_permuted(Cta& c, int N, int M, const double* H, const do
     c.sync();
 }
 
-/** unpivoted right-looking LDL^T on the packed lower triangle; tmp[n] scratch.  R = ceil(n / 32).
- *  Lane l owns rows l, l+32, ... (its multipliers L(i,j) stay in registers for the whole step); the columns k > j of the
- *  trailing matrix are dealt round-robin to the warps. */
+/** unpivoted right-looking LDL^T on the packed lower triangle, four columns (a panel) at a time.  R = ceil(n / 32).
+ *
+ *  Element-wise the arithmetic is exactly the column-by-column algorithm (and Eigen's left-looking inner products):
+ *  a(i,k) receives fma(-L(i,j), d_j L(k,j), .) for j ascending, L(i,j) = a(i,j) / d_j (only when |d_j| > 0).  The panel
+ *  form only changes the schedule: (P1) every thread factors the 4x4 diagonal block of the panel redundantly in
+ *  registers (no communication) and then eliminates its own row of the panel — 4 dependent divisions per row instead of
+ *  a barrier pair per column; (P2) the trailing matrix is updated once per panel: lane l keeps the 4 multipliers of its
+ *  rows l, l+32, ... in registers, the columns are dealt round-robin to the warps, and every element is read and written
+ *  once per panel (4 chained FMAs in registers) instead of once per column.  Two block barriers per panel. */
 template <int R>
-PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp, double* tmp)
+PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
 {
     const int tid = c.tid(), nt = c.nthreads(), lane = c.lane(), wid = c.warp_id(), nw = c.nwarps();
-    int bj = 0;                                    // packed_off(j, n) - j
-    for (int j = 0; j < n; ++j) {
-        double* cj = Lp + bj;                      // cj[i] = L(i,j), i >= j
-        const double dj = cj[j];
-        const bool scale = dm::fabs(dj) > 0.0;
-        for (int i = j + 1 + tid; i < n; i += nt) {
-            double v = cj[i];
-            if (scale) { v = v / dj; cj[i] = v; }
-            tmp[i] = dj * v;
+    PMB_NOUNROLL
+    for (int j0 = 0; j0 < n; j0 += 4) {
+        const int nb = (n - j0) < 4 ? (n - j0) : 4;            // columns in this panel (uniform)
+        int bc[4];                                             // packed_off(j0 + c, n) - (j0 + c)
+        bc[0] = j0 * n - ((j0 * (j0 + 1)) >> 1);
+        PMB_UNROLL
+        for (int q = 1; q < 4; ++q) bc[q] = bc[q - 1] + n - (j0 + q - 1) - 1;
+        // ---- P1a: 4x4 diagonal block, redundantly in every thread.  b[r][q] = a(j0 + r, j0 + q), q <= r
+        double b[4][4], d[4], ub[4][4];
+        bool sc[4];
+        PMB_UNROLL
+        for (int q = 0; q < 4; ++q)
+            PMB_UNROLL
+            for (int r = q; r < 4; ++r) b[r][q] = (r < nb) ? Lp[bc[q] + j0 + r] : 0.0;
+        PMB_UNROLL
+        for (int q = 0; q < 4; ++q) {
+            d[q] = b[q][q];
+            sc[q] = dm::fabs(d[q]) > 0.0;
+            PMB_UNROLL
+            for (int r = q + 1; r < 4; ++r) {
+                double v = b[r][q];
+                if (sc[q]) v = v / d[q];
+                b[r][q] = v;                                   // L(j0 + r, j0 + q)
+                ub[r][q] = d[q] * v;                           // d_q L(j0 + r, j0 + q)
+            }
+            PMB_UNROLL
+            for (int q2 = q + 1; q2 < 4; ++q2)
+                PMB_UNROLL
+                for (int r = q2; r < 4; ++r) b[r][q2] = dm::fma(-b[r][q], ub[q2][q], b[r][q2]);
+        }
+        // ---- P1b: every row below the panel eliminates its 4 panel entries (4 dependent divisions)
+        for (int i = j0 + nb + tid; i < n; i += nt) {
+            double av[4];
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) av[q] = (q < nb) ? Lp[bc[q] + i] : 0.0;
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) {
+                if (sc[q]) av[q] = av[q] / d[q];
+                PMB_UNROLL
+                for (int q2 = q + 1; q2 < 4; ++q2) av[q2] = dm::fma(-av[q], ub[q2][q], av[q2]);
+            }
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) if (q < nb) Lp[bc[q] + i] = av[q];
         }
         c.sync();
-        // a(i,k) = fma(-L(i,j), tmp[k], a(i,k)) for j < k <= i < n
-        double nl[R];
-        PMB_UNROLL
-        for (int r = 0; r < R; ++r) { const int i = lane + 32 * r; nl[r] = (i > j && i < n) ? -cj[i] : 0.0; }
-        int k = j + 1 + wid;
-        int bk = k * n - ((k * (k + 1)) >> 1);     // packed_off(k, n) - k
-        for (; k < n; k += nw) {
-            const double tk = tmp[k];
-            double* ck = Lp + bk + lane;
+        // rows inside the panel: thread r < nb stores row j0 + r of the factored diagonal block (after the barrier: every
+        // thread has read the unfactored block by now; nothing below reads these entries before the next barrier)
+        if (tid < nb) {
+            PMB_UNROLL
+            for (int r = 0; r < 4; ++r)
+                if (r == tid) {
+                    PMB_UNROLL
+                    for (int q = 0; q <= r; ++q) Lp[bc[q] + j0 + r] = (q == r) ? d[q] : b[r][q];
+                }
+        }
+        // ---- P2: trailing update, a(i,k) = fma(-L(i,j0+q), d_q L(k,j0+q), a(i,k)) for q ascending, k > panel, i >= k
+        const int kfirst = j0 + nb;
+        if (kfirst < n) {
+            double nl[R][4];
             PMB_UNROLL
             for (int r = 0; r < R; ++r) {
-                if (32 * r + 31 >= k) {            // warp-uniform: chunk has rows >= k
-                    const int i = lane + 32 * r;
-                    if (i >= k && i < n) ck[32 * r] = dm::fma(nl[r], tk, ck[32 * r]);
-                }
+                const int i = lane + 32 * r;
+                PMB_UNROLL
+                for (int q = 0; q < 4; ++q) nl[r][q] = (q < nb && i >= kfirst && i < n) ? -Lp[bc[q] + i] : 0.0;
             }
-            // advance nw columns: off(k+1) - off(k) = n - k - 1
-            PMB_UNROLL
-            for (int q = 0; q < 8; ++q) if (q < nw) bk += n - (k + q) - 1;
+            int k = kfirst + wid;
+            int bk = k * n - ((k * (k + 1)) >> 1);             // packed_off(k, n) - k
+            const int adv0 = nw * n - (nw * (nw + 1)) / 2;     // bk(k + nw) - bk(k) = nw*n - nw*k - nw(nw+1)/2
+            PMB_NOUNROLL
+            for (; k < n; k += nw) {
+                double uk[4];
+                PMB_UNROLL
+                for (int q = 0; q < 4; ++q) uk[q] = (q < nb) ? d[q] * Lp[bc[q] + k] : 0.0;
+                double* ck = Lp + bk + lane;
+                PMB_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    if (32 * r + 31 >= k) {                    // warp-uniform: chunk has rows >= k
+                        const int i = lane + 32 * r;
+                        if (i >= k && i < n) {
+                            double acc = ck[32 * r];
+                            PMB_UNROLL
+                            for (int q = 0; q < 4; ++q) if (q < nb) acc = dm::fma(nl[r][q], uk[q], acc);
+                            ck[32 * r] = acc;
+                        }
+                    }
+                }
+                bk += adv0 - nw * k;
+            }
         }
         c.sync();
-        bj += n - j - 1;
     }
 }
 
 /** solve (P^T L D L^T P) s = rhs; `sol` holds rhs on entry and the solution on exit (unpermuted indexing).
- *  Executed by warp 0: lane l keeps components l, l+32, ... in registers; step j broadcasts the finished component with
- *  one shuffle and applies column j (forward) / row j (backward) of L.  Ends with a block barrier. */
-template <int R>
-PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol)
+ *
+ *  The substitutions are a dependent chain of n steps (one shuffle + one FMA per step, ~45-60 cycles measured on B200), so
+ *  the schedule keeps that chain as short as possible and moves everything else off it.  Rows are split in chunks of 32;
+ *  chunk r belongs to warp r % NW and every thread keeps its rows in registers.  Phase p (ascending for L, descending
+ *  for L^T): (A) the owner warp substitutes through the 32x32 diagonal block of chunk p — the only serial part — and
+ *  publishes the finished components in shared memory; one block barrier; (B) every warp applies the 32 finished
+ *  columns (rows for L^T) to the chunks it owns further down (up) — 32 independent-of-other-warps FMAs per row, which
+ *  overlap with the next owner's diagonal block.  Every component still receives exactly the same fused multiply-adds
+ *  in exactly the same order as the plain column-by-column substitution: results are bit-identical to the oracle.
+ *  The division by D is spread over the whole block (an fp64 division is ~125 cycles).  Ends with a block barrier. */
+template <int R, int NW = 4>
+PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol, double* ybuf /* n doubles, shared */)
 {
-    if (c.warp_id() == 0) {
-        const Warp& w = c.w;
-        const int lane = w.lane();
-        double y[R];
-        int offr[R];      // packed_off(i, n) - i of the lane's rows
-        PMB_UNROLL
-        for (int r = 0; r < R; ++r) {
-            const int i = lane + 32 * r;
-            y[r] = i < n ? sol[perm[i]] : 0.0;
-            offr[r] = i < n ? i * n - ((i * (i + 1)) >> 1) : 0;
-        }
-        PMB_TICK(0)
-        // unit lower: ascending columns.  col_j[i] = Lp[bj + i], bj = packed_off(j) - j advances by n - j - 1
-        {
-            const double* colp = Lp + lane;
-            PMB_UNROLL
-            for (int jb = 0; jb < R; ++jb) {
-                const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
-                PMB_NOUNROLL
-                for (int jj = 0; jj < jend; ++jj) {
-                    const int j = jb * 32 + jj;
-                    const double yj = w.shfl(y[jb], jj);
-                    if (lane > jj && 32 * jb + lane < n) y[jb] = dm::fma(-colp[32 * jb], yj, y[jb]);
-                    PMB_UNROLL
-                    for (int r = jb + 1; r < R; ++r) {
-                        if (r < R - 1 || lane + 32 * r < n) y[r] = dm::fma(-colp[32 * r], yj, y[r]);
-                    }
-                    colp += n - j - 1;
-                }
-            }
-        }
-        PMB_TICK(1)
-        PMB_UNROLL
-        for (int r = 0; r < R; ++r) {
-            const int i = lane + 32 * r;
-            if (i < n) {
-                const double di = Lp[offr[r] + i];
-                y[r] = (dm::fabs(di) > DBL_MIN) ? (y[r] / di) : 0.0;
-            }
-        }
-        PMB_TICK(2)
-        // unit upper (L^T): descending columns; lane's row i reads L(j,i) = Lp[offr + j]
-        PMB_UNROLL
-        for (int jb = R - 1; jb >= 0; --jb) {
-            const int jend = (n - jb * 32) < 32 ? (n - jb * 32) : 32;
+    constexpr int RW = (R + NW - 1) / NW;        // chunks per warp
+    const Warp& w = c.w;
+    const int lane = w.lane(), wid = c.warp_id();
+    double y[RW];
+    int offr[RW];      // packed_off(i, n) - i of the thread's rows
+    PMB_UNROLL
+    for (int s = 0; s < RW; ++s) {
+        const int i = lane + 32 * (wid + NW * s);
+        y[s] = i < n ? sol[perm[i]] : 0.0;
+        offr[s] = i < n ? i * n - ((i * (i + 1)) >> 1) : 0;
+    }
+    PMB_TICK(0)
+    // ---- unit lower, ascending.  L(i,j) = Lp[bc(j) + i], bc(j) = packed_off(j) - j, bc(j+1) = bc(j) + n - j - 1
+    PMB_UNROLL
+    for (int p = 0; p < R; ++p) {
+        const int j0 = 32 * p;
+        const int jend = (n - j0) < 32 ? (n - j0) : 32;
+        const int bc0 = j0 * n - ((j0 * (j0 + 1)) >> 1);
+#ifdef PMB_UB_SKIP
+        if (!(PMB_UB_SKIP & 1))
+#endif
+        if (wid == p % NW) {                                  // (A) diagonal block of chunk p
+            const int s = p / NW;   // compile-time after unrolling
+            double yy = y[s];
+            // four columns at a time: the 4 partial components are broadcast with independent shuffles, every lane
+            // finishes the 4x4 triangle in registers (same FMAs, same order as the owner lane would do), then the
+            // rows below apply the four columns in ascending order — one shuffle latency per 4 steps instead of per step
+            int cb = bc0 + j0;                                // bc(j) + j0 for the block's first column j
+            int step = n - j0 - 1;                            // bc(j+1) - bc(j)
+            int l0 = 0;
             PMB_NOUNROLL
-            for (int jj = jend - 1; jj >= 0; --jj) {
-                const int j = jb * 32 + jj;
-                const double yj = w.shfl(y[jb], jj);
-                PMB_UNROLL
-                for (int r = 0; r < jb; ++r) y[r] = dm::fma(-Lp[offr[r] + j], yj, y[r]);
-                if (lane < jj) y[jb] = dm::fma(-Lp[offr[jb] + j], yj, y[jb]);
+            for (; l0 + 4 <= jend; l0 += 4) {
+                const int c0 = cb, c1 = c0 + step, c2 = c1 + step - 1, c3 = c2 + step - 2;
+                double y0 = w.shfl(yy, l0), y1 = w.shfl(yy, l0 + 1), y2 = w.shfl(yy, l0 + 2), y3 = w.shfl(yy, l0 + 3);
+                const double d10 = Lp[c0 + l0 + 1], d20 = Lp[c0 + l0 + 2], d30 = Lp[c0 + l0 + 3];
+                const double d21 = Lp[c1 + l0 + 2], d31 = Lp[c1 + l0 + 3], d32 = Lp[c2 + l0 + 3];
+                // branch-free: lanes that are not below the block read a valid dummy row and discard the result
+                const bool below = lane >= l0 + 4 && lane < jend;
+                const int il = below ? lane : l0 + 3;
+                const double e0 = Lp[c0 + il], e1 = Lp[c1 + il], e2 = Lp[c2 + il], e3 = Lp[c3 + il];
+                y1 = dm::fma(-d10, y0, y1);
+                y2 = dm::fma(-d20, y0, y2); y2 = dm::fma(-d21, y1, y2);
+                y3 = dm::fma(-d30, y0, y3); y3 = dm::fma(-d31, y1, y3); y3 = dm::fma(-d32, y2, y3);
+                double t = dm::fma(-e0, y0, yy); t = dm::fma(-e1, y1, t); t = dm::fma(-e2, y2, t); t = dm::fma(-e3, y3, t);
+                const double own = lane == l0 + 1 ? y1 : (lane == l0 + 2 ? y2 : (lane == l0 + 3 ? y3 : yy));
+                yy = below ? t : own;
+                cb = c3 + step - 3; step -= 4;
             }
+            const double* colp = Lp + cb + lane;              // remaining (< 4) columns one by one
+            PMB_NOUNROLL
+            for (int jj = l0; jj < jend; ++jj) {
+                const double yj = w.shfl(yy, jj);
+                if (lane > jj && lane < jend) yy = dm::fma(-colp[0], yj, yy);
+                colp += step; --step;
+            }
+            y[s] = yy;
+            if (lane < jend) ybuf[j0 + lane] = yy;
         }
-        PMB_TICK(3)
+        c.sync();
         PMB_UNROLL
-        for (int r = 0; r < R; ++r) {
+#ifdef PMB_UB_SKIP
+        if (!(PMB_UB_SKIP & 2))
+#endif
+        for (int s = 0; s < RW; ++s) {                        // (B) columns of chunk p -> owned chunks below
+            const int r = wid + NW * s;
             const int i = lane + 32 * r;
-            if (i < n) sol[perm[i]] = y[r];
+            if (r > p && r < R && i < n) {                    // chunk p has rows below it, so it is a full chunk: 32 columns
+                const double* colp = Lp + bc0 + i;
+                const double* yp = ybuf + j0;
+                double yy = y[s];
+                int step = n - j0 - 1;
+                PMB_UNROLL
+                for (int jj = 0; jj < 32; ++jj) { yy = dm::fma(-colp[0], yp[jj], yy); colp += step; --step; }
+                y[s] = yy;
+            }
         }
     }
+    PMB_TICK(1)
+    // ---- D^-1 (component zeroed when |d| <= DBL_MIN, like Eigen's LDLT::solve): every thread divides its own rows
+    PMB_UNROLL
+    for (int s = 0; s < RW; ++s) {
+        const int i = lane + 32 * (wid + NW * s);
+#ifdef PMB_UB_SKIP
+        if (PMB_UB_SKIP & 4) { if (i < n) y[s] = y[s] * Lp[offr[s] + i]; } else
+#endif
+        if (i < n) { const double di = Lp[offr[s] + i]; y[s] = (dm::fabs(di) > DBL_MIN) ? (y[s] / di) : 0.0; }
+    }
+    PMB_TICK(2)
+    // ---- unit upper (L^T), descending.  The thread's row i reads L(j,i) = Lp[offr + j]
+    PMB_UNROLL
+    for (int p = R - 1; p >= 0; --p) {
+        const int j0 = 32 * p;
+        const int jend = (n - j0) < 32 ? (n - j0) : 32;
+        if (wid == p % NW) {
+            const int s = p / NW;   // compile-time after unrolling
+            const double* rowp = Lp + offr[s] + j0;           // L(j0 + jj, i)
+            double yy = y[s];
+            const int full = jend & ~3;
+            PMB_NOUNROLL
+            for (int jj = jend - 1; jj >= full; --jj) {       // trailing (< 4) columns one by one
+                const double yj = w.shfl(yy, jj);
+                if (lane < jj) yy = dm::fma(-rowp[jj], yj, yy);
+            }
+            PMB_NOUNROLL
+            for (int l0 = full - 4; l0 >= 0; l0 -= 4) {       // four columns at a time, descending (see the forward sweep)
+                const int j = j0 + l0;
+                const int c0 = j * n - ((j * (j + 1)) >> 1), c1 = c0 + (n - j - 1), c2 = c1 + (n - j - 2);
+                double y0 = w.shfl(yy, l0), y1 = w.shfl(yy, l0 + 1), y2 = w.shfl(yy, l0 + 2), y3 = w.shfl(yy, l0 + 3);
+                const double d10 = Lp[c0 + j + 1], d20 = Lp[c0 + j + 2], d30 = Lp[c0 + j + 3];
+                const double d21 = Lp[c1 + j + 2], d31 = Lp[c1 + j + 3], d32 = Lp[c2 + j + 3];
+                const bool above = lane < l0;
+                const double* rp = above ? rowp : Lp + c0 + j0;       // dummy: L(j0 + l0 + t, j), valid entries of column j
+                const double e0 = rp[l0], e1 = rp[l0 + 1], e2 = rp[l0 + 2], e3 = rp[l0 + 3];
+                y2 = dm::fma(-d32, y3, y2);
+                y1 = dm::fma(-d31, y3, y1); y1 = dm::fma(-d21, y2, y1);
+                y0 = dm::fma(-d30, y3, y0); y0 = dm::fma(-d20, y2, y0); y0 = dm::fma(-d10, y1, y0);
+                double t = dm::fma(-e3, y3, yy); t = dm::fma(-e2, y2, t); t = dm::fma(-e1, y1, t); t = dm::fma(-e0, y0, t);
+                const double own = lane == l0 ? y0 : (lane == l0 + 1 ? y1 : (lane == l0 + 2 ? y2 : yy));
+                yy = above ? t : own;
+            }
+            y[s] = yy;
+            if (lane < jend) ybuf[j0 + lane] = yy;
+        }
+        c.sync();
+        PMB_UNROLL
+        for (int s = 0; s < RW; ++s) {
+            const int r = wid + NW * s;
+            if (r < p) {
+                const double* rowp = Lp + offr[s] + j0;
+                const double* yp = ybuf + j0;
+                double yy = y[s];
+                if (p == R - 1) {                             // only the last chunk can be partial
+                    PMB_UNROLL
+                    for (int jj = 31; jj >= 0; --jj) if (jj < jend) yy = dm::fma(-rowp[jj], yp[jj], yy);
+                } else {
+                    PMB_UNROLL
+                    for (int jj = 31; jj >= 0; --jj) yy = dm::fma(-rowp[jj], yp[jj], yy);
+                }
+                y[s] = yy;
+            }
+        }
+    }
+    PMB_TICK(3)
+    // every chunk's final values are in ybuf (published in its phase, visible after that phase's barrier)
+    for (int i = c.tid(); i < n; i += c.nthreads()) sol[perm[i]] = ybuf[i];
     c.sync();
     PMB_TICK(4)
 }
@@ -350,7 +505,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         const unsigned long long t1 = prof ? c.w.clock() : 0;
         kkt_gather_permuted(c, N, M, a.H, a.A, dK, perm, Lp);
         const unsigned long long t2 = prof ? c.w.clock() : 0;
-        ldlt_factor_packed<R>(c, n, Lp, tmp);
+        ldlt_factor_packed<R>(c, n, Lp);
         if (prof) { const unsigned long long t3 = c.w.clock(); prof->pivot += t1 - t0; prof->gather += t2 - t1; prof->factor += t3 - t2; }
         ++n_factor;
     };
@@ -406,7 +561,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
         c.sync();
         const unsigned long long tb = prof ? c.w.clock() : 0;
-        ldlt_solve_packed<R>(c, n, Lp, perm, sol);
+        ldlt_solve_packed<R>(c, n, Lp, perm, sol, tmp);
         const unsigned long long tc = prof ? c.w.clock() : 0;
         // z, y_A (126, 133-135, 142-144)
         for (int i = tid; i < M; i += nt) {

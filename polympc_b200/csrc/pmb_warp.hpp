@@ -23,6 +23,7 @@
 #define PMB_DEV_NOINLINE __device__ __noinline__
 #define PMB_UNROLL _Pragma("unroll")
 #define PMB_NOUNROLL _Pragma("unroll 1")
+#define PMB_UNROLL4 _Pragma("unroll 4")
 
 namespace pmb {
 
@@ -104,6 +105,7 @@ inline int resident_ctas(size_t smem, Args...)
 #define PMB_DEV_NOINLINE
 #define PMB_UNROLL
 #define PMB_NOUNROLL
+#define PMB_UNROLL4
 
 namespace pmb {
 

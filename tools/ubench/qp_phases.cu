@@ -5,6 +5,9 @@ __device__ long long g_tick[8];
 #define PMB_TICK(k) if (threadIdx.x == 0) g_tick[k] = clock64();
 #include "../../polympc_b200/csrc/pmb_qp.hpp"
 using namespace pmb;
+#ifndef NREP
+#define NREP 10
+#endif
 template <int R, int NT>
 __global__ void __launch_bounds__(NT, 4) phases(int n, const double* Kin, long long* cyc, double* out)
 {
@@ -24,11 +27,11 @@ __global__ void __launch_bounds__(NT, 4) phases(int n, const double* Kin, long l
     for (int i = threadIdx.x; i < n; i += NT) perm[i] = i;
     __syncthreads();
     long long t2 = clock64();
-    ldlt_factor_packed<R>(c, n, Lp, tmp);
+    ldlt_factor_packed<R>(c, n, Lp);
     long long t3 = clock64();
-    for (int rep = 0; rep < 10; ++rep) ldlt_solve_packed<R>(c, n, Lp, perm, sol);
+    for (int rep = 0; rep < NREP; ++rep) ldlt_solve_packed<R>(c, n, Lp, perm, sol, tmp);
     long long t4 = clock64();
-    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t3 - t2; cyc[2] = (t4 - t3) / 10; }
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t3 - t2; cyc[2] = (t4 - t3) / NREP; }
     for (int i = threadIdx.x; i < n; i += NT) out[i] = sol[i];
 }
 int main()

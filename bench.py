@@ -13,7 +13,8 @@ the same initial guess.  metric = sum over instances of sqp_info.iter / time.
   e2e   : the same solves through the C ABI with HOST buffers: every step copies x0 / guesses host->device
           (pmb_sqp_set_initial_conditions, pmb_sqp_set_primal, pmb_sqp_set_dual) and reads iterates and info back
           (pmb_sqp_get_primal, pmb_sqp_get_info) inside the timed region.
-  roofline     : the dominant kernel of the step (qp_box_admm), CUDA-event time per launch (pmb_sqp_set_profiling).
+  roofline     : the dominant kernel of the step (the fused persistent sqp_solve), CUDA-event time per launch and its
+                 phase split from SM cycle counters (pmb_sqp_set_profiling).
   kkt_kernel   : the materialising KKT kernel of the metric's second half (pmb_kkt_assemble_dev, box_admm.hpp:207-223),
                  B_KKT = 8 (N^2 + M N + (N+M)^2) bytes per instance, device-resident inputs larger than L2.
   cpu_baseline : the CPU restatement of the reference algorithm (oracle/, Eigen is not available so the reference itself
@@ -269,33 +270,46 @@ def run_gpu(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = sum_over_ranks(float(e2e_iters)) / (ms_e2e * 1e-3)
 
-    # ---- per-kernel device time (roofline of the dominant kernel) --------------------------------------------------------------
+    # ---- roofline of the dominant (only) kernel of the step: the fused persistent sqp_solve ---------------------------------------
+    # CUDA-event time of the kernel alone (pmb_sqp_set_profiling brackets the launch) and its phase split (SM cycle counters)
     s.set_profiling(True)
-    kt = {}
+    k_ms, k_n, phases = 0.0, 0, {}
     for _ in range(2):
         s.reset_guess(); s.solve()
-        for k, (ms, n) in s.kernel_times().items():
-            a = kt.setdefault(k, [0.0, 0]); a[0] += ms; a[1] += n
+        kt = s.kernel_times()
+        k_ms += sum(v[0] for v in kt.values()); k_n += 1
+        for k, v in s.phase_cycles().items():
+            phases[k] = phases.get(k, 0) + v
     s.set_profiling(False)
-    qp_info = None
     N, M = dims["N"], dims["M"]
     peak, peak_src = hbm_peak()
-    tot_ms = sum(v[0] for v in kt.values())
-    dom = max(kt, key=lambda k: kt[k][0])
-    # algorithmic bytes of one qp_box_admm launch per instance: read H (8N^2), A (8MN), h/Alb/Aub/xlb/xub, write x (N), y (N+M), info
-    qp_bytes_inst = 8 * (N * N + M * N + 3 * N + 2 * M + N + (N + M)) + 40
-    lin_bytes_inst = 8 * (2 * N * N + M * N + 8 * N + 3 * M)     # BFGS update reads+writes H, writes A, vectors
-    step_bytes_inst = 8 * (6 * N + 4 * (N + M))
-    per_inst = {"qp_box_admm": qp_bytes_inst, "sqp_linearise": lin_bytes_inst, "sqp_linesearch_step": step_bytes_inst}[dom]
-    # active instances per launch vary (converged instances leave the batch): bytes per launch = mean active * bytes/instance
-    mean_active = iters_per_solve / max(1, kt[dom][1] // 2)
-    dom_ms = kt[dom][0] / max(1, kt[dom][1])
-    achieved = mean_active * per_inst / (dom_ms * 1e-3) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "avg_launch_ms": dom_ms, "bytes_per_instance": per_inst, "mean_instances_per_launch": mean_active,
-                "kernel_share_of_step": {k: v[0] / tot_ms for k, v in kt.items()},
-                "note": "fused design: K is built, factored and used in shared memory and never written to HBM, so the kernel is "
-                        "fp64-latency bound, not HBM bound; the HBM-bound materialising KKT kernel is reported under kkt_kernel"}
+    kernel_ms = k_ms / k_n
+    # algorithmic bytes per SQP iteration (compulsory state traffic, fp64):
+    #   read+write x, lam, H, lag_grad_prev, step ; read lbx, ubx, lbg, ubg, d
+    b_iter = 8 * (2 * (N * N + 4 * N + M) + 2 * N + dims["ND"])
+    # flops per SQP iteration: QP = K^3/3 + trips (2 K^2 + 2 K) + floor(trips/10) 2 (2 M N + N^2); + BFGS and A^T lam
+    it_n = max(1, phases.get("sqp_iterations", 1))
+    trips = phases.get("admm_trips", 0) / it_n
+    K = N + M
+    flops_iter = K ** 3 / 3 + trips * (2 * K * K + 2 * K) + (trips / 10) * 2 * (2 * M * N + N * N) + 6 * N * N + 2 * M * N
+    achieved = iters_per_solve * b_iter / (kernel_ms * 1e-3) / 1e9
+    cyc_tot = sum(phases.get(k, 0) for k in ("linearise", "qp", "step")) or 1
+    roofline = {"kernel": "sqp_solve (fused persistent kernel: linearise + boxADMM/LDLT + line search, one CTA per instance)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": kernel_ms, "bytes_per_sqp_iteration": b_iter,
+                "sqp_iterations_per_launch": iters_per_solve,
+                "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
+                "phase_share": {k: phases.get(k, 0) / cyc_tot for k in ("linearise", "qp", "step")},
+                "qp_phase_share": {k: phases.get(k, 0) / max(1, phases.get("qp", 1)) for k in
+                                   ("qp_pivot", "qp_gather", "qp_factor", "qp_solve", "qp_update", "qp_resid")},
+                "admm_trips_per_iteration": trips,
+                "fp64": {"achieved_tflops": iters_per_solve * flops_iter / (kernel_ms * 1e-3) / 1e12, "peak_tflops": 37.07,
+                         "peak_source": "measured on this pool's B200 with tools/ubench/lat.cu (fp64 FMA, all SMs)",
+                         "flops_per_sqp_iteration": flops_iter},
+                "note": "fused design: K is built, factored and used in shared memory and never written to HBM; per-iteration state "
+                        "stays in L2.  The kernel is bound by the latency of dependent fp64 operations (triangular solves, "
+                        "division chain of the LDLT), not by HBM or fp64 throughput; the HBM-bound materialising KKT kernel is "
+                        "reported under kkt_kernel"}
 
     # ---- the materialising KKT kernel (a17), device-resident, B_KKT bytes per instance ----------------------------------------------
     kkt = None

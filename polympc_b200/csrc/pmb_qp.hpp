@@ -240,9 +240,11 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
         const int kfirst = j0 + nb;
         if (kfirst < n) {
             double nl[R][4];
+            int ic[R];                                         // the lane's row in chunk r, clamped into the matrix
             PMB_UNROLL
             for (int r = 0; r < R; ++r) {
                 const int i = lane + 32 * r;
+                ic[r] = i < n ? i : n - 1;
                 PMB_UNROLL
                 for (int q = 0; q < 4; ++q) nl[r][q] = (q < nb && i >= kfirst && i < n) ? -Lp[bc[q] + i] : 0.0;
             }
@@ -254,17 +256,25 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
                 double uk[4];
                 PMB_UNROLL
                 for (int q = 0; q < 4; ++q) uk[q] = (q < nb) ? d[q] * Lp[bc[q] + k] : 0.0;
-                double* ck = Lp + bk + lane;
+                double* ck = Lp + bk;
+                const int c0 = k >> 5;                         // first chunk with rows >= k (warp-uniform)
+                // one uniform dispatch per column, then straight-line code: unconditional loads (rows above the
+                // diagonal read the tail of earlier columns — valid memory, discarded), 4 chained FMAs, predicated stores
                 PMB_UNROLL
-                for (int r = 0; r < R; ++r) {
-                    if (32 * r + 31 >= k) {                    // warp-uniform: chunk has rows >= k
-                        const int i = lane + 32 * r;
-                        if (i >= k && i < n) {
-                            double acc = ck[32 * r];
-                            PMB_UNROLL
-                            for (int q = 0; q < 4; ++q) if (q < nb) acc = dm::fma(nl[r][q], uk[q], acc);
-                            ck[32 * r] = acc;
+                for (int r0 = 0; r0 < R; ++r0) {
+                    if (c0 == r0) {
+                        double acc[R];
+                        PMB_UNROLL
+                        for (int r = r0; r < R; ++r) acc[r] = ck[ic[r]];
+                        PMB_UNROLL
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < nb) {
+                                PMB_UNROLL
+                                for (int r = r0; r < R; ++r) acc[r] = dm::fma(nl[r][q], uk[q], acc[r]);
+                            }
                         }
+                        PMB_UNROLL
+                        for (int r = r0; r < R; ++r) { const int i = lane + 32 * r; if (i >= k && i < n) ck[i] = acc[r]; }
                     }
                 }
                 bk += adv0 - nw * k;
@@ -515,7 +525,6 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     for (int i = tid; i < N; i += nt) { double v = a.H[i + (size_t)i * N]; v += st.sigma; v += rb[i]; dK[i] = v; }
     for (int i = tid; i < M; i += nt) dK[N + i] = -rvi[i];
     c.sync();
-    factorise();
 
     int status = PMB_QP_UNSOLVED;
     double res_prim = 1.0, res_dual = 1.0, rho_estimate = 0.0, max_Ax_z = 0.0, max_Hx_ATy_h = 0.0;
@@ -553,8 +562,15 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         res_dual = m[rd];
     };
 
+    // The loop has ONE call site for the factorisation and one for the residuals (code size: the kernel's hot loops must
+    // stay resident in the instruction cache).  The reference factorises before the loop and again right after a rho
+    // update; doing it at the top of the next trip (also when that trip is not executed any more) is the same sequence of
+    // operations.
+    bool need_factor = true;
     int iter;
-    for (iter = 1; iter <= st.max_iter; ++iter) {
+    for (iter = 1; ; ++iter) {
+        if (need_factor) { factorise(); need_factor = false; }
+        if (iter > st.max_iter) break;
         const unsigned long long ta = prof ? c.w.clock() : 0;
         // compute_kkt_rhs (351-355)
         for (int i = tid; i < N; i += nt) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
@@ -586,16 +602,18 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         if (prof) { const unsigned long long td = c.w.clock(); prof->update += (tb - ta) + (td - tc); prof->solve += tc - tb; }
 
         const bool check = (st.check_termination != 0) && (iter % st.check_termination == 0);
-        if (check) {
+        const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
+        if (check || adapt) {
             const unsigned long long te = prof ? c.w.clock() : 0;
             residuals_update();
             if (prof) prof->resid += c.w.clock() - te;
+        }
+        if (check) {
             const double eps_prim = st.eps_abs + st.eps_rel * max_Ax_z;
             const double eps_dual = st.eps_abs + st.eps_rel * max_Hx_ATy_h;
             if (res_prim <= eps_prim && res_dual <= eps_dual) { status = PMB_QP_SOLVED; break; }
         }
-        if (st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0)) {
-            if (!check) residuals_update();
+        if (adapt) {
             const double rp_norm = res_prim / (max_Ax_z + qpc::DIV_BY_ZERO_REGUL);
             const double rd_norm = res_dual / (max_Hx_ATy_h + qpc::DIV_BY_ZERO_REGUL);
             double new_rho = rho * dm::sqrt(rp_norm / (rd_norm + qpc::DIV_BY_ZERO_REGUL));
@@ -609,7 +627,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
                 for (int i = tid; i < N; i += nt) dK[i] += (rb[i] - tmp[i]);
                 for (int i = tid; i < M; i += nt) dK[N + i] = -rvi[i];
                 c.sync();
-                factorise();
+                need_factor = true;
             }
         }
     }

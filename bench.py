@@ -185,13 +185,9 @@ def run_gpu(args):
     lo, hi = W.shard_bounds(B * world, world, rank)
 
     # shared Chebyshev tables: computed on rank 0, broadcast once at init, checked against the local tables (north_star)
+    from polympc_b200 import distributed as PD
     dims = api.dims(w_all.name)
-    nodes, Dm, wts = api.cheb_tables(dims["P"])
-    tab = torch.tensor(np.concatenate([nodes, Dm.ravel(), wts]), device=dev)
-    if world > 1:
-        ref_tab = tab.clone()
-        dist.broadcast(ref_tab, src=0)
-        assert torch.equal(ref_tab, tab), "Chebyshev tables differ across ranks"
+    PD.broadcast_tables(api, dims["P"], device=dev)
 
     stream = torch.cuda.Stream(device=dev)     # the engine launches on this stream, the events below are recorded on it
     torch.cuda.set_stream(stream)
@@ -213,18 +209,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return PD.max_over_ranks(v, device=dev)
 
     def sum_over_ranks(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return PD.sum_over_ranks(v, device=dev)
 
     # ---- device-resident throughput ("value") -----------------------------------------------------------------------
     for _ in range(args.warmup):

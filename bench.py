@@ -360,6 +360,17 @@ def run_gpu(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version banner) is
+    # sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(real_stdout, "w")
+    _print = print
+
+    def emit(line):
+        _print(line, file=json_out, flush=True)
+
+    globals()["print"] = lambda *a, **k: emit(a[0]) if (len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{")) else _print(*a, **k)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

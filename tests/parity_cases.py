@@ -11,8 +11,8 @@ PROBLEM_SETUP = {
     "mobile_robot_5x2": dict(t=(0.0, 1.0), d=1.0),
     "mobile_robot_5x3": dict(t=(0.0, 2.0), d=2.0),
     "cstr_5x2": dict(t=(0.0, 100.0), d=None),
-    "kite_4x2": dict(t=(0.0, 1.0), d=4.0),
-    "kite_12x1": dict(t=(0.0, 1.0), d=4.0),
+    "kite_4x2": dict(t=(0.0, 0.5), d=4.0),
+    "kite_12x1": dict(t=(0.0, 0.5), d=4.0),
 }
 
 

@@ -66,8 +66,8 @@ struct Ocp {
 template <class O> PMB_HD int var_index(int k, int a)
 { return a < O::NX ? k * O::NX + a : (a < O::NX + O::NU ? O::VARX + k * O::NU + (a - O::NX) : O::VARX + O::VARU + (a - O::NX - O::NU)); }
 
-/** The cold exact-Hessian path (first SQP iteration only) is NOT inlined, to keep the fused kernel's hot loops compact.
- *  (Out-lining the small evaluators as well was measured slower: the call ABI costs more than the instruction-cache misses.) */
+/** Everything is inlined into the fused kernel on purpose: out-lining the evaluators (or only the cold exact-Hessian path)
+ *  was measured slower — passing the problem descriptor by reference moves it from the constant bank to local memory. */
 template <class O>
 struct OcpEval {
     static constexpr int NX = O::NX, NU = O::NU, NP = O::NP, NG = O::NG, P = O::P, S = O::S, NN = O::NN;
@@ -280,7 +280,7 @@ struct OcpEval {
      *  nested dual is computed independently of the others, so the CTA instead spreads the NN*NDIR (node, Hessian
      *  column) pairs over all its threads and evaluates the functors on Dual<ad1,1>: identical arithmetic per entry,
      *  (NX+NU)x less live state per thread, and every thread busy even when NN < 32. */
-    PMB_DEV_NOINLINE static double cost_gradient_hessian(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
+    PMB_DEV static double cost_gradient_hessian(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
                                                 double* grad, double* H, double* nv /* shared scratch, NV_DOUBLES */)
     {
         const int tid = cta.tid(), nt = cta.nthreads();

@@ -188,42 +188,65 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
         bc[0] = j0 * n - ((j0 * (j0 + 1)) >> 1);
         PMB_UNROLL
         for (int q = 1; q < 4; ++q) bc[q] = bc[q - 1] + n - (j0 + q - 1) - 1;
-        // ---- P1a: 4x4 diagonal block, redundantly in every thread.  b[r][q] = a(j0 + r, j0 + q), q <= r
+        // ---- P1: the 4x4 diagonal block (redundantly in every thread, b[r][q] = a(j0 + r, j0 + q), q <= r) and the thread's
+        // own row below the panel are eliminated together, straight-line and branch-free, so that the divisions of one
+        // elimination step (3 + 1, 2 + 1, 1 + 1, 1) are independent and overlap: 4 division latencies per panel.
         double b[4][4], d[4], ub[4][4];
         bool sc[4];
         PMB_UNROLL
         for (int q = 0; q < 4; ++q)
             PMB_UNROLL
             for (int r = q; r < 4; ++r) b[r][q] = (r < nb) ? Lp[bc[q] + j0 + r] : 0.0;
+        const int i0 = j0 + nb + tid;                          // the thread's first row below the panel
+        const bool own = i0 < n;
+        const int i0c = own ? i0 : n - 1;                      // clamped: loads stay inside the matrix, stores are predicated
+        double av[4];
+        PMB_UNROLL
+        for (int q = 0; q < 4; ++q) av[q] = (q < nb) ? Lp[bc[q] + i0c] : 0.0;
         PMB_UNROLL
         for (int q = 0; q < 4; ++q) {
             d[q] = b[q][q];
             sc[q] = dm::fabs(d[q]) > 0.0;
             PMB_UNROLL
             for (int r = q + 1; r < 4; ++r) {
-                double v = b[r][q];
-                if (sc[q]) v = v / d[q];
+                const double v0 = b[r][q];
+#ifdef PMB_UB_SKIP
+                const double v = (PMB_UB_SKIP & 32) ? v0 * d[q] : (sc[q] ? v0 / d[q] : v0);
+#else
+                const double v = sc[q] ? v0 / d[q] : v0;       // division issued unconditionally, result selected
+#endif
                 b[r][q] = v;                                   // L(j0 + r, j0 + q)
                 ub[r][q] = d[q] * v;                           // d_q L(j0 + r, j0 + q)
             }
-            PMB_UNROLL
-            for (int q2 = q + 1; q2 < 4; ++q2)
-                PMB_UNROLL
-                for (int r = q2; r < 4; ++r) b[r][q2] = dm::fma(-b[r][q], ub[q2][q], b[r][q2]);
-        }
-        // ---- P1b: every row below the panel eliminates its 4 panel entries (4 dependent divisions)
-        for (int i = j0 + nb + tid; i < n; i += nt) {
-            double av[4];
-            PMB_UNROLL
-            for (int q = 0; q < 4; ++q) av[q] = (q < nb) ? Lp[bc[q] + i] : 0.0;
-            PMB_UNROLL
-            for (int q = 0; q < 4; ++q) {
-                if (sc[q]) av[q] = av[q] / d[q];
-                PMB_UNROLL
-                for (int q2 = q + 1; q2 < 4; ++q2) av[q2] = dm::fma(-av[q], ub[q2][q], av[q2]);
+            {
+#ifdef PMB_UB_SKIP
+                av[q] = (PMB_UB_SKIP & 16) ? av[q] * d[q] : (sc[q] ? av[q] / d[q] : av[q]);
+#else
+                av[q] = sc[q] ? av[q] / d[q] : av[q];
+#endif
             }
             PMB_UNROLL
-            for (int q = 0; q < 4; ++q) if (q < nb) Lp[bc[q] + i] = av[q];
+            for (int q2 = q + 1; q2 < 4; ++q2) {
+                PMB_UNROLL
+                for (int r = q2; r < 4; ++r) b[r][q2] = dm::fma(-b[r][q], ub[q2][q], b[r][q2]);
+                av[q2] = dm::fma(-av[q], ub[q2][q], av[q2]);
+            }
+        }
+        PMB_UNROLL
+        for (int q = 0; q < 4; ++q) if (q < nb && own) Lp[bc[q] + i0] = av[q];
+        // further rows of this thread (only when n - panel > number of threads)
+        for (int i = i0 + nt; i < n; i += nt) {
+            double aw[4];
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) aw[q] = (q < nb) ? Lp[bc[q] + i] : 0.0;
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) {
+                aw[q] = sc[q] ? aw[q] / d[q] : aw[q];
+                PMB_UNROLL
+                for (int q2 = q + 1; q2 < 4; ++q2) aw[q2] = dm::fma(-aw[q], ub[q2][q], aw[q2]);
+            }
+            PMB_UNROLL
+            for (int q = 0; q < 4; ++q) if (q < nb) Lp[bc[q] + i] = aw[q];
         }
         c.sync();
         // rows inside the panel: thread r < nb stores row j0 + r of the factored diagonal block (after the barrier: every
@@ -238,6 +261,9 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
         }
         // ---- P2: trailing update, a(i,k) = fma(-L(i,j0+q), d_q L(k,j0+q), a(i,k)) for q ascending, k > panel, i >= k
         const int kfirst = j0 + nb;
+#ifdef PMB_UB_SKIP
+        if (!(PMB_UB_SKIP & 8))
+#endif
         if (kfirst < n) {
             double nl[R][4];
             int ic[R];                                         // the lane's row in chunk r, clamped into the matrix
@@ -248,36 +274,46 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
                 PMB_UNROLL
                 for (int q = 0; q < 4; ++q) nl[r][q] = (q < nb && i >= kfirst && i < n) ? -Lp[bc[q] + i] : 0.0;
             }
-            int k = kfirst + wid;
-            int bk = k * n - ((k * (k + 1)) >> 1);             // packed_off(k, n) - k
-            const int adv0 = nw * n - (nw * (nw + 1)) / 2;     // bk(k + nw) - bk(k) = nw*n - nw*k - nw(nw+1)/2
+            // two columns (k and k + nw) per trip, so that two independent load -> 4 FMA -> store chains are in flight
             PMB_NOUNROLL
-            for (; k < n; k += nw) {
-                double uk[4];
+            for (int k = kfirst + wid; k < n; k += 2 * nw) {
+                const int k2 = k + nw;
+                const bool has2 = k2 < n;
+                const int k2c = has2 ? k2 : k;                 // clamped: loads stay inside the matrix, stores are predicated
+                const int bk = k * n - ((k * (k + 1)) >> 1);   // packed_off(k, n) - k
+                const int bk2 = k2c * n - ((k2c * (k2c + 1)) >> 1);
+                double uk[4], uk2[4];
                 PMB_UNROLL
-                for (int q = 0; q < 4; ++q) uk[q] = (q < nb) ? d[q] * Lp[bc[q] + k] : 0.0;
+                for (int q = 0; q < 4; ++q) {
+                    uk[q] = (q < nb) ? d[q] * Lp[bc[q] + k] : 0.0;
+                    uk2[q] = (q < nb) ? d[q] * Lp[bc[q] + k2c] : 0.0;
+                }
                 double* ck = Lp + bk;
+                double* ck2 = Lp + bk2;
                 const int c0 = k >> 5;                         // first chunk with rows >= k (warp-uniform)
-                // one uniform dispatch per column, then straight-line code: unconditional loads (rows above the
+                // one uniform dispatch per column pair, then straight-line code: unconditional loads (rows above the
                 // diagonal read the tail of earlier columns — valid memory, discarded), 4 chained FMAs, predicated stores
                 PMB_UNROLL
                 for (int r0 = 0; r0 < R; ++r0) {
                     if (c0 == r0) {
-                        double acc[R];
+                        double acc[R], acc2[R];
                         PMB_UNROLL
-                        for (int r = r0; r < R; ++r) acc[r] = ck[ic[r]];
+                        for (int r = r0; r < R; ++r) { acc[r] = ck[ic[r]]; acc2[r] = ck2[ic[r]]; }
                         PMB_UNROLL
                         for (int q = 0; q < 4; ++q) {
                             if (q < nb) {
                                 PMB_UNROLL
-                                for (int r = r0; r < R; ++r) acc[r] = dm::fma(nl[r][q], uk[q], acc[r]);
+                                for (int r = r0; r < R; ++r) { acc[r] = dm::fma(nl[r][q], uk[q], acc[r]); acc2[r] = dm::fma(nl[r][q], uk2[q], acc2[r]); }
                             }
                         }
                         PMB_UNROLL
-                        for (int r = r0; r < R; ++r) { const int i = lane + 32 * r; if (i >= k && i < n) ck[i] = acc[r]; }
+                        for (int r = r0; r < R; ++r) {
+                            const int i = lane + 32 * r;
+                            if (i >= k && i < n) ck[i] = acc[r];
+                            if (has2 && i >= k2 && i < n) ck2[i] = acc2[r];
+                        }
                     }
                 }
-                bk += adv0 - nw * k;
             }
         }
         c.sync();

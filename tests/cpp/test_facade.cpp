@@ -33,14 +33,14 @@ int main(int argc, char** argv)
     mpc.set_static_parameters({2.0});
     mpc.control_bounds({-1.5, -0.75}, {1.5, 0.75});
     vec x0((size_t)batch * 3);
-    for (int b = 0; b < batch; ++b) { x0[3 * b] = 0.5 - 0.01 * b; x0[3 * b + 1] = 0.5; x0[3 * b + 2] = 0.5; }   // instance 0 = the reference test
+    for (int b = 0; b < batch; ++b) { x0[3 * b] = 0.5; x0[3 * b + 1] = 0.5; x0[3 * b + 2] = 0.5; }   // every instance = the reference test
     mpc.initial_conditions(x0);
     mpc.solve();
     std::vector<int> first(batch);
     for (int b = 0; b < batch; ++b) { first[b] = mpc.info(b).iter; EXPECT(mpc.info(b).status == PMB_SQP_SOLVED); }
 
     // warm started iteration
-    for (int b = 0; b < batch; ++b) { x0[3 * b] = 0.3 - 0.01 * b; x0[3 * b + 1] = 0.4; x0[3 * b + 2] = 0.5; }
+    for (int b = 0; b < batch; ++b) { x0[3 * b] = 0.3; x0[3 * b + 1] = 0.4; x0[3 * b + 2] = 0.5; }
     mpc.initial_conditions(x0, x0);
     mpc.solve();
     for (int b = 0; b < batch; ++b) {
@@ -58,6 +58,8 @@ int main(int argc, char** argv)
         const vec u = mpc.solution_u(b);
         for (int k = 0; k < mpc.num_nodes(); ++k) EXPECT(std::fabs(u[2 * k]) <= 1.5 + 1e-3 && std::fabs(u[2 * k + 1]) <= 0.75 + 1e-3);
     }
+    // replicated instances are solved independently and deterministically: bit-identical results
+    for (int b = 1; b < batch; ++b) { EXPECT(mpc.solution_x(b) == mpc.solution_x(0)); EXPECT(mpc.solution_dual(b) == mpc.solution_dual(0)); }
     // exact interpolation at every node of the grid
     const vec tg = mpc.time_grid();
     for (int k = 0; k < mpc.num_nodes(); ++k) EXPECT(approx(mpc.solution_x_at(0, k), mpc.solution_x_at(0, tg[k]), 1e-9));

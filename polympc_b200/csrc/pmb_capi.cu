@@ -85,7 +85,7 @@ template <int R, bool IN_SMEM> bool launch_qp_r(size_t fac_doubles, size_t vec_b
     if (grid <= 0) { last_error_string() = "qp_box_admm: kernel does not fit on the device"; return false; }
     if (!IN_SMEM) grid = grid > 2 * 148 ? 2 * 148 : grid;      // keep the global factor slots L2 resident
     if (grid > batch) grid = batch;
-    FactorStore fs{nullptr, fac_doubles};
+    FactorStore fs{nullptr, fac_doubles, rt_sm_count()};
     if (!IN_SMEM) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
     return rt_launch<QpBody<R, IN_SMEM>>(grid, smem, s, st, qb, fs, batch, queue);
 }

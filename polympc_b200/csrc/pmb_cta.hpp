@@ -18,12 +18,21 @@ struct Cta {
     Warp w;
     double* bc;      // [BC_SLOTS] broadcast slots followed by [RED_DOUBLES] reduction scratch (shared memory)
     int ctr;
+    int vw;          // virtual warp id = (physical warp id - rot) mod nwarps
 
-    PMB_DEV Cta(const Warp& w_, double* scratch) : w(w_), bc(scratch), ctr(0) {}
-    PMB_DEV int tid() const { return w.tid(); }
+    /** `rot` rotates the warp numbering: the serial phases of the algorithms run on *virtual* warp 0, and the hardware
+     *  pins physical warp w of every CTA to scheduler w % 4 — without the rotation the serial warps of all CTAs resident on
+     *  an SM would share one scheduler while the other three idle.  Callers pass a different `rot` to co-resident CTAs. */
+    PMB_DEV Cta(const Warp& w_, double* scratch, int rot = 0) : w(w_), bc(scratch), ctr(0)
+    {
+        const int nw = (w.nthreads() + 31) >> 5;
+        int v = w.warp_id() - (rot % nw);
+        vw = v < 0 ? v + nw : v;
+    }
+    PMB_DEV int tid() const { return (vw << 5) | w.lane(); }
     PMB_DEV int nthreads() const { return w.nthreads(); }
     PMB_DEV int lane() const { return w.lane(); }
-    PMB_DEV int warp_id() const { return w.warp_id(); }
+    PMB_DEV int warp_id() const { return vw; }
     PMB_DEV int nwarps() const { return (w.nthreads() + 31) >> 5; }
     PMB_DEV void sync() const { w.block_sync(); }
 
@@ -32,7 +41,7 @@ struct Cta {
     {
         double* slot = bc + (ctr & (BC_SLOTS - 1));
         ++ctr;
-        if (w.tid() == src) *slot = v;
+        if (tid() == src) *slot = v;
         w.block_sync();
         return *slot;
     }
@@ -48,7 +57,7 @@ struct Cta {
         const int nw = nwarps();
         if (nw == 1) return;
         double* red = bc + BC_SLOTS;
-        if (w.lane() == 0) for (int k = 0; k < K; ++k) red[w.warp_id() * K + k] = m[k];
+        if (w.lane() == 0) for (int k = 0; k < K; ++k) red[vw * K + k] = m[k];
         w.block_sync();
         PMB_UNROLL
         for (int k = 0; k < K; ++k) {

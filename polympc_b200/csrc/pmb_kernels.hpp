@@ -32,8 +32,8 @@ struct OcpEvalBody {
         const double* lam = io.lam ? io.lam + (size_t)b * O::DUAL : nullptr;
         double cost = 0.0;
         if (MODE == OCP_COST) cost = E::cost(c, o, var, d);
-        else if (MODE == OCP_EQ) E::equalities(c, o, var, d, io.c + (size_t)b * O::NUM_EQ);
-        else if (MODE == OCP_INEQ) E::inequalities(c, o, var, d, io.g + (size_t)b * O::NUM_INEQ);
+        else if (MODE == OCP_EQ) E::equalities(c, o, var, d, io.c + (size_t)b * O::NUM_EQ, c.tid());
+        else if (MODE == OCP_INEQ) E::inequalities(c, o, var, d, io.g + (size_t)b * O::NUM_INEQ, c.tid());
         else if (MODE == OCP_EQ_LIN)
             E::constraints_linearised(c, o, var, d, io.c + (size_t)b * O::NUM_EQ, io.jac + (size_t)b * O::NUM_EQ * O::N, O::NUM_EQ, false);
         else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(c, o, var, d, io.grad + (size_t)b * O::N);
@@ -78,6 +78,7 @@ PMB_DEV QpArgs qp_instance(const QpBatch& q, int b)
 struct FactorStore {
     double* global;      // grid * factor_doubles (nullptr: shared memory)
     size_t doubles;      // n (n + 1) / 2
+    int sm_count;        // SMs of the device (0: unknown) — used to rotate the serial warp between co-resident CTAs
 };
 
 /** persistent CTA-per-instance boxADMM: CTAs draw instances from an atomic queue */
@@ -89,7 +90,7 @@ struct QpBody {
     static constexpr size_t EMU_STACK_BYTES = 1u << 20;
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, QpBatch qb, FactorStore fs, int batch, int* queue)
     {
-        Cta c(w, reinterpret_cast<double*>(smem));
+        Cta c(w, reinterpret_cast<double*>(smem), fs.sm_count > 0 ? blk + blk / fs.sm_count : 0);
         unsigned char* ws = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
         // IN_SMEM is a template parameter so that the factor pointer is provably a shared-memory address (LDS/STS)
         double* Lp = IN_SMEM ? reinterpret_cast<double*>(ws) : fs.global + (size_t)blk * fs.doubles;
@@ -147,36 +148,6 @@ struct BfgsBody {
 };
 
 // ---- SQP pipeline ---------------------------------------------------------------------------------------------------
-struct SqpWs {
-    double *x, *lam, *lam_k, *H, *A, *h, *al, *au, *lx, *ux, *lbx, *ubx, *lbg, *ubg, *d, *lag_grad, *step_prev, *p, *plam, *stats;
-    pmb_sqp_info_t* info;
-    pmb_qp_info_t* qp_info;
-    int* qp_nfac;
-    int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
-    double* tr_alpha;
-    int trace_rows;
-    unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
-                                 // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
-};
-
-template <class O>
-PMB_DEV SqpInst sqp_instance(const SqpWs& ws, int b)
-{
-    const size_t N = O::N, M = O::M, DUAL = O::DUAL, NI = O::NUM_INEQ, ND = O::ND, T = (size_t)ws.trace_rows;
-    SqpInst s;
-    s.x = ws.x + b * N; s.lam = ws.lam + b * DUAL; s.lam_k = ws.lam_k + b * DUAL; s.H = ws.H + b * N * N; s.A = ws.A + b * M * N;
-    s.h = ws.h + b * N; s.al = ws.al + b * M; s.au = ws.au + b * M; s.lx = ws.lx + b * N; s.ux = ws.ux + b * N;
-    s.lag_grad = ws.lag_grad + b * N; s.step_prev = ws.step_prev + b * N; s.p = ws.p + b * N; s.plam = ws.plam + b * DUAL;
-    s.stats = ws.stats + b * 4;
-    s.lbx = ws.lbx + b * N; s.ubx = ws.ubx + b * N; s.lbg = ws.lbg + b * NI; s.ubg = ws.ubg + b * NI; s.d = ws.d + b * ND;
-    s.info = ws.info + b; s.qp_info = ws.qp_info + b; s.qp_nfac = ws.qp_nfac + b;
-    s.tr_qp_iter = ws.tr_qp_iter ? ws.tr_qp_iter + b * T : nullptr; s.tr_bfgs = ws.tr_bfgs ? ws.tr_bfgs + b * T : nullptr;
-    s.tr_ls = ws.tr_ls ? ws.tr_ls + b * T : nullptr; s.tr_qp_factor = ws.tr_qp_factor ? ws.tr_qp_factor + b * T : nullptr;
-    s.tr_alpha = ws.tr_alpha ? ws.tr_alpha + b * T : nullptr;
-    s.phase = ws.phase;
-    return s;
-}
-
 /** the whole SQPBase::solve of the batch in ONE persistent launch: each CTA draws an instance from the atomic queue and
  *  iterates linearise -> boxADMM -> line search / step on it until it converges (no host round trip per iteration, no
  *  wave quantisation: a slow instance only occupies its own CTA). */
@@ -188,12 +159,18 @@ struct SqpSolveBody {
     static constexpr int R = (O::N + O::M + 31) / 32;
     static constexpr size_t FACTOR_DOUBLES = (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
     static constexpr size_t SCRATCH_BYTES = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
-    /** resident CTAs per SM the register allocation is asked to allow: what shared memory permits when the factor lives
-     *  there (mobile robot: 4 x 55 KB), 2 when the factor is in global scratch (large problems, heavy AD code) */
+    /** resident CTAs per SM the register allocation is asked to allow: at most 3 when the factor lives in shared memory
+     *  (168 registers per thread; measured on the mobile robot: 4 CTAs x 128 registers spill inside the QP loops and are
+     *  slower end to end — 127 ms vs 109 ms per batch of 8192 — although shared memory would admit 4), 2 when the factor is
+     *  in global scratch (large problems, heavy AD code) */
     static constexpr size_t SMEM_IN = Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
                                       (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
     static constexpr bool IN_SMEM = SMEM_IN <= 227 * 1024;    // placement of the factor, fixed per problem at compile time
-    static constexpr int MIN_BLOCKS = !IN_SMEM ? 2 : ((228 * 1024) / SMEM_IN > 4 ? 4 : (int)((228 * 1024) / SMEM_IN));
+#ifdef PMB_MINB
+    static constexpr int MIN_BLOCKS = PMB_MINB;
+#else
+    static constexpr int MIN_BLOCKS = !IN_SMEM ? 2 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
+#endif
     /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors      (factor in shared memory)
      *                 Cta scratch | SQP scratch | QP vectors                              (factor in global scratch) */
     static size_t smem_bytes()
@@ -205,7 +182,9 @@ struct SqpSolveBody {
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st, pmb_qp_settings_t qst,
                             FactorStore fs, int batch, int* queue)
     {
-        Cta c(w, reinterpret_cast<double*>(smem));
+        // CTAs blk, blk + #SMs, blk + 2 #SMs, ... share an SM (breadth-first placement of a one-wave grid): give them
+        // different serial warps (fs.sm_count is the number of SMs of the device)
+        Cta c(w, reinterpret_cast<double*>(smem), fs.sm_count > 0 ? blk + blk / fs.sm_count : 0);
         unsigned char* base = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
         double* scratch = reinterpret_cast<double*>(base);
         double* Lp;
@@ -219,7 +198,7 @@ struct SqpSolveBody {
         for (;;) {
             const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (b >= batch) break;
-            const SqpInst s = sqp_instance<O>(ws, b);
+            const SqpInst<O> s{ws, b};
             SqpDev<O>::template solve<R>(c, o, s, st, qst, Lp, vec, scratch);
         }
     }

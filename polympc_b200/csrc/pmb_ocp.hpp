@@ -130,7 +130,14 @@ struct OcpEval {
     // ---- a3: cost (continuous_ocp.hpp:1180-1207) -----------------------------------------------------------------
     PMB_DEV static double cost(Cta& c, const O& o, const double* var, const double* d)
     {
-        const int k = c.tid();
+        double acc = 0.0;
+        if (c.warp_id() == 0) acc = cost_warp0(c, o, var, d);
+        return c.bcast(acc, 0);
+    }
+    /** the same, called by (virtual) warp 0 only: no block barrier, the sum is returned in every lane of that warp */
+    PMB_DEV static double cost_warp0(Cta& c, const O& o, const double* var, const double* d)
+    {
+        const int k = c.lane();
         double ci = 0.0, mv = 0.0;
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0};
@@ -138,13 +145,20 @@ struct OcpEval {
             o.model.template lagrange<double>(x, u, p, d, o.time_nodes[k], ci);
             if (k == 0) o.model.template mayer<double>(x, u, p, d, o.time_nodes[0], mv);
         }
-        return quadrature_sum(c, o, ci, mv);
+        double acc = 0.0;
+        for (int s = 0; s < S; ++s)
+            for (int kk = 0; kk <= P; ++kk) {
+                const double v = c.w.shfl(ci, s * P + kk);
+                acc += (o.ts * o.w[kk]) * v;
+            }
+        acc += c.w.shfl(mv, 0);
+        return acc;
     }
 
     // ---- a4: equalities (continuous_ocp.hpp:738-766); lane k writes c[k*NX .. k*NX+NX) -----------------------------
-    PMB_DEV static void equalities(Cta& c, const O& o, const double* var, const double* d, double* ce)
+    /** node k is evaluated by the calling thread (callers pass c.tid(), or the lane when one warp does the whole job) */
+    PMB_DEV static void equalities(Cta& c, const O& o, const double* var, const double* d, double* ce, int k)
     {
-        const int k = c.tid();
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, f[NX], DXk[NX];
             load_plain<double>(var, k, x, u);
@@ -157,10 +171,9 @@ struct OcpEval {
     }
 
     // ---- a5: inequalities (continuous_ocp.hpp:769-782) ------------------------------------------------------------
-    PMB_DEV static void inequalities(Cta& c, const O& o, const double* var, const double* d, double* g)
+    PMB_DEV static void inequalities(Cta& c, const O& o, const double* var, const double* d, double* g, int k)
     {
         if (NG == 0) return;
-        const int k = c.tid();
         if (k < NN) {
             double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, gr[NG > 0 ? NG : 1];
             load_plain<double>(var, k, x, u);

@@ -485,10 +485,10 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
 
 /** the whole boxADMM solve of one instance by one CTA.  Lp: n(n+1)/2 doubles (shared or global), vec: qp_vec_bytes() of
  *  shared memory. */
-template <int R>
+template <int R, int NC = 0, int MC = 0>   // NC, MC: problem size when it is known at compile time (fused SQP kernel), 0 = a.N, a.M
 PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec)
 {
-    const int N = a.N, M = a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
+    const int N = NC > 0 ? NC : a.N, M = (NC > 0) ? MC : a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
     double* dK = reinterpret_cast<double*>(vec);
     double* tmp = dK + n;
     double* sol = tmp + n;

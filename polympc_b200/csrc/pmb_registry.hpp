@@ -70,7 +70,7 @@ struct ProblemImpl : IProblem {
     bool launch_solve(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
                       int batch, int* queue, stream_t s) const override
     {
-        FactorStore fs{Solve::IN_SMEM ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES};
+        FactorStore fs{Solve::IN_SMEM ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES, rt_sm_count()};
         return rt_launch<Solve>(grid, Solve::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
     }
 };

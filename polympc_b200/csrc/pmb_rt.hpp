@@ -26,6 +26,7 @@ inline bool rt_ok(cudaError_t e, const char* what)
 
 inline int rt_device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 inline bool rt_set_device(int dev) { return PMB_RT(cudaSetDevice(dev)); }
+inline int rt_sm_count() { int dev = 0, n = 0; if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 inline void* rt_alloc(size_t bytes) { void* p = nullptr; if (bytes == 0) bytes = 16; if (!PMB_RT(cudaMalloc(&p, bytes))) return nullptr; return p; }
 inline void rt_free(void* p) { if (p) cudaFree(p); }
 inline bool rt_h2d(void* dst, const void* src, size_t bytes, stream_t s) { return bytes == 0 || PMB_RT(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); }
@@ -48,6 +49,7 @@ typedef void* stream_t;
 typedef void* event_t;
 inline int rt_device_count() { return 1; }
 inline bool rt_set_device(int) { return true; }
+inline int rt_sm_count() { return 1; }   // emulator: every CTA gets a different rotation, which exercises the rotated numbering
 inline void* rt_alloc(size_t bytes) { return std::calloc(bytes ? bytes : 16, 1); }
 inline void rt_free(void* p) { std::free(p); }
 inline bool rt_h2d(void* dst, const void* src, size_t bytes, stream_t) { if (bytes) std::memcpy(dst, src, bytes); return true; }

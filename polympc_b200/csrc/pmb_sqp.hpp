@@ -58,17 +58,40 @@ PMB_DEV int bfgs_update_cta(Cta& c, int n, double* B, const double* s, const dou
     return branch;
 }
 
-/** per-instance views of the SQP state in global memory */
-struct SqpInst {
-    double *x, *lam, *lam_k, *H, *A, *h, *al, *au, *lx, *ux, *lag_grad, *step_prev, *p, *plam, *stats;
-    const double *lbx, *ubx, *lbg, *ubg, *d;
+/** batch-wide SQP state in global memory (instance-major arrays) */
+struct SqpWs {
+    double *x, *lam, *lam_k, *H, *A, *h, *al, *au, *lx, *ux, *lbx, *ubx, *lbg, *ubg, *d, *lag_grad, *step_prev, *p, *plam, *stats;
     pmb_sqp_info_t* info;
     pmb_qp_info_t* qp_info;
     int* qp_nfac;
-    // decision trace rows (may be null)
     int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
     double* tr_alpha;
-    unsigned long long* phase;   // profiling counters (may be null)
+    int trace_rows;
+    unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
+                                 // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
+};
+
+/** per-instance view of the SQP state.  Only (workspace, instance index) are held; every pointer is recomputed from the
+ *  kernel parameters where it is used — 25 live 64-bit pointers across the QP were the main cause of register spills in the
+ *  fused kernel. */
+template <class O>
+struct SqpInst {
+    const SqpWs& ws;
+    int b;
+#define PMB_INST_F(T, name, len) PMB_DEV T* name() const { return ws.name + (size_t)b * (size_t)(len); }
+    PMB_INST_F(double, x, O::N) PMB_INST_F(double, lam, O::DUAL) PMB_INST_F(double, lam_k, O::DUAL) PMB_INST_F(double, H, O::N * O::N)
+    PMB_INST_F(double, A, O::M * O::N) PMB_INST_F(double, h, O::N) PMB_INST_F(double, al, O::M) PMB_INST_F(double, au, O::M)
+    PMB_INST_F(double, lx, O::N) PMB_INST_F(double, ux, O::N) PMB_INST_F(double, lag_grad, O::N) PMB_INST_F(double, step_prev, O::N)
+    PMB_INST_F(double, p, O::N) PMB_INST_F(double, plam, O::DUAL) PMB_INST_F(double, stats, 4)
+    PMB_INST_F(const double, lbx, O::N) PMB_INST_F(const double, ubx, O::N) PMB_INST_F(const double, lbg, O::NUM_INEQ)
+    PMB_INST_F(const double, ubg, O::NUM_INEQ) PMB_INST_F(const double, d, O::ND)
+    PMB_INST_F(pmb_sqp_info_t, info, 1) PMB_INST_F(pmb_qp_info_t, qp_info, 1) PMB_INST_F(int, qp_nfac, 1)
+#undef PMB_INST_F
+    // decision trace rows (arrays may be null)
+#define PMB_INST_T(T, name) PMB_DEV T* name() const { return ws.name ? ws.name + (size_t)b * (size_t)ws.trace_rows : nullptr; }
+    PMB_INST_T(int, tr_qp_iter) PMB_INST_T(int, tr_bfgs) PMB_INST_T(int, tr_ls) PMB_INST_T(int, tr_qp_factor) PMB_INST_T(double, tr_alpha)
+#undef PMB_INST_T
+    PMB_DEV unsigned long long* phase() const { return ws.phase; }
 };
 
 template <class O>
@@ -79,40 +102,23 @@ struct SqpDev {
     /** shared scratch (doubles) needed by linearise / step */
     static constexpr int SCRATCH_DOUBLES = 4 * N + M + 8 + E::NV_DOUBLES;
 
-    /** sqp_base.hpp:421-444; cg: scratch of M doubles */
-    PMB_DEV static double constraints_violation(Cta& c, const O& o, const double* xv, const SqpInst& s, double* cg)
-    {
-        E::equalities(c, o, xv, s.d, cg);
-        E::inequalities(c, o, xv, s.d, cg + NUM_EQ);
-        c.sync();
-        double cl1 = DBL_EPSILON;
-        cl1 += sum_tree32(c, NUM_EQ, [&](int i, double acc) { return acc + dm::fabs(cg[i]); });
-        if (NUM_INEQ > 0) {
-            cl1 += sum_tree32(c, NUM_INEQ, [&](int i, double acc) { return acc + dm::max(s.lbg[i] - cg[NUM_EQ + i], 0.0); });
-            cl1 += sum_tree32(c, NUM_INEQ, [&](int i, double acc) { return acc + dm::max(cg[NUM_EQ + i] - s.ubg[i], 0.0); });
-        }
-        cl1 += sum_tree32(c, N, [&](int i, double acc) { return acc + dm::max(s.lbx[i] - xv[i], 0.0); });
-        cl1 += sum_tree32(c, N, [&](int i, double acc) { return acc + dm::max(xv[i] - s.ubx[i], 0.0); });
-        return cl1;
-    }
-
     /** sqp_base.hpp:446-474 */
-    PMB_DEV static double max_constraints_violation(Cta& c, const O& o, const double* xv, const SqpInst& s, double* cg)
+    /** have_cg: cg already holds c(xv) (and g(xv)) */
+    PMB_DEV static double max_constraints_violation(Cta& c, const O& o, const double* xv, const SqpInst<O>& s, double* cg, bool have_cg)
     {
         const int tid = c.tid(), nt = c.nthreads();
         double cv = 0.0;
-        if (NUM_EQ > 0) {
-            E::equalities(c, o, xv, s.d, cg);
+        if (!have_cg) {
+            E::equalities(c, o, xv, s.d(), cg, tid);
+            E::inequalities(c, o, xv, s.d(), cg + NUM_EQ, tid);
             c.sync();
-            cv = norm_inf_cta(c, cg, NUM_EQ);
         }
+        if (NUM_EQ > 0) cv = norm_inf_cta(c, cg, NUM_EQ);
         const double NEG = -dm::inf();
         if (NUM_INEQ > 0) {
-            E::inequalities(c, o, xv, s.d, cg + NUM_EQ);
-            c.sync();
             double m[2] = {NEG, NEG};
             for (int i = tid; i < NUM_INEQ; i += nt) {
-                const double a = s.lbg[i] - cg[NUM_EQ + i], b = cg[NUM_EQ + i] - s.ubg[i];
+                const double a = s.lbg()[i] - cg[NUM_EQ + i], b = cg[NUM_EQ + i] - s.ubg()[i];
                 if (a > m[0]) m[0] = a;
                 if (b > m[1]) m[1] = b;
             }
@@ -121,7 +127,7 @@ struct SqpDev {
         }
         double m[2] = {NEG, NEG};
         for (int i = tid; i < N; i += nt) {
-            const double a = s.lbx[i] - xv[i], b = xv[i] - s.ubx[i];
+            const double a = s.lbx()[i] - xv[i], b = xv[i] - s.ubx()[i];
             if (a > m[0]) m[0] = a;
             if (b > m[1]) m[1] = b;
         }
@@ -131,81 +137,146 @@ struct SqpDev {
     }
 
     /** first (exact Hessian) or later (BFGS) linearisation + QP bounds (sqp_base.hpp:583-593, 649-657, 489-504) */
-    PMB_DEV static void linearise(Cta& c, const O& o, const SqpInst& s, bool first, int trace_row, double* scratch)
+    /** returns the cost at x (the value every linearisation computes on the way) */
+    PMB_DEV static double linearise(Cta& c, const O& o, const SqpInst<O>& s, bool first, int trace_row, double* scratch)
     {
         const int tid = c.tid(), nt = c.nthreads();
+        double cost_x;
         if (first) {
-            E::lagrangian_gradient_hessian(c, o, s.x, s.d, s.lam, s.lag_grad, s.H, s.h, s.al, s.A, scratch);
-            if (s.tr_bfgs && tid == 0) s.tr_bfgs[trace_row] = -1;
+            cost_x = E::lagrangian_gradient_hessian(c, o, s.x(), s.d(), s.lam(), s.lag_grad(), s.H(), s.h(), s.al(), s.A(), scratch);
+            if (s.tr_bfgs() && tid == 0) s.tr_bfgs()[trace_row] = -1;
         } else {
             double* lg = scratch;          // N
             double* yv = lg + N;           // N
             double* Bs = yv + N;           // N
             double* r = Bs + N;            // N
-            E::lagrangian_gradient(c, o, s.x, s.d, s.lam, lg, s.h, s.al, s.A);
-            for (int i = tid; i < N; i += nt) yv[i] = lg[i] - s.lag_grad[i];
+            cost_x = E::lagrangian_gradient(c, o, s.x(), s.d(), s.lam(), lg, s.h(), s.al(), s.A());
+            for (int i = tid; i < N; i += nt) yv[i] = lg[i] - s.lag_grad()[i];
             c.sync();
-            const int br = bfgs_update_cta(c, N, s.H, s.step_prev, yv, Bs, r);
-            if (s.tr_bfgs && tid == 0) s.tr_bfgs[trace_row] = br;
-            for (int i = tid; i < N; i += nt) s.lag_grad[i] = lg[i];
+            const int br = bfgs_update_cta(c, N, s.H(), s.step_prev(), yv, Bs, r);
+            if (s.tr_bfgs() && tid == 0) s.tr_bfgs()[trace_row] = br;
+            for (int i = tid; i < N; i += nt) s.lag_grad()[i] = lg[i];
         }
         // sqp_base.hpp:588-593
         for (int i = tid; i < M; i += nt) {
-            double a = -s.al[i];
+            double a = -s.al()[i];
             double b = a;
-            if (i >= NUM_EQ) { a += s.lbg[i - NUM_EQ]; b += s.ubg[i - NUM_EQ]; }
-            s.al[i] = a; s.au[i] = b;
+            if (i >= NUM_EQ) { a += s.lbg()[i - NUM_EQ]; b += s.ubg()[i - NUM_EQ]; }
+            s.al()[i] = a; s.au()[i] = b;
         }
-        for (int i = tid; i < N; i += nt) { s.lx[i] = s.lbx[i] - s.x[i]; s.ux[i] = s.ubx[i] - s.x[i]; }
+        for (int i = tid; i < N; i += nt) { s.lx()[i] = s.lbx()[i] - s.x()[i]; s.ux()[i] = s.ubx()[i] - s.x()[i]; }
         c.sync();
+        return cost_x;
     }
 
-    /** everything after the QP: multipliers, line search, step, norms, termination.  Returns true when converged. */
-    PMB_DEV static bool step(Cta& c, const O& o, const SqpInst& s, const pmb_sqp_settings_t& st, int trace_row, double* scratch)
+    /** merit ingredients at the point xv for the line search (sqp_base.hpp:395-399, 421-444): cost(xv) and
+     *  viol_1(xv) = eps + |c|_1 + sum max(0, lbg - g) + sum max(0, g - ubg) + sum max(0, lbx - xv) + sum max(0, xv - ubx).
+     *  The four independent pieces run on different warps (cost on warp 0, constraints on warp 1, the two box sums on
+     *  warp 2) and meet at ONE barrier; every sum keeps its canonical tree32 order.  cg[M] receives c(xv) (and g(xv)). */
+    PMB_DEV static void merit_terms(Cta& c, const O& o, const double* xv, const SqpInst<O>& s, double* cg, double& cost_out, double& viol_out)
+    {
+        const int nw = c.nwarps(), wid = c.warp_id(), lane = c.lane();
+        double* slot = c.bc + Cta::BC_SLOTS;       // reduction scratch doubles as the meeting point: [cost, eq, ilb, iub, lbx, ubx]
+        const Warp& w = c.w;
+        auto tree = [&](int n, auto term) {        // tree32 sum inside the calling warp; result in every lane
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) acc = term(i, acc);
+            for (int off = 16; off >= 1; off >>= 1) acc = acc + w.shfl_xor(acc, off);
+            return acc;
+        };
+        if (wid == 0) {
+            const double cv = E::cost_warp0(c, o, xv, s.d());
+            if (lane == 0) slot[0] = cv;
+        }
+        if (wid == 1 % nw) {
+            E::equalities(c, o, xv, s.d(), cg, lane);
+            E::inequalities(c, o, xv, s.d(), cg + NUM_EQ, lane);
+            w.sync();
+            const double se = tree(NUM_EQ, [&](int i, double acc) { return acc + dm::fabs(cg[i]); });
+            double sl = 0.0, su = 0.0;
+            if (NUM_INEQ > 0) {
+                sl = tree(NUM_INEQ, [&](int i, double acc) { return acc + dm::max(s.lbg()[i] - cg[NUM_EQ + i], 0.0); });
+                su = tree(NUM_INEQ, [&](int i, double acc) { return acc + dm::max(cg[NUM_EQ + i] - s.ubg()[i], 0.0); });
+            }
+            if (lane == 0) { slot[1] = se; slot[2] = sl; slot[3] = su; }
+        }
+        if (wid == 2 % nw) {
+            const double sl = tree(N, [&](int i, double acc) { return acc + dm::max(s.lbx()[i] - xv[i], 0.0); });
+            const double su = tree(N, [&](int i, double acc) { return acc + dm::max(xv[i] - s.ubx()[i], 0.0); });
+            if (lane == 0) { slot[4] = sl; slot[5] = su; }
+        }
+        c.sync();
+        cost_out = slot[0];
+        double cl1 = DBL_EPSILON;
+        cl1 += slot[1];
+        if (NUM_INEQ > 0) { cl1 += slot[2]; cl1 += slot[3]; }
+        cl1 += slot[4];
+        cl1 += slot[5];
+        viol_out = cl1;
+        c.sync();                                   // the slots may be rewritten after this point
+    }
+
+    /** everything after the QP: multipliers, line search, step, norms, termination.  Returns true when converged.
+     *  cost_x = cost at the current x (known from the linearisation); the constraint values at x are known as well:
+     *  s.al() still holds -c(x) (the QP bounds) when there are no inequality rows. */
+    PMB_DEV static bool step(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, int trace_row, double* scratch, double cost_x)
     {
         const int tid = c.tid(), nt = c.nthreads();
         double* x_step = scratch;       // N
         double* cg = x_step + N;        // M
         // solve_qp bookkeeping (sqp_base.hpp:532-565) and lam_k / p_lambda (617-619)
         if (tid == 0) {
-            s.info->qp_solver_iter += s.qp_info->iter;
-            if (s.tr_qp_iter) s.tr_qp_iter[trace_row] = s.qp_info->iter;
-            if (s.tr_qp_factor) s.tr_qp_factor[trace_row] = *s.qp_nfac;
+            s.info()->qp_solver_iter += s.qp_info()->iter;
+            if (s.tr_qp_iter()) s.tr_qp_iter()[trace_row] = s.qp_info()->iter;
+            if (s.tr_qp_factor()) s.tr_qp_factor()[trace_row] = *s.qp_nfac();
         }
-        for (int i = tid; i < DUAL; i += nt) { const double v = s.plam[i]; s.lam_k[i] = v; s.plam[i] = v - s.lam[i]; }
+        for (int i = tid; i < DUAL; i += nt) { const double v = s.plam()[i]; s.lam_k()[i] = v; s.plam()[i] = v - s.lam()[i]; }
         c.sync();
 
         // ---- step_size_selection_impl (378-419)
-        const double constr_l1 = constraints_violation(c, o, s.x, s, cg);
-        const double mu = norm_inf_cta(c, s.lam_k, DUAL);
-        const double cost_1 = E::cost(c, o, s.x, s.d);
+        double constr_l1, cost_1;
+        if (NUM_INEQ == 0) {
+            // |c(x)|_1 from the QP bounds al = -c(x) (|-c| == |c| bit for bit), cost(x) from the linearisation
+            double cl1 = DBL_EPSILON;
+            cl1 += sum_tree32(c, NUM_EQ, [&](int i, double acc) { return acc + dm::fabs(s.al()[i]); });
+            cl1 += sum_tree32(c, N, [&](int i, double acc) { return acc + dm::max(s.lbx()[i] - s.x()[i], 0.0); });
+            cl1 += sum_tree32(c, N, [&](int i, double acc) { return acc + dm::max(s.x()[i] - s.ubx()[i], 0.0); });
+            constr_l1 = cl1;
+            cost_1 = cost_x;
+        } else {
+            merit_terms(c, o, s.x(), s, cg, cost_1, constr_l1);
+        }
+        const double mu = norm_inf_cta(c, s.lam_k(), DUAL);
         const double phi_l1 = cost_1 + mu * constr_l1;
-        const double Dp_phi_l1 = dot_tree32(c, s.h, s.p, N) - mu * constr_l1;
+        const double Dp_phi_l1 = dot_tree32(c, s.h(), s.p(), N) - mu * constr_l1;
         double alpha = 1.0, cost_step = 0.0;
         int trials = 0;
+        bool accepted = false;          // cg holds c(x + alpha p) of the accepted trial
         for (int it = 1; it < st.line_search_max_iter; ++it) {
-            for (int j = tid; j < N; j += nt) { double v = alpha * s.p[j]; v += s.x[j]; x_step[j] = v; }
+            for (int j = tid; j < N; j += nt) { double v = alpha * s.p()[j]; v += s.x()[j]; x_step[j] = v; }
             c.sync();
-            cost_step = E::cost(c, o, x_step, s.d);
+            double viol_step;
+            merit_terms(c, o, x_step, s, cg, cost_step, viol_step);
             ++trials;
-            const double phi_l1_step = cost_step + mu * constraints_violation(c, o, x_step, s, cg);
-            if (phi_l1_step <= (phi_l1 + alpha * st.eta * Dp_phi_l1)) break;
+            const double phi_l1_step = cost_step + mu * viol_step;
+            if (phi_l1_step <= (phi_l1 + alpha * st.eta * Dp_phi_l1)) { accepted = true; break; }
             alpha = st.tau * alpha;
         }
 
         // ---- take the step (626-632)
-        const double primal_norm = alpha * norm_inf_cta(c, s.p, N);
-        const double dual_norm = alpha * norm_inf_cta(c, s.plam, DUAL);
-        for (int i = tid; i < N; i += nt) { const double sp = alpha * s.p[i]; s.x[i] += sp; s.step_prev[i] = sp; }
-        for (int i = tid; i < DUAL; i += nt) s.lam[i] += alpha * s.plam[i];
+        const double primal_norm = alpha * norm_inf_cta(c, s.p(), N);
+        const double dual_norm = alpha * norm_inf_cta(c, s.plam(), DUAL);
+        for (int i = tid; i < N; i += nt) { const double sp = alpha * s.p()[i]; s.x()[i] += sp; s.step_prev()[i] = sp; }
+        for (int i = tid; i < DUAL; i += nt) s.lam()[i] += alpha * s.plam()[i];
         c.sync();
-        // ---- termination_criteria_impl (523-529)
-        const double max_viol = max_constraints_violation(c, o, s.x, s, cg);
+        // ---- termination_criteria_impl (523-529).  x + (alpha p) == (alpha p) + x bit for bit, so after an accepted trial
+        // cg already holds the constraint values at the new x
+        const double max_viol = max_constraints_violation(c, o, s.x(), s, cg, accepted);
         const bool done = (primal_norm <= st.eps_prim) && (dual_norm <= st.eps_dual) && (max_viol <= st.eps_prim);
         if (tid == 0) {
-            s.stats[0] = cost_step; s.stats[1] = primal_norm; s.stats[2] = dual_norm; s.stats[3] = max_viol;
-            if (s.tr_alpha) s.tr_alpha[trace_row] = alpha;
-            if (s.tr_ls) s.tr_ls[trace_row] = trials;
+            s.stats()[0] = cost_step; s.stats()[1] = primal_norm; s.stats()[2] = dual_norm; s.stats()[3] = max_viol;
+            if (s.tr_alpha()) s.tr_alpha()[trace_row] = alpha;
+            if (s.tr_ls()) s.tr_ls()[trace_row] = trials;
         }
         return done;
     }
@@ -213,36 +284,36 @@ struct SqpDev {
     /** SQPBase::solve (sqp_base.hpp:568-696) of one instance: iterate linearise -> QP -> line search / step until the
      *  termination test holds or max_iter QPs were solved.  Lp / vec: QP workspaces (pmb_qp.hpp), scratch: SCRATCH_DOUBLES. */
     template <int R>
-    PMB_DEV static void solve(Cta& c, const O& o, const SqpInst& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
+    PMB_DEV static void solve(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* Lp, unsigned char* vec, double* scratch)
     {
-        if (c.tid() == 0) { s.info->iter = 1; s.info->qp_solver_iter = 0; s.info->status = PMB_SQP_MAX_ITER_EXCEEDED; }
+        if (c.tid() == 0) { s.info()->iter = 1; s.info()->qp_solver_iter = 0; s.info()->status = PMB_SQP_MAX_ITER_EXCEEDED; }
         QpArgs qa;
-        qa.N = N; qa.M = M; qa.H = s.H; qa.h = s.h; qa.A = s.A; qa.Alb = s.al; qa.Aub = s.au; qa.xlb = s.lx; qa.xub = s.ux;
-        qa.xg = nullptr; qa.yg = nullptr; qa.x = s.p; qa.y = s.plam; qa.info = s.qp_info; qa.z = nullptr; qa.q = nullptr;
-        qa.perm = nullptr; qa.ctype = nullptr; qa.nfac = s.qp_nfac;
+        qa.N = N; qa.M = M; qa.H = s.H(); qa.h = s.h(); qa.A = s.A(); qa.Alb = s.al(); qa.Aub = s.au(); qa.xlb = s.lx(); qa.xub = s.ux();
+        qa.xg = nullptr; qa.yg = nullptr; qa.x = s.p(); qa.y = s.plam(); qa.info = s.qp_info(); qa.z = nullptr; qa.q = nullptr;
+        qa.perm = nullptr; qa.ctype = nullptr; qa.nfac = s.qp_nfac();
         QpProf qprof;
-        qa.prof = s.phase ? &qprof : nullptr;
+        qa.prof = s.phase() ? &qprof : nullptr;
         c.sync();
         unsigned long long t_lin = 0, t_qp = 0, t_step = 0, n_it = 0;
         for (int it = 1; it <= st.max_iter; ++it) {
             const int row = it - 1;
             const unsigned long long t0 = c.w.clock();
-            linearise(c, o, s, it == 1, row, scratch);
+            const double cost_x = linearise(c, o, s, it == 1, row, scratch);
             const unsigned long long t1 = c.w.clock();
-            qp_solve_cta<R>(c, qst, qa, Lp, vec);
+            qp_solve_cta<R, N, M>(c, qst, qa, Lp, vec);
             const unsigned long long t2 = c.w.clock();
-            const bool done = step(c, o, s, st, row, scratch);
+            const bool done = step(c, o, s, st, row, scratch, cost_x);
             const unsigned long long t3 = c.w.clock();
             t_lin += t1 - t0; t_qp += t2 - t1; t_step += t3 - t2; ++n_it;
-            if (done) { if (c.tid() == 0) s.info->status = PMB_SQP_SOLVED; break; }
-            if (it < st.max_iter && c.tid() == 0) s.info->iter = it + 1;
+            if (done) { if (c.tid() == 0) s.info()->status = PMB_SQP_SOLVED; break; }
+            if (it < st.max_iter && c.tid() == 0) s.info()->iter = it + 1;
         }
-        if (s.phase && c.tid() == 0) {
-            atomic_add_u64(s.phase + 0, t_lin); atomic_add_u64(s.phase + 1, t_qp); atomic_add_u64(s.phase + 2, t_step); atomic_add_u64(s.phase + 3, n_it);
-            atomic_add_u64(s.phase + 4, qprof.pivot); atomic_add_u64(s.phase + 5, qprof.gather); atomic_add_u64(s.phase + 6, qprof.factor);
-            atomic_add_u64(s.phase + 7, qprof.solve); atomic_add_u64(s.phase + 8, qprof.update); atomic_add_u64(s.phase + 9, qprof.resid);
-            atomic_add_u64(s.phase + 10, (unsigned long long)s.info->qp_solver_iter);
+        if (s.phase() && c.tid() == 0) {
+            atomic_add_u64(s.phase() + 0, t_lin); atomic_add_u64(s.phase() + 1, t_qp); atomic_add_u64(s.phase() + 2, t_step); atomic_add_u64(s.phase() + 3, n_it);
+            atomic_add_u64(s.phase() + 4, qprof.pivot); atomic_add_u64(s.phase() + 5, qprof.gather); atomic_add_u64(s.phase() + 6, qprof.factor);
+            atomic_add_u64(s.phase() + 7, qprof.solve); atomic_add_u64(s.phase() + 8, qprof.update); atomic_add_u64(s.phase() + 9, qprof.resid);
+            atomic_add_u64(s.phase() + 10, (unsigned long long)s.info()->qp_solver_iter);
         }
         c.sync();
     }

@@ -229,7 +229,7 @@ inline int launch(int grid, size_t smem, void* /*stream*/, Args... args)
 {
     std::vector<unsigned char> sm(smem + 64);
     unsigned char* smp = sm.data() + ((16 - ((uintptr_t)sm.data() & 15)) & 15);
-    for (int blk = 0; blk < grid; ++blk) {
+    for (int blk = grid - 1; blk >= 0; --blk) {   // last block first: persistent kernels then run with a rotated warp numbering
         EmuBlock eb;
         eb.run(Body::THREADS, Body::EMU_STACK_BYTES, [&](int t) {
             Warp w{&eb, t};
@@ -241,7 +241,7 @@ inline int launch(int grid, size_t smem, void* /*stream*/, Args... args)
 
 /** emulator: a handful of "resident" CTAs (they run one after the other; the first drains the queue) */
 template <class Body, class... Args>
-inline int resident_ctas(size_t, Args...) { return 2; }
+inline int resident_ctas(size_t, Args...) { return 3; }
 
 } // namespace pmb
 #endif

@@ -200,8 +200,21 @@ def run_gpu(args):
         guess_x[:dims["NX"] * dims["NN"]] = np.tile(w_all.x_guess, dims["NN"])
     if w_all.u_guess is not None:
         guess_x[dims["NX"] * dims["NN"]:dims["NX"] * dims["NN"] + dims["NU"] * dims["NN"]] = np.tile(w_all.u_guess, dims["NN"])
-    guess_x_b = np.ascontiguousarray(np.tile(guess_x, (hi - lo, 1)))
-    guess_l_b = np.zeros((hi - lo, dims["DUAL"]))
+    def pinned(a):
+        """copy of `a` in page-locked host memory (numpy view of a pinned torch tensor)"""
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, dtype=a.dtype)).dtype).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        pinned.keep.append(t)
+        return v
+    pinned.keep = []
+    x0 = pinned(x0)
+    guess_x_b = pinned(np.tile(guess_x, (hi - lo, 1)))
+    guess_l_b = pinned(np.zeros((hi - lo, dims["DUAL"])))
+    out_x = pinned(np.zeros((hi - lo, dims["N"])))
+    out_info_t = torch.empty((hi - lo) * 12, dtype=torch.uint8).pin_memory()
+    from polympc_b200.capi import SQP_INFO_DTYPE
+    out_info = out_info_t.numpy().view(SQP_INFO_DTYPE)
 
     def barrier():
         if world > 1:
@@ -242,7 +255,7 @@ def run_gpu(args):
     h2d = x0.nbytes * 2 + guess_x_b.nbytes + guess_l_b.nbytes
     d2h = (hi - lo) * dims["N"] * 8 + (hi - lo) * 12
     for _ in range(max(1, args.warmup // 2)):
-        s.set_initial_conditions(x0); s.set_primal(guess_x_b); s.set_dual(guess_l_b); s.solve(); s.primal(); s.info()
+        s.set_initial_conditions(x0); s.set_primal(guess_x_b); s.set_dual(guess_l_b); s.solve(); s.primal(out_x); s.info(out_info)
     barrier()
     e0.record(stream)
     e2e_iters = 0
@@ -251,8 +264,8 @@ def run_gpu(args):
         s.set_primal(guess_x_b)
         s.set_dual(guess_l_b)
         s.solve()
-        xs = s.primal()
-        e2e_iters += int(s.info()["iter"].sum())
+        xs = s.primal(out_x)
+        e2e_iters += int(s.info(out_info)["iter"].sum())
     e1.record(stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

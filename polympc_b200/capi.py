@@ -454,8 +454,9 @@ class Sqp:
         self.api._chk(self.api._fn("sqp_get_kernel_times")(self.h, _p(ms), n.ctypes.data_as(C.POINTER(C.c_longlong))), "sqp_get_kernel_times")
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("sqp_linearise", "qp_box_admm", "sqp_linesearch_step"))}
 
-    def primal(self):
-        x = np.zeros((self.batch, self.d["N"]))
+    def primal(self, out=None):
+        """out: optional preallocated (e.g. pinned) float64 array of shape (batch, N)"""
+        x = np.zeros((self.batch, self.d["N"])) if out is None else out
         self.api._chk(self.api._fn("sqp_get_primal")(self.h, _p(x)), "sqp_get_primal")
         return x
 
@@ -464,8 +465,8 @@ class Sqp:
         self.api._chk(self.api._fn("sqp_get_dual")(self.h, _p(lam)), "sqp_get_dual")
         return lam
 
-    def info(self):
-        info = np.zeros(self.batch, dtype=SQP_INFO_DTYPE)
+    def info(self, out=None):
+        info = np.zeros(self.batch, dtype=SQP_INFO_DTYPE) if out is None else out
         self.api._chk(self.api._fn("sqp_get_info")(self.h, info.ctypes.data_as(C.c_void_p)), "sqp_get_info")
         return info
 

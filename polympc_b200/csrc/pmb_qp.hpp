@@ -199,10 +199,9 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
             for (int r = q; r < 4; ++r) b[r][q] = (r < nb) ? Lp[bc[q] + j0 + r] : 0.0;
         const int i0 = j0 + nb + tid;                          // the thread's first row below the panel
         const bool own = i0 < n;
-        const int i0c = own ? i0 : n - 1;                      // clamped: loads stay inside the matrix, stores are predicated
-        double av[4];
+        double av[4];                                          // threads without a row read the (read-only in P1) diagonal entry instead
         PMB_UNROLL
-        for (int q = 0; q < 4; ++q) av[q] = (q < nb) ? Lp[bc[q] + i0c] : 0.0;
+        for (int q = 0; q < 4; ++q) av[q] = (q < nb) ? Lp[bc[q] + (own ? i0 : j0 + q)] : 0.0;
         PMB_UNROLL
         for (int q = 0; q < 4; ++q) {
             d[q] = b[q][q];
@@ -266,11 +265,9 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
 #endif
         if (kfirst < n) {
             double nl[R][4];
-            int ic[R];                                         // the lane's row in chunk r, clamped into the matrix
             PMB_UNROLL
             for (int r = 0; r < R; ++r) {
                 const int i = lane + 32 * r;
-                ic[r] = i < n ? i : n - 1;
                 PMB_UNROLL
                 for (int q = 0; q < 4; ++q) nl[r][q] = (q < nb && i >= kfirst && i < n) ? -Lp[bc[q] + i] : 0.0;
             }
@@ -291,14 +288,20 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
                 double* ck = Lp + bk;
                 double* ck2 = Lp + bk2;
                 const int c0 = k >> 5;                         // first chunk with rows >= k (warp-uniform)
-                // one uniform dispatch per column pair, then straight-line code: unconditional loads (rows above the
-                // diagonal read the tail of earlier columns — valid memory, discarded), 4 chained FMAs, predicated stores
+                // one uniform dispatch per column pair, then straight-line code: unconditional loads (lanes whose row
+                // lies above the diagonal read an entry of the finished panel instead — nobody writes it in P2 — and
+                // discard it), 4 chained FMAs, predicated stores
+                const double* dummy = Lp + bc[0] + k;
                 PMB_UNROLL
                 for (int r0 = 0; r0 < R; ++r0) {
                     if (c0 == r0) {
                         double acc[R], acc2[R];
                         PMB_UNROLL
-                        for (int r = r0; r < R; ++r) { acc[r] = ck[ic[r]]; acc2[r] = ck2[ic[r]]; }
+                        for (int r = r0; r < R; ++r) {
+                            const int i = lane + 32 * r;
+                            acc[r] = *((i >= k && i < n) ? ck + i : dummy);
+                            acc2[r] = *((i >= k2c && i < n) ? ck2 + i : dummy);
+                        }
                         PMB_UNROLL
                         for (int q = 0; q < 4; ++q) {
                             if (q < nb) {

@@ -49,6 +49,20 @@ def measured_peaks():
         return None
 
 
+def ncu_traffic(csv_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` capture (profiles/), bytes per launch"""
+    try:
+        tot, unit_mul = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        found = 0
+        for line in open(os.path.join(ROOT, "profiles", csv_name)):
+            f = line.strip().split(",")
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * unit_mul.get(f[2], 1.0); found += 1
+        return tot if found == 2 else None
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = measured_peaks()
     if p and p.get("hbm_gbs"):
@@ -296,7 +310,9 @@ def run_gpu(args):
     achieved = iters_per_solve * b_iter / (kernel_ms * 1e-3) / 1e9
     cyc_tot = sum(phases.get(k, 0) for k in ("linearise", "qp", "step")) or 1
     roofline = {"kernel": "sqp_solve (fused persistent kernel: linearise + boxADMM/LDLT + line search, one CTA per instance)",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic("r1_sqp_solve_ncu_raw.csv") if (args.workload == "mobile_robot" and B == 8192) else None,
+                "traffic_source": "profiles/r1_sqp_solve_ncu_raw.csv (one ncu --set full capture of the same launch, batch 8192)",
                 "peak_source": peak_src, "avg_launch_ms": kernel_ms, "bytes_per_sqp_iteration": b_iter,
                 "sqp_iterations_per_launch": iters_per_solve,
                 "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
@@ -338,7 +354,8 @@ def run_gpu(args):
         bk = 8 * (N * N + M * N + (N + M) * (N + M))
         gbs = nb * bk / (kms * 1e-3) / 1e9
         kkt = {"kernel": "kkt_assemble_dense", "bytes_per_instance": bk, "batch": nb, "avg_launch_ms": kms, "achieved": gbs, "peak": peak,
-               "unit": "GB/s", "frac": gbs / peak, "working_set_mb": nb * bk / 1e6}
+               "unit": "GB/s", "frac": gbs / peak, "working_set_mb": nb * bk / 1e6,
+               "traffic": ncu_traffic("r1_kkt_assemble_ncu_raw.csv") if (args.workload == "mobile_robot" and nb == 8192) else None}
         launches_kkt = reps
         del H_d, A_d, K_d
     except Exception as e:   # never let the auxiliary measurement kill the bench line

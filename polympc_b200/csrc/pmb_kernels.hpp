@@ -153,7 +153,11 @@ struct BfgsBody {
  *  wave quantisation: a slow instance only occupies its own CTA). */
 template <class O>
 struct SqpSolveBody {
+#ifdef PMB_SQP_THREADS
+    static constexpr int THREADS = PMB_SQP_THREADS;
+#else
     static constexpr int THREADS = 128;
+#endif
     static constexpr const char* NAME = "sqp_solve";
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
     static constexpr int R = (O::N + O::M + 31) / 32;
@@ -199,7 +203,7 @@ struct SqpSolveBody {
             const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (b >= batch) break;
             const SqpInst<O> s{ws, b};
-            SqpDev<O>::template solve<R>(c, o, s, st, qst, Lp, vec, scratch);
+            SqpDev<O>::template solve<R, THREADS / 32>(c, o, s, st, qst, Lp, vec, scratch);
         }
     }
 };

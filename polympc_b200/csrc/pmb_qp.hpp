@@ -488,7 +488,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
 
 /** the whole boxADMM solve of one instance by one CTA.  Lp: n(n+1)/2 doubles (shared or global), vec: qp_vec_bytes() of
  *  shared memory. */
-template <int R, int NC = 0, int MC = 0>   // NC, MC: problem size when it is known at compile time (fused SQP kernel), 0 = a.N, a.M
+template <int R, int NC = 0, int MC = 0, int NW = 4>   // NC, MC: problem size when known at compile time (fused SQP kernel), 0 = a.N, a.M; NW: warps per CTA
 PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec)
 {
     const int N = NC > 0 ? NC : a.N, M = (NC > 0) ? MC : a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
@@ -616,7 +616,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
         c.sync();
         const unsigned long long tb = prof ? c.w.clock() : 0;
-        ldlt_solve_packed<R>(c, n, Lp, perm, sol, tmp);
+        ldlt_solve_packed<R, NW>(c, n, Lp, perm, sol, tmp);
         const unsigned long long tc = prof ? c.w.clock() : 0;
         // z, y_A (126, 133-135, 142-144)
         for (int i = tid; i < M; i += nt) {

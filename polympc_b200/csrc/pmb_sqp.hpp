@@ -283,7 +283,7 @@ struct SqpDev {
 
     /** SQPBase::solve (sqp_base.hpp:568-696) of one instance: iterate linearise -> QP -> line search / step until the
      *  termination test holds or max_iter QPs were solved.  Lp / vec: QP workspaces (pmb_qp.hpp), scratch: SCRATCH_DOUBLES. */
-    template <int R>
+    template <int R, int NW>
     PMB_DEV static void solve(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* Lp, unsigned char* vec, double* scratch)
     {
@@ -296,18 +296,19 @@ struct SqpDev {
         qa.prof = s.phase() ? &qprof : nullptr;
         c.sync();
         unsigned long long t_lin = 0, t_qp = 0, t_step = 0, n_it = 0;
-        for (int it = 1; it <= st.max_iter; ++it) {
+        for (int it = 1; ; ++it) {                   // the first iteration always runs (sqp_base.hpp:583-637 precede the loop)
             const int row = it - 1;
             const unsigned long long t0 = c.w.clock();
             const double cost_x = linearise(c, o, s, it == 1, row, scratch);
             const unsigned long long t1 = c.w.clock();
-            qp_solve_cta<R, N, M>(c, qst, qa, Lp, vec);
+            qp_solve_cta<R, N, M, NW>(c, qst, qa, Lp, vec);
             const unsigned long long t2 = c.w.clock();
             const bool done = step(c, o, s, st, row, scratch, cost_x);
             const unsigned long long t3 = c.w.clock();
             t_lin += t1 - t0; t_qp += t2 - t1; t_step += t3 - t2; ++n_it;
             if (done) { if (c.tid() == 0) s.info()->status = PMB_SQP_SOLVED; break; }
-            if (it < st.max_iter && c.tid() == 0) s.info()->iter = it + 1;
+            if (it >= st.max_iter) break;
+            if (c.tid() == 0) s.info()->iter = it + 1;
         }
         if (s.phase() && c.tid() == 0) {
             atomic_add_u64(s.phase() + 0, t_lin); atomic_add_u64(s.phase() + 1, t_qp); atomic_add_u64(s.phase() + 2, t_step); atomic_add_u64(s.phase() + 3, n_it);

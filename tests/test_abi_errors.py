@@ -1,0 +1,52 @@
+"""Error behaviour of the C ABI (argument checking happens before any device work, so the warp-emulator build exercises the
+same code on a CPU).  The reference reports problems through status enums and never throws; the C layer returns negative
+pmb_error_t codes and keeps a message in pmb_last_error()."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from polympc_b200.capi import PmbError
+
+
+def test_unknown_problem(emu):
+    with pytest.raises(PmbError):
+        emu.sqp("no_such_problem", 4)
+    with pytest.raises(PmbError):
+        emu.ocp("no_such_problem")
+    assert emu._fn("sqp_create")(b"mobile_robot_6x2", 0, 0) is None      # non-positive batch
+
+
+def test_null_and_size_checks(emu):
+    s = emu.sqp("mobile_robot_6x2", 2)
+    f = emu._fn
+    assert f("sqp_set_bounds_x")(s.h, None, None, 65) == -2              # PMB_ERR_BAD_ARGUMENT
+    v = np.zeros(2 * 65)
+    p = v.ctypes.data_as(C.POINTER(C.c_double))
+    assert f("sqp_set_bounds_x")(s.h, p, p, 64) == -2                    # stride must be 0 or N
+    assert f("sqp_set_initial_conditions")(s.h, None, None) == -2
+    assert f("sqp_get_primal")(s.h, None) == -2
+    assert f("sqp_solve")(None) == -2
+    assert "bad" in emu.last_error() or "null" in emu.last_error()
+    o = emu.ocp("mobile_robot_6x2")
+    with pytest.raises(PmbError):
+        o.set_params(np.zeros(3))                                         # NPARAM is 8
+    assert f("ocp_cost")(o.h, 1, p, None, p) == -2                       # static parameters required (ND = 1)
+    assert f("cheb_tables")(1, p, p, p) == -2
+    st = emu.sqp_default_qp_settings()
+    assert f("qp_solve")(0, 0, 1, p, p, p, p, p, p, p, None, None, C.byref(st), p, p, None, None, None, None, None, None) == -2
+    s.close()
+
+
+def test_zero_max_iter_and_empty_work(emu, orc):
+    """max_iter = 0: like the reference (sqp_base.hpp:583-637 precede the while loop) exactly one iteration is done"""
+    from polympc_b200 import workloads as W
+    w = W.mobile_robot(2, sqp_max_iter=0)
+    out = []
+    for api in (emu, orc):
+        s = api.sqp(w.name, 2); W.configure(s, w); s.solve()
+        info = s.info()
+        assert (info["iter"] == 1).all() and (info["status"] == 1).all() and (info["qp_solver_iter"] > 0).all()
+        out.append(s.primal())
+        s.close()
+    assert np.array_equal(out[0], out[1])

@@ -159,6 +159,45 @@ def test_sqp_full_size_properties(pmb, orc):
     pc.assert_same(r["lam"][sub], rb["lam"], "sample vs oracle lam")
 
 
+def test_cstr_full_size_properties(pmb, orc):
+    """BASELINE config 3 at full size (CSTR 5x2, batch 4096)"""
+    B = 4096
+    w = W.cstr(B)
+    r = pc.solve_workload(pmb, w)
+    info = r["info"]
+    assert (info["status"] == 0).mean() > 0.99            # cstr_control_test.cpp:177 asserts SOLVED
+    solved = info["status"] == 0
+    x = r["x"]
+    assert np.isfinite(x).all()
+    assert np.abs(x[solved, 40:44] - w.x0[solved]).max() < 1e-2 * 100         # initial condition (states ~100) to QP tolerance
+    u = x[:, 44:].reshape(B, 11, 2)
+    assert u[solved, :, 0].min() >= 3.0 - 1e-2 and u[solved, :, 0].max() <= 35.0 + 1e-2
+    assert u[solved, :, 1].min() >= -9000.0 - 1.0 and u[solved, :, 1].max() <= 0.0 + 1.0
+    sub = np.random.default_rng(1).permutation(B)[:48]
+    w2 = W.cstr(B); w2.x0 = w.x0[sub]
+    rb = pc.solve_workload(orc, w2)
+    pc.assert_same(x[sub], rb["x"], "sample vs oracle x")
+    pc.assert_same(info["iter"][sub], rb["info"]["iter"], "sample vs oracle iter")
+
+
+def test_kite_full_size_properties(pmb, orc):
+    """BASELINE config 4 at full size (kite 12x1, batch 1024; factor in the L2-resident global slot)"""
+    B = 1024
+    w = W.kite(B)
+    r = pc.solve_workload(pmb, w)
+    info = r["info"]
+    assert (info["status"] == 0).mean() > 0.95
+    x = r["x"]
+    assert np.isfinite(x).all()
+    solved = info["status"] == 0
+    assert np.abs(x[solved, 156:169] - w.x0[solved]).max() < 1e-2             # initial condition on the last state block
+    sub = np.random.default_rng(2).permutation(B)[:8]
+    w2 = W.kite(B); w2.x0 = w.x0[sub]
+    rb = pc.solve_workload(orc, w2)
+    pc.assert_same(x[sub], rb["x"], "sample vs oracle x")
+    pc.assert_same(r["lam"][sub], rb["lam"], "sample vs oracle lam")
+
+
 def test_warm_restart_matches_oracle(pmb, orc):
     """MPC re-solve: a second solve() warm-starts from the kept (x, lam) (mpc_wrapper.hpp / sqp_base.hpp:568-696).
     One instance of this batch re-linearises to an indefinite exact Hessian and boxADMM diverges to inf/NaN on BOTH sides

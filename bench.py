@@ -121,12 +121,13 @@ def build_workload(args, n_inst: int, offset_seed: int = 0):
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the CPU restatement of the reference algorithm (oracle/), timed on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int):
+def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int, keep=None):
     from oracle import pyoracle   # the one place bench.py executes oracle/: as the timed CPU arm
     orc = pyoracle.load()
     cores = os.cpu_count() or 1
     pyoracle.set_num_threads(cores)
-    w = build_workload(args, n_inst)
+    w = build_workload(args, max(args.batch, n_inst))        # the GPU arm's workload ...
+    w.x0 = np.ascontiguousarray(w.x0[:n_inst])               # ... of which the CPU arm solves the first n_inst instances
     s = orc.sqp(w.name, n_inst)
     W.configure(s, w)
     total_it, total_t = 0, 0.0
@@ -137,6 +138,8 @@ def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if k >= warmup:
             total_it += int(s.info()["iter"].sum()); total_t += dt
+    if keep is not None:
+        keep["x"] = s.primal(); keep["lam"] = s.dual(); keep["info"] = s.info()
     s.close()
     return total_it / total_t, total_t / max(steps, 1), cores, total_it
 
@@ -363,8 +366,25 @@ def run_gpu(args):
 
     # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------------------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, t_step, cores, _ = cpu_solve_rate(args, args.cpu_sample, 1, 0)
+        kept = {}
+        rate, t_step, cores, _ = cpu_solve_rate(args, args.cpu_sample, 1, 0, keep=kept)
+        # the CPU leg solved the first cpu_sample instances of the same workload: compare the GPU's results for them
+        s.reset_guess(); s.solve()
+        ns = min(args.cpu_sample, hi - lo)
+        xg, lg, ig = s.primal()[:ns], s.dual()[:ns], s.info()[:ns]
+        xc, lc, ic = kept["x"][:ns], kept["lam"][:ns], kept["info"][:ns]
+        fin = np.isfinite(xc).all(axis=1) & np.isfinite(xg).all(axis=1)
+        same_x = ((xg == xc) | (np.isnan(xg) & np.isnan(xc))).all(axis=1)
+        same_l = ((lg == lc) | (np.isnan(lg) & np.isnan(lc))).all(axis=1)
+        denom = np.maximum(1.0, np.abs(xc[fin]).max(axis=1)) if fin.any() else np.ones(1)
+        rel = (np.abs(xg[fin] - xc[fin]).max(axis=1) / denom) if fin.any() else np.zeros(1)
+        parity = {"instances": int(ns), "max_rel_inf_x": float(rel.max()), "tolerance": 1e-10,
+                  "bit_identical_x_pct": 100.0 * float(same_x.mean()), "bit_identical_lam_pct": 100.0 * float(same_l.mean()),
+                  "identical_iteration_counts_pct": 100.0 * float((ig["iter"] == ic["iter"]).mean()),
+                  "identical_status_pct": 100.0 * float((ig["status"] == ic["status"]).mean()),
+                  "against": "CPU restatement (oracle/) on the same inputs"}
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {args.cpu_sample} instances of the same workload, one solve to convergence ({t_step:.1f} s), all host cores",
                "note": "CPU restatement of PolyMPC's algorithm (oracle/); Eigen is absent so the reference itself cannot be built"}
@@ -378,7 +398,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "kkt_kernel": kkt, "cpu_baseline": cpu,
+            "roofline": roofline, "kkt_kernel": kkt, "cpu_baseline": cpu, "parity": parity,
             "sqp_iterations_per_step": total_iters / args.steps, "solved_fraction": solved_frac,
             "mean_sqp_iter_per_instance": iters_per_solve / (hi - lo),
         }

@@ -54,6 +54,19 @@ struct RobotModel {
 };
 
 // =====================================================================================================================
+/** mobile robot with one generic inequality constraint per node (NG = 1): squared distance to a disc-shaped obstacle,
+ *  lbg <= g(x) <= ubg.  Not a reference test case; it exercises the NG > 0 paths of the transcription
+ *  (continuous_ocp.hpp:546-575, 769-782, 2150-2157) and of the SQP (sqp_base.hpp:425-443, 457-465, 588-593). */
+struct RobotObstacleModel : RobotModel {
+    static constexpr int NG = 1;
+    template <class T>
+    void ineq(const T* x, const T*, const T*, const double*, double, T* g) const
+    {
+        g[0] = (x[0] - 0.25) * (x[0] - 0.25) + (x[1] - 0.25) * (x[1] - 0.25);
+    }
+};
+
+// =====================================================================================================================
 struct CstrModel {
     static constexpr int NX = 4, NU = 2, NP = 0, ND = 0, NG = 0;
     static constexpr int NPARAM = 16 + 4 + 16 + 4 + 2;

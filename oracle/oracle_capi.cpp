@@ -145,6 +145,7 @@ const Registry g_registry[] = {
     REG("cstr_5x2", CstrModel, 5, 2),            // cstr_control_test.cpp, BASELINE.json config 3
     REG("kite_12x1", KiteModel, 12, 1),          // BASELINE.json config 4 (our model)
     REG("kite_4x2", KiteModel, 4, 2),            // small kite variant for fast parity tests
+    REG("robot_obstacle_5x2", RobotObstacleModel, 5, 2),   // NG = 1: generic inequality constraints
 };
 const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
 const Registry* find(const char* name)

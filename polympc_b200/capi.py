@@ -314,6 +314,12 @@ class Ocp:
         self.api._chk(self.api._fn("ocp_equalities")(self.h, B, _p(var), _p(dd), _p(c)), "ocp_equalities")
         return c
 
+    def inequalities(self, var, d=None):
+        var, dd, B = self._in(var, d)
+        g = np.zeros((B, self.d["NG"] * self.d["NN"]))
+        self.api._chk(self.api._fn("ocp_inequalities")(self.h, B, _p(var), _p(dd), _p(g)), "ocp_inequalities")
+        return g
+
     def equalities_linearised(self, var, d=None):
         var, dd, B = self._in(var, d)
         ne, N = self.d["NX"] * self.d["NN"], self.d["N"]

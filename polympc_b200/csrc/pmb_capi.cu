@@ -21,6 +21,7 @@ PMB_DECLARE_PROBLEM(mobile_robot_5x3)
 PMB_DECLARE_PROBLEM(cstr_5x2)
 PMB_DECLARE_PROBLEM(kite_12x1)
 PMB_DECLARE_PROBLEM(kite_4x2)
+PMB_DECLARE_PROBLEM(robot_obstacle_5x2)
 
 namespace pmb {
 namespace {
@@ -36,6 +37,7 @@ const Registry g_registry[] = {
     PMB_REG("cstr_5x2", cstr_5x2),                   // reference cstr_control_test.cpp, BASELINE.json config 3
     PMB_REG("kite_12x1", kite_12x1),                 // BASELINE.json config 4 (our model)
     PMB_REG("kite_4x2", kite_4x2),                   // small kite variant for fast parity tests
+    PMB_REG("robot_obstacle_5x2", robot_obstacle_5x2),   // NG = 1: generic inequality constraints
 };
 const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
 const Registry* find_problem(const char* name)

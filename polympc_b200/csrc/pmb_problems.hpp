@@ -58,6 +58,17 @@ struct MobileRobot {
     template <class T> PMB_HD void ineq(const T*, const T*, const T*, const double*, double, T*) const {}
 };
 
+/** mobile robot with one generic inequality constraint per node (NG = 1): squared distance to a disc-shaped obstacle.
+ *  Exercises the NG > 0 paths (reference continuous_ocp.hpp:546-575, 769-782, 2150-2157; sqp_base.hpp:425-443, 457-465). */
+struct MobileRobotObstacle : MobileRobot {
+    static constexpr int NG = 1;
+    template <class T>
+    PMB_HD void ineq(const T* x, const T*, const T*, const double*, double, T* g) const
+    {
+        g[0] = (x[0] - 0.25) * (x[0] - 0.25) + (x[1] - 0.25) * (x[1] - 0.25);
+    }
+};
+
 struct Cstr {
     static constexpr int NX = 4, NU = 2, NP = 0, ND = 0, NG = 0, NPARAM = 16 + 4 + 16 + 4 + 2;
     double Q[16], R[4], P[16], xs[4], us[2];  // column-major dense, cstr_control_test.cpp:40-50

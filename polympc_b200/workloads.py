@@ -25,6 +25,8 @@ class Workload:
     u_guess: np.ndarray | None = None
     sqp_max_iter: int = 100
     ls_max_iter: int = 100
+    g_lb: np.ndarray | None = None       # (NG,) bounds of the generic inequality constraints, same at every node
+    g_ub: np.ndarray | None = None
     meta: dict = field(default_factory=dict)
 
     @property
@@ -38,6 +40,17 @@ def mobile_robot(batch: int, seed: int = 20260117 + 2, grid: str = "6x2", sqp_ma
     return Workload(f"mobile_robot_{grid}", 0.0, 2.0, np.array([2.0]), np.array([-1.5, -0.75]), np.array([1.5, 0.75]), x0,
                     sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
                     meta={"x0": "U([-1,1]^2 x [-pi/4,pi/4])", "seed": seed})
+
+
+def robot_obstacle(batch: int, seed: int = 20260117 + 6, sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
+    """mobile robot 5x2 that has to keep a distance of 0.3 from an obstacle at (0.25, 0.25): NG = 1 (not a reference case)"""
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0, 2 * np.pi, batch)
+    rad = rng.uniform(0.6, 1.0, batch)
+    x0 = np.column_stack([0.25 + rad * np.cos(ang), 0.25 + rad * np.sin(ang), rng.uniform(-np.pi / 4, np.pi / 4, batch)])
+    return Workload("robot_obstacle_5x2", 0.0, 2.0, np.array([2.0]), np.array([-1.5, -0.75]), np.array([1.5, 0.75]), x0,
+                    sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter, g_lb=np.array([0.09]), g_ub=np.array([np.inf]),
+                    meta={"x0": "ring of radius 0.6-1.0 around the obstacle", "seed": seed})
 
 
 def cstr(batch: int, seed: int = 20260117 + 3, sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
@@ -64,7 +77,7 @@ def kite(batch: int, seed: int = 20260117 + 4, grid: str = "12x1", sqp_max_iter:
                     meta={"x0": "nominal +- 5 %", "seed": seed})
 
 
-WORKLOADS = {"mobile_robot": mobile_robot, "cstr": cstr, "kite": kite}
+WORKLOADS = {"mobile_robot": mobile_robot, "cstr": cstr, "kite": kite, "robot_obstacle": robot_obstacle}
 
 
 def bounds_x(dims: dict, w: Workload):
@@ -88,6 +101,11 @@ def configure(solver, w: Workload, lo: int = 0, hi: int | None = None) -> None:
     solver.set_settings(st)
     lbx, ubx = bounds_x(d, w)
     solver.set_bounds_x(lbx, ubx)
+    if d["NG"] > 0:
+        ng = d["NG"] * d["NN"]
+        lbg = np.full(ng, -np.inf) if w.g_lb is None else np.tile(np.asarray(w.g_lb, dtype=np.float64), d["NN"])
+        ubg = np.full(ng, np.inf) if w.g_ub is None else np.tile(np.asarray(w.g_ub, dtype=np.float64), d["NN"])
+        solver.set_bounds_g(lbg, ubg)
     if d["ND"] > 0:
         solver.set_parameters(np.asarray(w.d, dtype=np.float64))
     guess = np.zeros(d["N"])

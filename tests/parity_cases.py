@@ -13,12 +13,13 @@ PROBLEM_SETUP = {
     "cstr_5x2": dict(t=(0.0, 100.0), d=None),
     "kite_4x2": dict(t=(0.0, 0.5), d=4.0),
     "kite_12x1": dict(t=(0.0, 0.5), d=4.0),
+    "robot_obstacle_5x2": dict(t=(0.0, 2.0), d=2.0),
 }
 
 
 def sample_var(name, dims, B, rng):
     N, NX, NU, NN = dims["N"], dims["NX"], dims["NU"], dims["NN"]
-    if name.startswith("mobile_robot"):
+    if name.startswith("mobile_robot") or name.startswith("robot_obstacle"):
         var = rng.uniform(-1.0, 1.0, (B, N))
     elif name.startswith("cstr"):
         x = np.array([2.0, 1.0, 110.0, 108.0]) + rng.uniform(-1, 1, (B, NN, NX)) * np.array([0.5, 0.3, 5.0, 5.0])
@@ -54,6 +55,8 @@ def ocp_case(api, orc, name, B=3, seed=0):
     lam = rng.uniform(-2, 2, (B, D["DUAL"]))
     assert_same(oa.cost(var, d), ob.cost(var, d), "cost")
     assert_same(oa.equalities(var, d), ob.equalities(var, d), "equalities")
+    if D["NG"] > 0:
+        assert_same(oa.inequalities(var, d), ob.inequalities(var, d), "inequalities")
     for x, y, n in zip(oa.equalities_linearised(var, d), ob.equalities_linearised(var, d), ("c", "jac")):
         assert_same(x, y, "equalities_linearised." + n)
     for x, y, n in zip(oa.cost_gradient(var, d), ob.cost_gradient(var, d), ("cost", "grad")):

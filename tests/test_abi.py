@@ -51,7 +51,7 @@ def test_library_contains_sm100a_code():
 def test_registry_and_dims(pmb, orc):
     names = pmb.problems()
     assert names == orc.problems()
-    assert {"mobile_robot_6x2", "cstr_5x2", "kite_12x1"} <= set(names)
+    assert {"mobile_robot_6x2", "cstr_5x2", "kite_12x1", "robot_obstacle_5x2"} <= set(names)
     d = pmb.dims("mobile_robot_6x2")
     assert (d["NX"], d["NU"], d["NN"], d["N"], d["M"], d["DUAL"]) == (3, 2, 13, 65, 39, 104)
     d = pmb.dims("cstr_5x2")

@@ -8,7 +8,7 @@ import parity_cases as pc
 from polympc_b200 import workloads as W
 
 
-@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2"])
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "robot_obstacle_5x2"])
 def test_ocp_operators(emu, orc, name):
     pc.ocp_case(emu, orc, name, B=2, seed=1)
 
@@ -85,3 +85,9 @@ def test_qp_nan_and_inf_data(emu, orc):
         pc.assert_same(ra[k], rb[k], "qp." + k)
     for f in ("status", "iter"):
         pc.assert_same(ra["info"][f], rb["info"][f], "qp.info." + f)
+
+
+def test_sqp_inequality_constraints(emu, orc):
+    """NG = 1 (obstacle avoidance): inequality rows in the QP, lbg/ubg in the merit function and the termination test"""
+    w = W.robot_obstacle(2, sqp_max_iter=6, ls_max_iter=10)
+    pc.sqp_case(emu, orc, w)

@@ -20,7 +20,7 @@ def test_device_present(pmb):
     assert "sm_100a" in pmb.version()
 
 
-@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1"])
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1", "robot_obstacle_5x2"])
 def test_ocp_operators(pmb, orc, name):
     pc.ocp_case(pmb, orc, name, B=37, seed=1)
 
@@ -157,6 +157,17 @@ def test_sqp_full_size_properties(pmb, orc):
     rb = pc.solve_workload(orc, w3)
     pc.assert_same(x[sub], rb["x"], "sample vs oracle x")
     pc.assert_same(r["lam"][sub], rb["lam"], "sample vs oracle lam")
+
+
+def test_sqp_inequality_constraints_vs_oracle(pmb, orc):
+    """NG = 1 (obstacle avoidance): bit-exact vs oracle, and the constraint holds on converged instances"""
+    w = W.robot_obstacle(192)
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    solved = ra["info"]["status"] == 0
+    assert solved.mean() > 0.7
+    X = ra["x"][:, :33].reshape(-1, 11, 3)
+    g = (X[:, :, 0] - 0.25) ** 2 + (X[:, :, 1] - 0.25) ** 2
+    assert g[solved].min() >= 0.09 - 1e-3
 
 
 def test_cstr_full_size_properties(pmb, orc):

@@ -86,6 +86,14 @@ void pmb_qp_default_settings(pmb_qp_settings_t* s);      /* qp_base.hpp:17-53 de
 void pmb_sqp_default_settings(pmb_sqp_settings_t* s);    /* sqp_base.hpp:24-34 defaults */
 void pmb_sqp_default_qp_settings(pmb_qp_settings_t* s);  /* defaults after the SQPBase ctor overrides, sqp_base.hpp:83-90 */
 
+/* Deterministic fp64 elementary functions used by every problem functor and by the Chebyshev tables (csrc/pmb_detmath.h):
+ * the same IEEE-only algorithms on host and device, so that decisions taken on their results are reproducible.  They stand
+ * in for the std:: calls of the reference's AutoDiffScalar chain rules (src/autodiff/AutoDiffScalar.h:592-684).
+ * out[i] = fn(x[i]) or fn(x[i], y[i]) evaluated ON THE DEVICE; y may be NULL for unary functions. */
+typedef enum pmb_dm_fn { PMB_DM_SIN = 0, PMB_DM_COS, PMB_DM_TAN, PMB_DM_EXP, PMB_DM_LOG, PMB_DM_ATAN2, PMB_DM_ASIN, PMB_DM_ACOS,
+                         PMB_DM_SINH, PMB_DM_COSH, PMB_DM_TANH, PMB_DM_POW, PMB_DM_SQRT, PMB_DM_COUNT } pmb_dm_fn_t;
+int pmb_dm_eval(int fn, int n, const double* x, const double* y, double* out);
+
 /* a1: Chebyshev<P, GAUSS_LOBATTO>::compute_nodes / compute_diff_matrix / compute_int_weights
  *     (src/polynomials/ebyshev.hpp:111-117, 198-214, 120-159).  nodes[P+1], D[(P+1)^2] column-major, w[P+1]. */
 int pmb_cheb_tables(int P, double* nodes, double* D, double* w);

@@ -486,6 +486,12 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf
 double pmb_sqp_last_solve_ms(const pmb_sqp_t*) { return 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t*) { return 0; }
 int pmb_sqp_set_stream(pmb_sqp_t*, void*) { return PMB_OK; }
+int pmb_dm_eval(int fn, int n, const double* x, const double* y, double* out)
+{
+    if (fn < 0 || fn >= PMB_DM_COUNT || n < 0 || !x || !out) return PMB_ERR_BAD_ARGUMENT;
+    for (int i = 0; i < n; ++i) out[i] = pmb::dm::dm_dispatch(fn, x[i], y ? y[i] : 0.0);   // the host instantiation of the same header
+    return PMB_OK;
+}
 int pmb_sqp_set_profiling(pmb_sqp_t*, int) { return PMB_OK; }
 int pmb_sqp_get_phase_cycles(const pmb_sqp_t*, unsigned long long* c) { if (c) for (int k = 0; k < 16; ++k) c[k] = 0; return PMB_OK; }
 int pmb_sqp_get_kernel_times(const pmb_sqp_t*, double* ms, long long* n) { for (int k = 0; k < 3; ++k) { if (ms) ms[k] = 0; if (n) n[k] = 0; } return PMB_OK; }

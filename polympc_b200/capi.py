@@ -52,7 +52,7 @@ INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = 0, 1, 2
 # every function name declared in include/polympc_b200.h (checked against the header by tests/test_abi.py)
 ABI_FUNCTIONS = [
     "version", "last_error", "device_count", "problem_count", "problem_name", "problem_dims",
-    "qp_default_settings", "sqp_default_settings", "sqp_default_qp_settings", "cheb_tables",
+    "qp_default_settings", "sqp_default_settings", "sqp_default_qp_settings", "dm_eval", "cheb_tables",
     "ocp_create", "ocp_destroy", "ocp_dims", "ocp_set_params", "ocp_get_params", "ocp_set_time_limits", "ocp_time_nodes",
     "ocp_cost", "ocp_equalities", "ocp_inequalities", "ocp_equalities_linearised", "ocp_cost_gradient",
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian",
@@ -111,6 +111,7 @@ class CApi:
         g("ocp_lagrangian_gradient").argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 8
         g("ocp_lagrangian_gradient_hessian").argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 9
         g("cheb_tables").argtypes = [C.c_int, c_double_p, c_double_p, c_double_p]
+        g("dm_eval").argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
         g("qp_solve").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 9 + [C.POINTER(QpSettings)] + \
             [c_double_p, c_double_p, C.c_void_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p]
         g("kkt_assemble").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 4 + [C.c_double, c_double_p]
@@ -194,6 +195,16 @@ class CApi:
         s = QpSettings()
         self._fn("sqp_default_qp_settings")(C.byref(s))
         return s
+
+    DM_FUNCTIONS = ("sin", "cos", "tan", "exp", "log", "atan2", "asin", "acos", "sinh", "cosh", "tanh", "pow", "sqrt")
+
+    def dm_eval(self, fn: str, x, y=None):
+        """deterministic elementary function `fn` of csrc/pmb_detmath.h applied element-wise"""
+        x = _f64(x).ravel()
+        yy = None if y is None else _f64(y).ravel()
+        out = np.zeros_like(x)
+        self._chk(self._fn("dm_eval")(self.DM_FUNCTIONS.index(fn), x.size, _p(x), _p(yy), _p(out)), "dm_eval")
+        return out
 
     def cheb_tables(self, P: int):
         nodes = np.zeros(P + 1)

@@ -197,6 +197,33 @@ void pmb_sqp_default_qp_settings(pmb_qp_settings_t* s)
     s->adaptive_rho = 1; s->adaptive_rho_interval = 50; s->alpha = 1.0;
 }
 
+struct DmEvalBody {
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr const char* NAME = "dm_eval";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char*, int fn, int n, const double* x, const double* y, double* out)
+    {
+        const int e = blk * THREADS + w.tid();
+        if (e < n) out[e] = dm::dm_dispatch(fn, x[e], y ? y[e] : 0.0);
+    }
+};
+
+int pmb_dm_eval(int fn, int n, const double* x, const double* y, double* out)
+{
+    if (fn < 0 || fn >= PMB_DM_COUNT || n < 0 || !x || !out) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "dm_eval: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (n == 0) return PMB_OK;
+    Staging st;
+    const double* dx = st.in(x, (size_t)n); const double* dy = st.in(y, (size_t)n);
+    double* dout = st.out(out, (size_t)n);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!rt_launch<DmEvalBody>((n + DmEvalBody::THREADS - 1) / DmEvalBody::THREADS, 0, st.s, fn, n, dx, dy, dout)) return PMB_ERR_CUDA;
+    st.back(out, (const double*)dout, (size_t)n);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
 int pmb_cheb_tables(int P, double* nodes, double* D, double* w)
 {
     if (P < 2 || P > 64 || !nodes || !D || !w) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "cheb_tables: bad argument");

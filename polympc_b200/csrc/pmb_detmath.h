@@ -155,11 +155,37 @@ PMB_HD int rem_pio2(double x, double& y0, double& y1)
     return (int)q;
 }
 
+/** exact remainder ax mod C for finite ax >= 0 (every subtraction is exact by Sterbenz' lemma: y <= ax < 2y) */
+PMB_HD double fmod_pos(double ax, double C)
+{
+    if (ax < C) return ax;
+    const int ex = (int)((to_bits(ax) >> 52) & 0x7ff) - (int)((to_bits(C) >> 52) & 0x7ff);
+    double y = C * pow2i(ex);
+    if (y > ax) y *= 0.5;
+    while (y >= C) {
+        if (ax >= y) ax -= y;
+        y *= 0.5;
+    }
+    return ax;
+}
+
+/** arguments beyond the range of the Cody-Waite reduction are first folded, exactly, modulo C = fl(2^18 * 2 pi): the result
+ *  stays a sine/cosine of a nearby angle (|value| <= 1, phase error <= |x| * 2^-53) instead of degenerating — at such
+ *  magnitudes the spacing of doubles exceeds 2 pi anyway.  Same operations on host and device. */
+PMB_HD double fold_large(double x)
+{
+    const double C = 1647099.3291652855;   // fl(2^20 * pi / 2)
+    if (fabs(x) < C) return x;
+    const double r = fmod_pos(fabs(x), C);
+    return x < 0.0 ? -r : r;
+}
+
 } // namespace detail
 
 PMB_HD double sin(double x)
 {
     if (isnan(x) || fabs(x) == inf()) return nan();
+    x = detail::fold_large(x);
     if (fabs(x) <= 0.78539816339744830962) {
         if (fabs(x) < 7.450580596923828125e-09) return x;  // 2^-27
         return detail::k_sin(x, 0.0, 0);
@@ -177,6 +203,7 @@ PMB_HD double sin(double x)
 PMB_HD double cos(double x)
 {
     if (isnan(x) || fabs(x) == inf()) return nan();
+    x = detail::fold_large(x);
     if (fabs(x) <= 0.78539816339744830962) {
         if (fabs(x) < 7.450580596923828125e-09) return 1.0;
         return detail::k_cos(x, 0.0);
@@ -400,6 +427,27 @@ PMB_HD double pow(double x, double y)
     if (x < 0.0) return nan();
     if (x == 0.0) return y > 0.0 ? 0.0 : inf();
     return exp(y * log(x));
+}
+
+/** function table of pmb_dm_eval (include/polympc_b200.h, enum pmb_dm_fn) */
+PMB_HD double dm_dispatch(int fn, double x, double y)
+{
+    switch (fn) {
+    case 0: return sin(x);
+    case 1: return cos(x);
+    case 2: return tan(x);
+    case 3: return exp(x);
+    case 4: return log(x);
+    case 5: return atan2(x, y);
+    case 6: return asin(x);
+    case 7: return acos(x);
+    case 8: return sinh(x);
+    case 9: return cosh(x);
+    case 10: return tanh(x);
+    case 11: return pow(x, y);
+    case 12: return sqrt(x);
+    }
+    return nan();
 }
 
 } // namespace dm

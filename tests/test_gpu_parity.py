@@ -228,4 +228,5 @@ def test_warm_restart_matches_oracle(pmb, orc):
     finite = np.isfinite(outs[1][0]).all(axis=1)
     assert finite.sum() >= 30
     pc.assert_same(outs[0][1][finite], outs[1][1][finite], "lam (finite instances)")
-    assert not np.isfinite(outs[0][1][~finite]).all()
+    if (~finite).any():
+        assert not np.isfinite(outs[0][1][~finite]).all()

@@ -81,6 +81,11 @@ int pmb_device_count(void);
 int pmb_problem_count(void);
 const char* pmb_problem_name(int index);
 int pmb_problem_dims(const char* name, pmb_dims_t* out);
+/* Adds the kernels of a problem class compiled OUTSIDE the library (a user translation unit built by nvcc against
+ * include/polympc_compat/ — the counterpart of instantiating SQPBase<Derived, Problem, QP> with a new Problem in the
+ * header-only reference, sqp_base.hpp:64-70).  `factory` returns a new pmb::IProblem (pmb_registry.hpp) as void*.  The name
+ * then works with pmb_ocp_create / pmb_sqp_create.  Re-registering an existing name fails with PMB_ERR_BAD_ARGUMENT. */
+int pmb_register_problem(const char* name, void* (*factory)(void));
 
 void pmb_qp_default_settings(pmb_qp_settings_t* s);      /* qp_base.hpp:17-53 defaults */
 void pmb_sqp_default_settings(pmb_sqp_settings_t* s);    /* sqp_base.hpp:24-34 defaults */

@@ -1,0 +1,536 @@
+// polympc_compat.hpp — source-compatibility layer: PolyMPC problem classes and host code, written against the reference's
+// header-only API, compile unchanged on top of the B200 engine.
+//
+//   reference header / concept (file:line)                                    what this header provides
+//   ------------------------------------------------------------------------------------------------------------------
+//   polympc::Chebyshev<P, GAUSS_LOBATTO, double>  (src/polynomials/ebyshev.hpp:27-95)   tag carrying POLY_ORDER
+//   polympc::Spline<Polynomial, S>                (src/polynomials/splines.hpp:22-46)   tag carrying NUM_SEGMENTS / NUM_NODES
+//   POLYMPC_FORWARD_DECLARATION, polympc_traits   (src/control/continuous_ocp.hpp:22-37) same macro, same traits
+//   ContinuousOCP<OCP, Approximation, FMT>        (continuous_ocp.hpp:39-182, 191-288)   sizes, state_t<T> ..., default *_impl
+//                                                                                        functors, set_time_limits; NO
+//                                                                                        transcription — that is the kernels
+//   SQPBase<Derived, Problem, QPSolver>           (src/solvers/sqp_base.hpp:64-197, 568) host object, one instance, same
+//                                                                                        getters / setters, solve() runs the
+//                                                                                        fused sm_100a kernel
+//   boxADMM<...>, ADMM<...>, qp_solver_settings_t (src/solvers/box_admm.hpp:15, qp_base.hpp:17-53)  settings carrier
+//   MPC<OCP, Solver, Args...>                     (src/control/mpc_wrapper.hpp:17-298)   same methods
+//
+// The GPU side: pmb::compat::Model<OCP> adapts the Eigen-style functors of a problem class to the engine's pointer-style
+// functor concept (pmb_problems.hpp); plain-double evaluations are routed through Dual<double,0> so that user code calling
+// an unqualified cos()/sin()/exp() always lands in the deterministic pmb::dm implementations (argument-dependent lookup),
+// never in libm / the CUDA math library.  A problem class must be trivially copyable (it is passed to the kernel by value)
+// and its functors must be callable on the device: either mark them POLYMPC_HD, or rely on the default below which makes
+// `inline` mean `__host__ __device__ inline` for the code that FOLLOWS this header in an nvcc translation unit (the
+// reference's functors are all declared `inline` / EIGEN_STRONG_INLINE).  Define POLYMPC_B200_NO_INLINE_HD to opt out.
+//
+// What is NOT honoured (documented deviation): CRTP overrides of SQPBase hooks in a Derived solver
+// (hessian_update_impl, step_size_selection_impl ...) are host code the fused kernel cannot call; the engine always runs
+// the reference's *default* implementations (dense damped BFGS, l1 merit line search).  MATRIXFMT is accepted and ignored
+// (the engine is dense).
+#pragma once
+#include "pmb_eigen_shim.hpp"
+#include "../polympc_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <typeinfo>
+#include <vector>
+
+#if defined(__CUDACC__)
+#define POLYMPC_HD __host__ __device__
+#else
+#define POLYMPC_HD
+#endif
+
+// ---- polynomial / spline tags ------------------------------------------------------------------------------------------
+namespace polympc {
+enum collocation_scheme { GAUSS, GAUSS_RADAU, GAUSS_LOBATTO };
+template <int PolyOrder, collocation_scheme Qtype = GAUSS_LOBATTO, typename _Scalar = double>
+class Chebyshev {
+public:
+    static_assert(Qtype == GAUSS_LOBATTO, "the engine transcribes on Chebyshev-Gauss-Lobatto nodes");
+    enum { POLY_ORDER = PolyOrder, NUM_NODES = PolyOrder + 1 };
+    using scalar_t = _Scalar;
+    using nodes_t = Eigen::Matrix<_Scalar, PolyOrder + 1, 1>;
+    using q_weights_t = Eigen::Matrix<_Scalar, PolyOrder + 1, 1>;
+    using diff_mat_t = Eigen::Matrix<_Scalar, PolyOrder + 1, PolyOrder + 1>;
+    /** tables of the engine (pmb_cheb_tables), same formulas as ebyshev.hpp:111-214 */
+    static nodes_t compute_nodes() { nodes_t n; diff_mat_t D; q_weights_t w; pmb_cheb_tables(PolyOrder, n.data(), D.data(), w.data()); return n; }
+    static diff_mat_t compute_diff_matrix() { nodes_t n; diff_mat_t D; q_weights_t w; pmb_cheb_tables(PolyOrder, n.data(), D.data(), w.data()); return D; }
+    static q_weights_t compute_int_weights() { nodes_t n; diff_mat_t D; q_weights_t w; pmb_cheb_tables(PolyOrder, n.data(), D.data(), w.data()); return w; }
+};
+template <typename Polynomial, int NumSegments>
+class Spline {
+public:
+    enum { POLY_ORDER = Polynomial::POLY_ORDER, NUM_SEGMENTS = NumSegments, NUM_NODES = POLY_ORDER * NUM_SEGMENTS + 1 };
+    using scalar_t = typename Polynomial::scalar_t;
+    using nodes_t = typename Polynomial::nodes_t;
+    using q_weights_t = typename Polynomial::q_weights_t;
+    using diff_mat_t = typename Polynomial::diff_mat_t;
+    static diff_mat_t compute_diff_matrix() { return Polynomial::compute_diff_matrix(); }
+    static q_weights_t compute_int_weights() { return Polynomial::compute_int_weights(); }
+    static nodes_t compute_nodes() { return Polynomial::compute_nodes(); }
+};
+typedef std::chrono::time_point<std::chrono::system_clock> time_point;
+inline time_point get_time() { return std::chrono::system_clock::now(); }
+struct IdentityPreconditioner {};
+template <typename Scalar, int N, int M, int FMT> struct RuizEquilibration {};   // accepted as a type; not on the GPU path
+} // namespace polympc
+
+enum MEMORY { DENSE = 0, SPARSE = 1 };
+template <int FMT> struct linear_solver_traits { template <typename Type, int Flags> struct default_solver {}; };
+
+template <typename Derived> struct polympc_traits;
+template <typename T> struct polympc_traits<const T> : polympc_traits<T> {};
+#define POLYMPC_FORWARD_DECLARATION(cNAME, cNX, cNU, cNP, cND, cNG, TYPE) \
+    class cNAME;                                                           \
+    template <> struct polympc_traits<cNAME> {                             \
+        using Scalar = TYPE;                                               \
+        enum { NX = cNX, NU = cNU, NP = cNP, ND = cND, NG = cNG };         \
+    };
+
+// ---- ContinuousOCP: sizes, types and the functor defaults (continuous_ocp.hpp:39-288) ----------------------------------
+template <typename OCP, typename Approximation, int MatrixFormat = DENSE>
+class ContinuousOCP {
+public:
+    enum {
+        NX = polympc_traits<OCP>::NX, NU = polympc_traits<OCP>::NU, NP = polympc_traits<OCP>::NP,
+        ND = polympc_traits<OCP>::ND, NG = polympc_traits<OCP>::NG,
+        NUM_NODES = Approximation::NUM_NODES, POLY_ORDER = Approximation::POLY_ORDER, NUM_SEGMENTS = Approximation::NUM_SEGMENTS,
+        VARX_SIZE = NX * NUM_NODES, VARU_SIZE = NU * NUM_NODES, VARP_SIZE = NP, VARD_SIZE = ND,
+        VAR_SIZE = VARX_SIZE + VARU_SIZE + VARP_SIZE, NUM_EQ = VARX_SIZE, NUM_INEQ = NG * NUM_NODES, NUM_BOX = VAR_SIZE,
+        DUAL_SIZE = NUM_EQ + NUM_INEQ + NUM_BOX,
+        is_sparse = (MatrixFormat == SPARSE) ? 1 : 0, is_dense = is_sparse ? 0 : 1, MATRIXFMT = MatrixFormat
+    };
+    static_assert(NP == 0, "optimised parameters (NP > 0) are not on the GPU path yet");
+    template <typename scalar_t> using state_t = Eigen::Matrix<scalar_t, NX, 1>;
+    template <typename scalar_t> using control_t = Eigen::Matrix<scalar_t, NU, 1>;
+    template <typename scalar_t> using parameter_t = Eigen::Matrix<scalar_t, NP, 1>;
+    template <typename scalar_t> using constraint_t = Eigen::Matrix<scalar_t, NG, 1>;
+    using scalar_t = typename polympc_traits<OCP>::Scalar;
+    static_assert(std::is_same<scalar_t, double>::value, "the engine computes in fp64");
+    using static_parameter_t = Eigen::Matrix<scalar_t, ND, 1>;
+    using time_t = Eigen::Matrix<scalar_t, NUM_NODES, 1>;
+    using nodes_t = typename Approximation::nodes_t;
+
+    using nlp_variable_t = Eigen::Matrix<scalar_t, VAR_SIZE, 1>;
+    using nlp_constraints_t = Eigen::Matrix<scalar_t, NUM_EQ + NUM_INEQ, 1>;
+    using nlp_eq_constraints_t = Eigen::Matrix<scalar_t, NUM_EQ, 1>;
+    using nlp_ineq_constraints_t = Eigen::Matrix<scalar_t, NUM_INEQ, 1>;
+    using nlp_dual_t = Eigen::Matrix<scalar_t, DUAL_SIZE, 1>;
+    using nlp_hessian_t = Eigen::Matrix<scalar_t, VAR_SIZE, VAR_SIZE>;                 // never materialised on the host
+    using nlp_jacobian_t = Eigen::Matrix<scalar_t, NUM_EQ + NUM_INEQ, VAR_SIZE>;
+    using nlp_eq_jacobian_t = Eigen::Matrix<scalar_t, NUM_EQ, VAR_SIZE>;
+
+    scalar_t t_start{0};
+    scalar_t t_stop{1};
+    /** continuous_ocp.hpp:147-159 (the time grid itself lives in the engine's problem descriptor) */
+    void set_time_limits(const scalar_t& t0, const scalar_t& tf) noexcept { t_start = t0; t_stop = tf; }
+
+    /** defaults of the functor concept: no-ops, like continuous_ocp.hpp:206-216, 247-257, 278-288 */
+    template <typename T>
+    POLYMPC_HD void inequality_constraints_impl(const Eigen::Ref<const state_t<T>> x, const Eigen::Ref<const control_t<T>> u,
+                                                const Eigen::Ref<const parameter_t<T>> p, const Eigen::Ref<const static_parameter_t> d,
+                                                const scalar_t& t, Eigen::Ref<constraint_t<T>> g) const noexcept {}
+    template <typename T>
+    POLYMPC_HD void mayer_term_impl(const Eigen::Ref<const state_t<T>> x, const Eigen::Ref<const control_t<T>> u,
+                                    const Eigen::Ref<const parameter_t<T>> p, const Eigen::Ref<const static_parameter_t> d,
+                                    const scalar_t& t, T& mayer) noexcept { mayer = T(0.0); }
+    template <typename T>
+    POLYMPC_HD void lagrange_term_impl(const Eigen::Ref<const state_t<T>> x, const Eigen::Ref<const control_t<T>> u,
+                                       const Eigen::Ref<const parameter_t<T>> p, const Eigen::Ref<const static_parameter_t> d,
+                                       const scalar_t& t, T& lagrange) noexcept { lagrange = T(0.0); }
+};
+
+// ---- settings / info structs, field for field (sqp_base.hpp:24-61, qp_base.hpp:17-72) -----------------------------------
+template <typename Scalar>
+struct sqp_settings_t {
+    Scalar tau = 0.5, eta = 0.25, rho = 0.5, eps_prim = 1e-3, eps_dual = 1e-3;
+    int max_iter = 100;
+    int line_search_max_iter = 100;
+    void (*iteration_callback)(void* solver) = nullptr;   // host callback: cannot be honoured by a fused device loop
+    bool validate() const
+    { return 0.0 < tau && tau < 1.0 && 0.0 < eta && eta < 1.0 && 0.0 < rho && rho < 1.0 && eps_prim > 0.0 && eps_dual > 0.0 && max_iter > 0 && line_search_max_iter > 0; }
+};
+struct sqp_status_t { enum { SOLVED, MAX_ITER_EXCEEDED, INVALID_SETTINGS } value; };
+struct sqp_info_t { int iter; int qp_solver_iter; sqp_status_t status; };
+
+template <typename Scalar>
+struct qp_solver_settings_t {
+    Scalar rho = 1e-1, sigma = 1e-6, alpha = 1.0, eps_rel = 1e-3, eps_abs = 1e-3;
+    int max_iter = 1000, check_termination = 25;
+    bool warm_start = false, adaptive_rho = false, reuse_pattern = false, verbose = false;
+    Scalar adaptive_rho_tolerance = 5;
+    int adaptive_rho_interval = 25;
+};
+/** QP solver type tags: the engine's inner solver is always boxADMM + dense LDL^T; the template arguments are accepted so
+ *  that `boxADMM<VAR_SIZE, NUM_EQ, scalar_t, MATRIXFMT, linear_solver_traits<FMT>::default_solver>` spells the same */
+template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
+          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
+struct boxADMM {
+    using scalar_t = Scalar;
+    using settings_t = qp_solver_settings_t<Scalar>;
+    settings_t m_settings;
+    settings_t& settings() noexcept { return m_settings; }
+    const settings_t& settings() const noexcept { return m_settings; }
+};
+template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
+          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
+struct ADMM : boxADMM<N, M, Scalar, MatrixType, LinearSolver, LinearSolver_UpLo> {};
+
+// ---- device side: adapter from the Eigen-style functors to the engine's functor concept ---------------------------------
+#if defined(__CUDACC__) || defined(PMB_EMU)
+#include "pmb_registry.hpp"
+namespace pmb {
+namespace compat {
+
+template <class U>
+struct Model {
+    static constexpr int NX = U::NX, NU = U::NU, NP = U::NP, ND = U::ND, NG = U::NG;
+    static constexpr int NPARAM = (int)((sizeof(U) + 7) / 8);   // the problem object travels as an opaque blob
+    U ocp;
+    void defaults() { ocp = U(); }
+    void set_params(const double* v) { std::memcpy((void*)&ocp, v, sizeof(U)); }
+    void get_params(double* v) const { std::memset(v, 0, sizeof(double) * NPARAM); std::memcpy(v, (const void*)&ocp, sizeof(U)); }
+
+    template <class T> using W = typename std::conditional<std::is_same<T, double>::value, Dual<double, 0>, T>::type;
+    template <class T> using St = Eigen::Matrix<T, NX, 1>;
+    template <class T> using Ct = Eigen::Matrix<T, NU, 1>;
+    template <class T> using Pt = Eigen::Matrix<T, NP, 1>;
+    template <class T> using Gt = Eigen::Matrix<T, NG, 1>;
+    using Dt = Eigen::Matrix<double, ND, 1>;
+    PMB_HD U& self() const { return const_cast<U&>(ocp); }
+
+    template <class T>
+    PMB_HD void dynamics(const T* x, const T* u, const T* p, const double* d, const T& t, T* xdot) const
+    {
+        if constexpr (std::is_same<T, double>::value) {
+            using R = Dual<double, 0>;
+            St<R> xs; Ct<R> us; Pt<R> ps; St<R> out;
+            for (int i = 0; i < NX; ++i) xs.m[i].v = x[i];
+            for (int i = 0; i < NU; ++i) us.m[i].v = u[i];
+            for (int i = 0; i < NP; ++i) ps.m[i].v = p[i];
+            R tt; tt.v = t;
+            self().template dynamics_impl<R>(Eigen::Ref<const St<R>>(xs.m), Eigen::Ref<const Ct<R>>(us.m), Eigen::Ref<const Pt<R>>(ps.m),
+                                             Eigen::Ref<const Dt>(d), tt, Eigen::Ref<St<R>>(out.m));
+            for (int i = 0; i < NX; ++i) xdot[i] = out.m[i].v;
+        } else {
+            self().template dynamics_impl<T>(Eigen::Ref<const St<T>>(x), Eigen::Ref<const Ct<T>>(u), Eigen::Ref<const Pt<T>>(p),
+                                             Eigen::Ref<const Dt>(d), t, Eigen::Ref<St<T>>(xdot));
+        }
+    }
+    template <class T>
+    PMB_HD void ineq(const T* x, const T* u, const T* p, const double* d, double t, T* g) const
+    {
+        if constexpr (NG == 0) { return; }
+        else if constexpr (std::is_same<T, double>::value) {
+            using R = Dual<double, 0>;
+            St<R> xs; Ct<R> us; Pt<R> ps; Gt<R> out;
+            for (int i = 0; i < NX; ++i) xs.m[i].v = x[i];
+            for (int i = 0; i < NU; ++i) us.m[i].v = u[i];
+            for (int i = 0; i < NP; ++i) ps.m[i].v = p[i];
+            self().template inequality_constraints_impl<R>(Eigen::Ref<const St<R>>(xs.m), Eigen::Ref<const Ct<R>>(us.m), Eigen::Ref<const Pt<R>>(ps.m),
+                                                           Eigen::Ref<const Dt>(d), t, Eigen::Ref<Gt<R>>(out.m));
+            for (int i = 0; i < NG; ++i) g[i] = out.m[i].v;
+        } else {
+            self().template inequality_constraints_impl<T>(Eigen::Ref<const St<T>>(x), Eigen::Ref<const Ct<T>>(u), Eigen::Ref<const Pt<T>>(p),
+                                                           Eigen::Ref<const Dt>(d), t, Eigen::Ref<Gt<T>>(g));
+        }
+    }
+#define PMB_COMPAT_SCALAR_FUNCTOR(NAME, IMPL)                                                                                  \
+    template <class T>                                                                                                         \
+    PMB_HD void NAME(const T* x, const T* u, const T* p, const double* d, double t, T& out) const                              \
+    {                                                                                                                          \
+        if constexpr (std::is_same<T, double>::value) {                                                                        \
+            using R = Dual<double, 0>;                                                                                         \
+            St<R> xs; Ct<R> us; Pt<R> ps; R o;                                                                                 \
+            for (int i = 0; i < NX; ++i) xs.m[i].v = x[i];                                                                     \
+            for (int i = 0; i < NU; ++i) us.m[i].v = u[i];                                                                     \
+            for (int i = 0; i < NP; ++i) ps.m[i].v = p[i];                                                                     \
+            self().template IMPL<R>(Eigen::Ref<const St<R>>(xs.m), Eigen::Ref<const Ct<R>>(us.m), Eigen::Ref<const Pt<R>>(ps.m), \
+                                    Eigen::Ref<const Dt>(d), t, o);                                                            \
+            out = o.v;                                                                                                         \
+        } else {                                                                                                               \
+            self().template IMPL<T>(Eigen::Ref<const St<T>>(x), Eigen::Ref<const Ct<T>>(u), Eigen::Ref<const Pt<T>>(p),        \
+                                    Eigen::Ref<const Dt>(d), t, out);                                                          \
+        }                                                                                                                      \
+    }
+    PMB_COMPAT_SCALAR_FUNCTOR(lagrange, lagrange_term_impl)
+    PMB_COMPAT_SCALAR_FUNCTOR(mayer, mayer_term_impl)
+#undef PMB_COMPAT_SCALAR_FUNCTOR
+};
+
+/** found by argument-dependent lookup from Ocp<>::init(): the horizon a problem class set in its constructor */
+template <class U> inline void model_time_limits(const Model<U>& m, double& t0, double& tf) { t0 = m.ocp.t_start; tf = m.ocp.t_stop; }
+
+template <class U> using OcpOf = Ocp<Model<U>, U::POLY_ORDER, U::NUM_SEGMENTS>;
+template <class U> IProblem* make_problem() { return new ProblemImpl<OcpOf<U>>(); }
+
+/** registers the kernels of a problem class compiled in THIS translation unit with the engine (once) and returns the name
+ *  to give to pmb_sqp_create / polympc::b200::BatchedMPC */
+template <class U>
+const char* problem_name()
+{
+    static const std::string name = [] {
+        std::string n = std::string("compat:") + typeid(U).name();
+        const int rc = pmb_register_problem(n.c_str(), (void* (*)())(&make_problem<U>));
+        if (rc != PMB_OK) throw std::runtime_error(std::string("pmb_register_problem: ") + pmb_last_error());
+        return n;
+    }();
+    return name.c_str();
+}
+
+} // namespace compat
+} // namespace pmb
+/** in-library registration of a reference-style problem class (problems/*.cu) */
+#define PMB_DEFINE_COMPAT_PROBLEM(ID, USER_OCP) \
+    namespace pmb { IProblem* pmb_make_##ID() { return compat::make_problem<USER_OCP>(); } }
+#endif // __CUDACC__ || PMB_EMU
+
+// ---- SQPBase: one NLP instance on the host, solved by the engine (sqp_base.hpp:64-197, 568-696) --------------------------
+template <typename Derived, typename Problem,
+          typename QPSolver = boxADMM<Problem::VAR_SIZE, Problem::NUM_EQ + Problem::NUM_INEQ, typename Problem::scalar_t>,
+          typename Preconditioner = polympc::IdentityPreconditioner>
+class SQPBase {
+public:
+    enum { VAR_SIZE = Problem::VAR_SIZE, NUM_EQ = Problem::NUM_EQ, NUM_INEQ = Problem::NUM_INEQ, NUM_CONSTR = Problem::DUAL_SIZE };
+    using nlp_variable_t = typename Problem::nlp_variable_t;
+    using nlp_constraints_t = typename Problem::nlp_constraints_t;
+    using nlp_eq_constraints_t = typename Problem::nlp_eq_constraints_t;
+    using nlp_ineq_constraints_t = typename Problem::nlp_ineq_constraints_t;
+    using nlp_eq_jacobian_t = typename Problem::nlp_eq_jacobian_t;
+    using nlp_jacobian_t = typename Problem::nlp_jacobian_t;
+    using nlp_hessian_t = typename Problem::nlp_hessian_t;
+    using nlp_cost_t = typename Problem::scalar_t;
+    using nlp_dual_t = typename Problem::nlp_dual_t;
+    using scalar_t = typename Problem::scalar_t;
+    using parameter_t = typename Problem::static_parameter_t;
+    using qp_solver_t = QPSolver;
+    using nlp_settings_t = sqp_settings_t<scalar_t>;
+    using nlp_info_t = sqp_info_t;
+
+    Problem problem;
+    nlp_settings_t m_settings;
+    nlp_info_t m_info;
+    qp_solver_t m_qp_solver;
+    nlp_variable_t m_x, m_lbx, m_ubx;
+    nlp_dual_t m_lam;
+    nlp_ineq_constraints_t m_lbg, m_ubg;
+    parameter_t m_p;
+
+    SQPBase()
+    {
+        const scalar_t INF = std::numeric_limits<scalar_t>::infinity();                       // sqp_base.hpp:72-99
+        m_lbx.setConstant(-INF); m_ubx.setConstant(INF); m_lbg.setConstant(-INF); m_ubg.setConstant(INF);
+        m_x.setZero(); m_lam.setZero(); m_p.setZero();
+        m_info.iter = 0; m_info.qp_solver_iter = 0; m_info.status.value = sqp_status_t::MAX_ITER_EXCEEDED;
+        pmb_qp_settings_t q; pmb_sqp_default_qp_settings(&q);
+        auto& s = m_qp_solver.m_settings;
+        s.warm_start = q.warm_start; s.check_termination = q.check_termination; s.eps_abs = q.eps_abs; s.eps_rel = q.eps_rel;
+        s.max_iter = q.max_iter; s.adaptive_rho = q.adaptive_rho; s.adaptive_rho_interval = q.adaptive_rho_interval; s.alpha = q.alpha;
+        s.rho = q.rho; s.sigma = q.sigma; s.adaptive_rho_tolerance = q.adaptive_rho_tolerance;
+    }
+    ~SQPBase() { if (m_handle) pmb_sqp_destroy(m_handle); }
+    SQPBase(const SQPBase&) = delete;
+    SQPBase& operator=(const SQPBase&) = delete;
+
+    const Problem& get_problem() const noexcept { return problem; }
+    Problem& get_problem() noexcept { return problem; }
+    const nlp_variable_t& primal_solution() const noexcept { return m_x; }
+    nlp_variable_t& primal_solution() noexcept { return m_x; }
+    const nlp_dual_t& dual_solution() const noexcept { return m_lam; }
+    nlp_dual_t& dual_solution() noexcept { return m_lam; }
+    const nlp_settings_t& settings() const noexcept { return m_settings; }
+    nlp_settings_t& settings() noexcept { return m_settings; }
+    const sqp_info_t& info() const noexcept { return m_info; }
+    sqp_info_t& info() noexcept { return m_info; }
+    const nlp_variable_t& lower_bound_x() const noexcept { return m_lbx; }
+    nlp_variable_t& lower_bound_x() noexcept { return m_lbx; }
+    const nlp_variable_t& upper_bound_x() const noexcept { return m_ubx; }
+    nlp_variable_t& upper_bound_x() noexcept { return m_ubx; }
+    const nlp_ineq_constraints_t& lower_bound_g() const noexcept { return m_lbg; }
+    nlp_ineq_constraints_t& lower_bound_g() noexcept { return m_lbg; }
+    const nlp_ineq_constraints_t& upper_bound_g() const noexcept { return m_ubg; }
+    nlp_ineq_constraints_t& upper_bound_g() noexcept { return m_ubg; }
+    const parameter_t& parameters() const noexcept { return m_p; }
+    parameter_t& parameters() noexcept { return m_p; }
+    const typename qp_solver_t::settings_t& qp_settings() const noexcept { return m_qp_solver.m_settings; }
+    typename qp_solver_t::settings_t& qp_settings() noexcept { return m_qp_solver.m_settings; }
+    scalar_t primal_norm() const noexcept { return m_stats[1]; }
+    scalar_t dual_norm() const noexcept { return m_stats[2]; }
+    scalar_t constr_violation() const noexcept { return m_stats[3]; }
+    scalar_t cost() const noexcept { return m_stats[0]; }
+    /** device time of the last solve, ms (not in the reference) */
+    double last_solve_ms() const { return m_handle ? pmb_sqp_last_solve_ms(m_handle) : 0.0; }
+
+    void solve() { solve_impl(); }
+    void solve(const Eigen::Ref<const nlp_variable_t>& x_guess, const Eigen::Ref<const nlp_dual_t>& lam_guess)   // sqp_base.hpp:558-566
+    { m_x = x_guess; m_lam = lam_guess; solve_impl(); }
+
+private:
+    pmb_sqp_t* m_handle = nullptr;
+    double m_stats[4] = {0, 0, 0, 0};
+    static void check(int rc, const char* what)
+    { if (rc != PMB_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + pmb_last_error()); }
+    void solve_impl()
+    {
+#if defined(__CUDACC__) || defined(PMB_EMU)
+        if (!m_handle) {
+            m_handle = pmb_sqp_create(pmb::compat::problem_name<Problem>(), 1, 0);
+            if (!m_handle) throw std::runtime_error(std::string("pmb_sqp_create: ") + pmb_last_error());
+        }
+#else
+        static_assert(sizeof(Problem) == 0, "compile this translation unit with nvcc: the kernels of the problem class are instantiated here");
+#endif
+        pmb_ocp_t* ocp = pmb_sqp_problem(m_handle);
+        // the problem object (Q, R, ... members) travels as a blob; then the horizon
+        std::vector<double> blob((sizeof(Problem) + 7) / 8, 0.0);
+        std::memcpy(blob.data(), (const void*)&problem, sizeof(Problem));
+        check(pmb_ocp_set_params(ocp, blob.data(), (int)blob.size()), "set_params");
+        check(pmb_ocp_set_time_limits(ocp, problem.t_start, problem.t_stop), "set_time_limits");
+        pmb_sqp_settings_t st; pmb_sqp_default_settings(&st);
+        st.tau = m_settings.tau; st.eta = m_settings.eta; st.rho = m_settings.rho; st.eps_prim = m_settings.eps_prim; st.eps_dual = m_settings.eps_dual;
+        st.max_iter = m_settings.max_iter; st.line_search_max_iter = m_settings.line_search_max_iter;
+        check(pmb_sqp_set_settings(m_handle, &st), "set_settings");
+        pmb_qp_settings_t q; pmb_sqp_default_qp_settings(&q);
+        const auto& s = m_qp_solver.m_settings;
+        q.rho = s.rho; q.sigma = s.sigma; q.alpha = s.alpha; q.eps_rel = s.eps_rel; q.eps_abs = s.eps_abs; q.max_iter = s.max_iter;
+        q.check_termination = s.check_termination; q.warm_start = s.warm_start; q.adaptive_rho = s.adaptive_rho;
+        q.adaptive_rho_tolerance = s.adaptive_rho_tolerance; q.adaptive_rho_interval = s.adaptive_rho_interval;
+        q.reuse_pattern = s.reuse_pattern; q.verbose = s.verbose;
+        check(pmb_sqp_set_qp_settings(m_handle, &q), "set_qp_settings");
+        check(pmb_sqp_set_bounds_x(m_handle, m_lbx.data(), m_ubx.data(), VAR_SIZE), "set_bounds_x");
+        if (NUM_INEQ > 0) check(pmb_sqp_set_bounds_g(m_handle, m_lbg.data(), m_ubg.data(), NUM_INEQ), "set_bounds_g");
+        if (Problem::ND > 0) check(pmb_sqp_set_parameters(m_handle, m_p.data(), Problem::ND), "set_parameters");
+        check(pmb_sqp_set_primal(m_handle, m_x.data(), VAR_SIZE), "set_primal");          // warm start from the kept iterate,
+        check(pmb_sqp_set_dual(m_handle, m_lam.data(), NUM_CONSTR), "set_dual");          // like a second reference solve()
+        check(pmb_sqp_solve(m_handle), "solve");
+        check(pmb_sqp_get_primal(m_handle, m_x.data()), "get_primal");
+        check(pmb_sqp_get_dual(m_handle, m_lam.data()), "get_dual");
+        pmb_sqp_info_t inf;
+        check(pmb_sqp_get_info(m_handle, &inf), "get_info");
+        m_info.iter = inf.iter; m_info.qp_solver_iter = inf.qp_solver_iter;
+        m_info.status.value = inf.status == PMB_SQP_SOLVED ? sqp_status_t::SOLVED
+                            : (inf.status == PMB_SQP_MAX_ITER_EXCEEDED ? sqp_status_t::MAX_ITER_EXCEEDED : sqp_status_t::INVALID_SETTINGS);
+        check(pmb_sqp_get_stats(m_handle, m_stats), "get_stats");
+    }
+};
+
+// ---- MPC facade (mpc_wrapper.hpp:17-298) -----------------------------------------------------------------------------------
+template <typename OCP, template <typename, typename...> class Solver, typename... Args>
+class MPC {
+private:
+    using nlp_solver_t = Solver<OCP, Args...>;
+    nlp_solver_t m_solver;
+public:
+    static constexpr int nx = OCP::NX, nu = OCP::NU, np = OCP::NP, nd = OCP::ND, ng = OCP::NG;
+    static constexpr int var_size = OCP::VAR_SIZE, varx_size = OCP::VARX_SIZE, varu_size = OCP::VARU_SIZE, dual_size = OCP::DUAL_SIZE;
+    static constexpr int num_nodes = OCP::NUM_NODES, num_segms = OCP::NUM_SEGMENTS, num_ineq = OCP::NUM_INEQ, poly_order = OCP::POLY_ORDER;
+
+    using scalar_t = typename OCP::scalar_t;
+    using state_t = Eigen::Matrix<scalar_t, nx, 1>;
+    using control_t = Eigen::Matrix<scalar_t, nu, 1>;
+    using parameter_t = Eigen::Matrix<scalar_t, np, 1>;
+    using static_param = Eigen::Matrix<scalar_t, nd, 1>;
+    using constraint_t = Eigen::Matrix<scalar_t, ng, 1>;
+    using traj_state_t = Eigen::Matrix<scalar_t, varx_size, 1>;
+    using traj_control_t = Eigen::Matrix<scalar_t, varu_size, 1>;
+    using dual_var_t = Eigen::Matrix<scalar_t, dual_size, 1>;
+    using constraints_t = Eigen::Matrix<scalar_t, num_ineq, 1>;
+
+    MPC() = default;
+
+    void set_time_limits(const scalar_t& t0, const scalar_t& tf) noexcept { m_solver.get_problem().set_time_limits(t0, tf); }
+    void initial_conditions(const Eigen::Ref<const state_t>& x0) noexcept { initial_conditions(x0, x0); }
+    void initial_conditions(const Eigen::Ref<const state_t>& x0_lb, const Eigen::Ref<const state_t>& x0_ub) noexcept
+    { put(m_solver.upper_bound_x(), varx_size - nx, x0_ub); put(m_solver.lower_bound_x(), varx_size - nx, x0_lb); }
+    void x_lower_bound(const Eigen::Ref<const state_t>& xlb) noexcept { for (int k = 0; k < num_nodes - 1; ++k) put(m_solver.lower_bound_x(), k * nx, xlb); }
+    void x_upper_bound(const Eigen::Ref<const state_t>& xub) noexcept { for (int k = 0; k < num_nodes - 1; ++k) put(m_solver.upper_bound_x(), k * nx, xub); }
+    void state_bounds(const Eigen::Ref<const state_t>& xlb, const Eigen::Ref<const state_t>& xub) noexcept { x_lower_bound(xlb); x_upper_bound(xub); }
+    void state_trajectory_bounds(const Eigen::Ref<const traj_state_t>& xlb, const Eigen::Ref<const traj_state_t>& xub) noexcept
+    { put(m_solver.lower_bound_x(), 0, xlb); put(m_solver.upper_bound_x(), 0, xub); }
+    void x_final_lower_bound(const Eigen::Ref<const state_t>& xlb) noexcept { put(m_solver.lower_bound_x(), 0, xlb); }
+    void x_final_upper_bound(const Eigen::Ref<const state_t>& xub) noexcept { put(m_solver.upper_bound_x(), 0, xub); }
+    void final_state_bounds(const Eigen::Ref<const state_t>& xlb, const Eigen::Ref<const state_t>& xub) noexcept { x_final_lower_bound(xlb); x_final_upper_bound(xub); }
+    void u_lower_bound(const Eigen::Ref<const control_t>& lb) noexcept { for (int k = 0; k < num_nodes; ++k) put(m_solver.lower_bound_x(), varx_size + k * nu, lb); }
+    void u_upper_bound(const Eigen::Ref<const control_t>& ub) noexcept { for (int k = 0; k < num_nodes; ++k) put(m_solver.upper_bound_x(), varx_size + k * nu, ub); }
+    void control_trajecotry_bounds(const Eigen::Ref<const traj_control_t>& lb, const Eigen::Ref<const traj_control_t>& ub) noexcept
+    { put(m_solver.lower_bound_x(), varx_size, lb); put(m_solver.upper_bound_x(), varx_size, ub); }
+    void control_bounds(const Eigen::Ref<const control_t>& lb, const Eigen::Ref<const control_t>& ub) noexcept { u_lower_bound(lb); u_upper_bound(ub); }
+    void constraints_trajectory_bounds(const Eigen::Ref<const constraints_t>& lbg, const Eigen::Ref<const constraints_t>& ubg) noexcept
+    { put(m_solver.lower_bound_g(), 0, lbg); put(m_solver.upper_bound_g(), 0, ubg); }
+    void constraints_bounds(const Eigen::Ref<const constraint_t>& lbg, const Eigen::Ref<const constraint_t>& ubg) noexcept
+    { for (int k = 0; k < num_nodes; ++k) { put(m_solver.lower_bound_g(), k * ng, lbg); put(m_solver.upper_bound_g(), k * ng, ubg); } }
+    void set_static_parameters(const Eigen::Ref<const static_param>& param) noexcept { put(m_solver.parameters(), 0, param); }
+    void x_guess(const Eigen::Ref<const traj_state_t>& g) noexcept { put(m_solver.primal_solution(), 0, g); }
+    void u_guess(const Eigen::Ref<const traj_control_t>& g) noexcept { put(m_solver.primal_solution(), varx_size, g); }
+    void lam_guess(const Eigen::Ref<const dual_var_t>& g) noexcept { put(m_solver.dual_solution(), 0, g); }
+
+    const typename nlp_solver_t::nlp_settings_t& settings() const noexcept { return m_solver.m_settings; }
+    typename nlp_solver_t::nlp_settings_t& settings() noexcept { return m_solver.m_settings; }
+    const typename nlp_solver_t::qp_solver_t::settings_t& qp_settings() const noexcept { return m_solver.m_qp_solver.m_settings; }
+    typename nlp_solver_t::qp_solver_t::settings_t& qp_settings() noexcept { return m_solver.m_qp_solver.m_settings; }
+    const typename nlp_solver_t::nlp_info_t& info() const noexcept { return m_solver.m_info; }
+    typename nlp_solver_t::nlp_info_t& info() noexcept { return m_solver.m_info; }
+    const nlp_solver_t& solver() const noexcept { return m_solver; }
+    nlp_solver_t& solver() noexcept { return m_solver; }
+    const OCP& ocp() const noexcept { return m_solver.get_problem(); }
+    OCP& ocp() noexcept { return m_solver.get_problem(); }
+    scalar_t primal_norm() const noexcept { return m_solver.primal_norm(); }
+    scalar_t dual_norm() const noexcept { return m_solver.dual_norm(); }
+    scalar_t constr_violation() const noexcept { return m_solver.constr_violation(); }
+    scalar_t cost() const noexcept { return m_solver.cost(); }
+
+    traj_state_t solution_x() const noexcept { return get<varx_size>(m_solver.primal_solution(), 0); }
+    Eigen::Matrix<scalar_t, nx, num_nodes> solution_x_reshaped() const noexcept
+    { Eigen::Matrix<scalar_t, nx, num_nodes> r; for (int i = 0; i < varx_size; ++i) r.m[i] = m_solver.primal_solution()(i); return r; }
+    /** k-th node counted from the initial time (the NLP variable stores the final time first), mpc_wrapper.hpp:241-243 */
+    state_t solution_x_at(const int& k) const noexcept { return get<nx>(m_solver.primal_solution(), varx_size - (k + 1) * nx); }
+    state_t solution_x_at(const scalar_t& t) const noexcept { return interpolate<nx>(t, varx_size); }
+    traj_control_t solution_u() const noexcept { return get<varu_size>(m_solver.primal_solution(), varx_size); }
+    Eigen::Matrix<scalar_t, nu, num_nodes> solution_u_reshaped() const noexcept
+    { Eigen::Matrix<scalar_t, nu, num_nodes> r; for (int i = 0; i < varu_size; ++i) r.m[i] = m_solver.primal_solution()(varx_size + i); return r; }
+    control_t solution_u_at(const int& k) const noexcept { return get<nu>(m_solver.primal_solution(), varx_size + varu_size - (k + 1) * nu); }
+    control_t solution_u_at(const scalar_t& t) const noexcept { return interpolate<nu>(t, varx_size + varu_size); }
+    parameter_t solution_p() const noexcept { return get<np>(m_solver.primal_solution(), varx_size + varu_size); }
+    dual_var_t solution_dual() const noexcept { return m_solver.dual_solution(); }
+
+    void solve() noexcept { m_solver.solve(); }
+
+private:
+    template <class Dst, class Src> static void put(Dst& dst, int off, const Src& src) { for (int i = 0; i < (int)Src::Size; ++i) dst(off + i) = src(i); }
+    template <int LEN, class Src> static Eigen::Matrix<scalar_t, LEN, 1> get(const Src& src, int off)
+    { Eigen::Matrix<scalar_t, LEN, 1> r; for (int i = 0; i < LEN; ++i) r.m[i] = src(off + i); return r; }
+    /** Lagrange interpolation on the Chebyshev nodes of the segment containing t (t relative to t_start), as
+     *  polympc::LagrangeSpline::eval does (src/polynomials/splines.hpp:101-139, mpc_wrapper.hpp:245-281) */
+    template <int W> Eigen::Matrix<scalar_t, W, 1> interpolate(const scalar_t& t, int block_end) const
+    {
+        const OCP& o = m_solver.get_problem();
+        const scalar_t seg = (o.t_stop - o.t_start) / num_segms;
+        const auto nodes = polympc::Chebyshev<poly_order>::compute_nodes();     // descending: cos(k pi / P)
+        int idx = (int)std::floor(t / seg);
+        idx = idx < 0 ? 0 : (idx > num_segms - 1 ? num_segms - 1 : idx);
+        scalar_t tg[poly_order + 1];                                            // ascending time grid of the segment
+        for (int a = 0; a <= poly_order; ++a) tg[a] = (seg / 2) * nodes(poly_order - a) + (o.t_start + seg / 2 + idx * seg);
+        const scalar_t tq = o.t_start + t;
+        Eigen::Matrix<scalar_t, W, 1> out; out.setZero();
+        for (int a = 0; a <= poly_order; ++a) {
+            scalar_t l = 1.0;
+            for (int c = 0; c <= poly_order; ++c) if (c != a) l *= (tq - tg[c]) / (tg[a] - tg[c]);
+            const int ka = idx * poly_order + a;
+            for (int i = 0; i < W; ++i) out(i) += l * m_solver.primal_solution()(block_end - (ka + 1) * W + i);
+        }
+        return out;
+    }
+};
+
+// ---- functor annotation for the code that follows (see the header comment) ----------------------------------------------
+#if defined(__CUDACC__) && !defined(POLYMPC_B200_NO_INLINE_HD)
+#define inline __host__ __device__ inline
+#endif

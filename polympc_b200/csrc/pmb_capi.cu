@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,8 @@ PMB_DECLARE_PROBLEM(cstr_5x2)
 PMB_DECLARE_PROBLEM(kite_12x1)
 PMB_DECLARE_PROBLEM(kite_4x2)
 PMB_DECLARE_PROBLEM(robot_obstacle_5x2)
+PMB_DECLARE_PROBLEM(dropin_robot_5x3)
+PMB_DECLARE_PROBLEM(dropin_cstr_5x2)
 
 namespace pmb {
 namespace {
@@ -30,7 +33,7 @@ namespace {
 
 struct Registry { const char* name; IProblem* (*make)(); };
 #define PMB_REG(NAME, ID) { NAME, &pmb_make_##ID }
-const Registry g_registry[] = {
+const Registry g_builtin[] = {
     PMB_REG("mobile_robot_6x2", mobile_robot_6x2),   // BASELINE.json configs 1, 2, 5
     PMB_REG("mobile_robot_5x2", mobile_robot_5x2),   // reference CasADi fixture / continuous_ocp_test.cpp
     PMB_REG("mobile_robot_5x3", mobile_robot_5x3),   // reference mpc_wrapper_test.cpp
@@ -38,13 +41,34 @@ const Registry g_registry[] = {
     PMB_REG("kite_12x1", kite_12x1),                 // BASELINE.json config 4 (our model)
     PMB_REG("kite_4x2", kite_4x2),                   // small kite variant for fast parity tests
     PMB_REG("robot_obstacle_5x2", robot_obstacle_5x2),   // NG = 1: generic inequality constraints
+    // reference-style problem classes (Eigen functors) compiled through include/polympc_compat/, see problems/dropin_*.cu
+    PMB_REG("dropin_robot_5x3", dropin_robot_5x3),
+    PMB_REG("dropin_cstr_5x2", dropin_cstr_5x2),
 };
-const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
-const Registry* find_problem(const char* name)
+/** built-in problems followed by the ones user translation units registered (pmb_register_problem); entries are never
+ *  removed, names are owned by the registry (std::deque-like stability through unique_ptr) */
+struct RegistryTable {
+    std::vector<std::unique_ptr<std::string>> names;
+    std::vector<Registry> rows;
+    std::mutex mu;
+    RegistryTable() { for (const Registry& r : g_builtin) rows.push_back(r); }
+};
+RegistryTable& table() { static RegistryTable t; return t; }
+int registry_size() { RegistryTable& t = table(); std::lock_guard<std::mutex> g(t.mu); return (int)t.rows.size(); }
+bool registry_row(int i, Registry* out)
 {
-    if (!name) return nullptr;
-    for (int i = 0; i < g_nreg; ++i) if (std::strcmp(g_registry[i].name, name) == 0) return &g_registry[i];
-    return nullptr;
+    RegistryTable& t = table(); std::lock_guard<std::mutex> g(t.mu);
+    if (i < 0 || i >= (int)t.rows.size()) return false;
+    *out = t.rows[i];
+    return true;
+}
+/** copies the row out: the vector may grow under a concurrent registration */
+bool find_problem(const char* name, Registry* out)
+{
+    if (!name) return false;
+    RegistryTable& t = table(); std::lock_guard<std::mutex> g(t.mu);
+    for (const Registry& r : t.rows) if (std::strcmp(r.name, name) == 0) { *out = r; return true; }
+    return false;
 }
 
 bool have_device() { return rt_device_count() > 0; }
@@ -176,11 +200,21 @@ const char* pmb_version(void)
 }
 const char* pmb_last_error(void) { return last_error_string().c_str(); }
 int pmb_device_count(void) { return rt_device_count(); }
-int pmb_problem_count(void) { return g_nreg; }
-const char* pmb_problem_name(int i) { return (i >= 0 && i < g_nreg) ? g_registry[i].name : nullptr; }
+int pmb_problem_count(void) { return registry_size(); }
+const char* pmb_problem_name(int i) { Registry r; return registry_row(i, &r) ? r.name : nullptr; }
+int pmb_register_problem(const char* name, void* (*factory)(void))
+{
+    if (!name || !*name || !factory) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "pmb_register_problem: null name or factory");
+    RegistryTable& t = table();
+    std::lock_guard<std::mutex> g(t.mu);
+    for (const Registry& r : t.rows) if (std::strcmp(r.name, name) == 0) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "pmb_register_problem: name already registered");
+    t.names.emplace_back(new std::string(name));
+    t.rows.push_back(Registry{t.names.back()->c_str(), reinterpret_cast<IProblem* (*)()>(factory)});
+    return PMB_OK;
+}
 int pmb_problem_dims(const char* name, pmb_dims_t* out)
 {
-    const Registry* r = find_problem(name);
+    Registry reg; const Registry* r = find_problem(name, &reg) ? &reg : nullptr;
     if (!r) PMB_FAIL(PMB_ERR_UNKNOWN_PROBLEM, "unknown problem");
     if (!out) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null output");
     std::unique_ptr<IProblem> p(r->make());
@@ -234,7 +268,7 @@ int pmb_cheb_tables(int P, double* nodes, double* D, double* w)
 // ---- ContinuousOCP ---------------------------------------------------------------------------------------------
 pmb_ocp_t* pmb_ocp_create(const char* name, int device)
 {
-    const Registry* r = find_problem(name);
+    Registry reg; const Registry* r = find_problem(name, &reg) ? &reg : nullptr;
     if (!r) { last_error_string() = "unknown problem"; return nullptr; }
     pmb_ocp_t* h = new pmb_ocp_t();
     h->impl = r->make();
@@ -382,7 +416,7 @@ int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double*
 // ---- SQP -------------------------------------------------------------------------------------------------------
 pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
 {
-    const Registry* r = find_problem(name);
+    Registry reg; const Registry* r = find_problem(name, &reg) ? &reg : nullptr;
     if (!r || batch <= 0) { last_error_string() = "sqp_create: unknown problem or bad batch"; return nullptr; }
     if (!have_device()) { last_error_string() = "no CUDA device: the engine has no CPU fallback"; return nullptr; }
     if (device < 0 || device >= rt_device_count() || !rt_set_device(device)) { last_error_string() = "sqp_create: bad device"; return nullptr; }

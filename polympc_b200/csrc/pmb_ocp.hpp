@@ -20,6 +20,11 @@
 
 namespace pmb {
 
+/** horizon a model wants at construction; the default leaves [0, 1].  Overloads for other model types are found by
+ *  argument-dependent lookup (include/polympc_compat/polympc_compat.hpp: the horizon a reference-style class set in its
+ *  constructor through ContinuousOCP::set_time_limits, continuous_ocp.hpp:147-159). */
+template <class M> inline void model_time_limits(const M&, double&, double&) {}
+
 template <class Model_, int P_, int S_>
 struct Ocp {
     using Model = Model_;
@@ -45,7 +50,9 @@ struct Ocp {
     {
         model.defaults();
         cheb_tables(P, nodes, D, w);
-        set_time_limits(0.0, 1.0);
+        double t0 = 0.0, tf = 1.0;
+        model_time_limits(model, t0, tf);
+        set_time_limits(t0, tf);
     }
     /** continuous_ocp.hpp:45-55, 147-159 */
     void set_time_limits(double t0, double tf)

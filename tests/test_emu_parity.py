@@ -8,7 +8,8 @@ import parity_cases as pc
 from polympc_b200 import workloads as W
 
 
-@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "robot_obstacle_5x2"])
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "robot_obstacle_5x2",
+                                  "dropin_robot_5x3", "dropin_cstr_5x2"])
 def test_ocp_operators(emu, orc, name):
     pc.ocp_case(emu, orc, name, B=2, seed=1)
 
@@ -91,3 +92,18 @@ def test_sqp_inequality_constraints(emu, orc):
     """NG = 1 (obstacle avoidance): inequality rows in the QP, lbg/ubg in the merit function and the termination test"""
     w = W.robot_obstacle(2, sqp_max_iter=6, ls_max_iter=10)
     pc.sqp_case(emu, orc, w)
+
+
+@pytest.mark.parametrize("kind", ["robot", "cstr"])
+def test_sqp_dropin_problem_classes(emu, orc, kind):
+    """reference-style problem classes (Eigen functors over include/polympc_compat/, examples/dropin/*.hpp) driven through
+    the kernels reproduce the hand-restated oracle model bit for bit — including the horizon the CSTR class sets in its
+    own constructor"""
+    import dataclasses
+    w = W.mobile_robot(2, seed=5, grid="5x3", sqp_max_iter=6, ls_max_iter=10) if kind == "robot" else W.cstr(1, seed=4, sqp_max_iter=3, ls_max_iter=10)
+    w = dataclasses.replace(w, name={"robot": "dropin_robot_5x3", "cstr": "dropin_cstr_5x2"}[kind])
+    pc.sqp_case(emu, orc, w)
+    if kind == "cstr":
+        a, b = emu.ocp("dropin_cstr_5x2"), orc.ocp("cstr_5x2")
+        b.set_time_limits(0.0, 100.0)
+        pc.assert_same(a.time_nodes(), b.time_nodes(), "horizon from the class constructor")

@@ -20,7 +20,8 @@ def test_device_present(pmb):
     assert "sm_100a" in pmb.version()
 
 
-@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1", "robot_obstacle_5x2"])
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1", "robot_obstacle_5x2",
+                                  "dropin_robot_5x3", "dropin_cstr_5x2"])
 def test_ocp_operators(pmb, orc, name):
     pc.ocp_case(pmb, orc, name, B=37, seed=1)
 
@@ -230,3 +231,18 @@ def test_warm_restart_matches_oracle(pmb, orc):
     pc.assert_same(outs[0][1][finite], outs[1][1][finite], "lam (finite instances)")
     if (~finite).any():
         assert not np.isfinite(outs[0][1][~finite]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,batch", [("robot", 512), ("cstr", 256)])
+def test_sqp_dropin_problem_classes(pmb, orc, kind, batch):
+    """reference-style problem classes (examples/dropin/*.hpp: Eigen functors over include/polympc_compat/) on the GPU ==
+    the fixture-pinned oracle model, bit for bit, and == the engine's hand-written twin problem"""
+    import dataclasses
+    w = W.mobile_robot(batch, seed=21, grid="5x3", sqp_max_iter=10, ls_max_iter=10) if kind == "robot" else W.cstr(batch, seed=22, sqp_max_iter=20, ls_max_iter=20)
+    twin = w.name
+    wd = dataclasses.replace(w, name={"robot": "dropin_robot_5x3", "cstr": "dropin_cstr_5x2"}[kind])
+    ra, rb = pc.sqp_case(pmb, orc, wd)
+    rt = pc.solve_workload(pmb, w)
+    pc.assert_same(ra["x"], rt["x"], "drop-in class vs hand-written twin on the GPU")
+    assert (rb["info"]["status"] == 0).mean() > 0.9

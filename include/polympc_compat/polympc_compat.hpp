@@ -84,7 +84,7 @@ template <typename Scalar, int N, int M, int FMT> struct RuizEquilibration {};  
 } // namespace polympc
 
 enum MEMORY { DENSE = 0, SPARSE = 1 };
-template <int FMT> struct linear_solver_traits { template <typename Type, int Flags> struct default_solver {}; };
+template <int FMT> struct linear_solver_traits { template <typename Type, int Flags, typename... Args> struct default_solver {}; };
 
 template <typename Derived> struct polympc_traits;
 template <typename T> struct polympc_traits<const T> : polympc_traits<T> {};

@@ -165,6 +165,14 @@ int pmb_sqp_set_settings(pmb_sqp_t* s, const pmb_sqp_settings_t* st);       /* S
 int pmb_sqp_get_settings(const pmb_sqp_t* s, pmb_sqp_settings_t* st);
 int pmb_sqp_set_qp_settings(pmb_sqp_t* s, const pmb_qp_settings_t* st);     /* SQPBase::qp_settings() */
 int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st);
+/* The fixed menu of SQPBase CRTP hooks (sqp_base.hpp:198-350) a fused device loop can honour — the two overrides the
+ * reference's own solvers install (tests/control/minimal_time_test.cpp:90-135):
+ *   exact_every_iteration     update_linearisation_dense_impl := linearisation_dense_impl (exact Lagrangian Hessian at every
+ *                             SQP iteration instead of the damped BFGS update, sqp_base.hpp:489-504);
+ *   gershgorin_regularisation hessian_regularisation_dense_impl := for every column i with H_ii - r_i <= 0,
+ *                             r_i = sum_{j != i} |H_ji|:  H_ii += (r_i - H_ii) + 0.01  (applied after each exact Hessian).
+ * Both default to 0 = the reference defaults. */
+int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int gershgorin_regularisation);
 /* stride == 0: one vector broadcast to every instance; stride == len: one vector per instance */
 int pmb_sqp_set_bounds_x(pmb_sqp_t* s, const double* lbx, const double* ubx, int stride);   /* lower/upper_bound_x() */
 int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lbg, const double* ubg, int stride);   /* lower/upper_bound_g() */

@@ -315,6 +315,12 @@ public:
     using nlp_settings_t = sqp_settings_t<scalar_t>;
     using nlp_info_t = sqp_info_t;
 
+    /** engine-side replacements for the two CRTP overrides the reference's own solvers install
+     *  (tests/control/minimal_time_test.cpp:90-135); host overrides in Derived are never called by the fused kernel */
+    struct engine_options_t { bool exact_hessian_every_iteration = false; bool gershgorin_regularisation = false; };
+    engine_options_t m_engine_options;
+    engine_options_t& engine_options() noexcept { return m_engine_options; }
+
     Problem problem;
     nlp_settings_t m_settings;
     nlp_info_t m_info;
@@ -405,6 +411,8 @@ private:
         q.adaptive_rho_tolerance = s.adaptive_rho_tolerance; q.adaptive_rho_interval = s.adaptive_rho_interval;
         q.reuse_pattern = s.reuse_pattern; q.verbose = s.verbose;
         check(pmb_sqp_set_qp_settings(m_handle, &q), "set_qp_settings");
+        check(pmb_sqp_set_hessian_options(m_handle, m_engine_options.exact_hessian_every_iteration, m_engine_options.gershgorin_regularisation),
+              "set_hessian_options");
         check(pmb_sqp_set_bounds_x(m_handle, m_lbx.data(), m_ubx.data(), VAR_SIZE), "set_bounds_x");
         if (NUM_INEQ > 0) check(pmb_sqp_set_bounds_g(m_handle, m_lbg.data(), m_ubg.data(), NUM_INEQ), "set_bounds_g");
         if (Problem::ND > 0) check(pmb_sqp_set_parameters(m_handle, m_p.data(), Problem::ND), "set_parameters");

@@ -83,6 +83,7 @@ struct ISqpInst {
     virtual void solve() = 0;
     virtual SqpSettings& settings() = 0;
     virtual QpSettings& qp_settings() = 0;
+    virtual void hessian_options(int exact, int gershgorin) = 0;
     virtual SqpInfo& info() = 0;
     virtual std::vector<double>& x() = 0;
     virtual std::vector<double>& lam() = 0;
@@ -102,6 +103,7 @@ struct SqpInst : ISqpInst {
     void solve() override { s.solve(); }
     SqpSettings& settings() override { return s.settings; }
     QpSettings& qp_settings() override { return s.qp.settings; }
+    void hessian_options(int exact, int gershgorin) override { s.opt_exact_hessian = exact; s.opt_gershgorin = gershgorin; }
     SqpInfo& info() override { return s.info; }
     std::vector<double>& x() override { return s.x; }
     std::vector<double>& lam() override { return s.lam; }
@@ -389,6 +391,14 @@ int pmb_sqp_set_qp_settings(pmb_sqp_t* s, const pmb_qp_settings_t* st)
 { if (!s || !st) return PMB_ERR_BAD_ARGUMENT; for (auto& i : s->inst) to_qp(*st, i->qp_settings()); return PMB_OK; }
 int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st)
 { if (!s || !st) return PMB_ERR_BAD_ARGUMENT; from_qp(s->inst[0]->qp_settings(), *st); return PMB_OK; }
+int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int gershgorin_regularisation)
+{
+    if (!s) return PMB_ERR_BAD_ARGUMENT;
+    for (auto& i : s->inst) i->hessian_options(exact_every_iteration != 0, gershgorin_regularisation != 0);
+    return PMB_OK;
+}
+/* the oracle has no kernels to register: problem classes are added to its own table (REG above) */
+int pmb_register_problem(const char*, void* (*)(void)) { g_err = "the oracle does not register external problems"; return PMB_ERR_BAD_ARGUMENT; }
 
 static int set_vec(pmb_sqp_t* s, const double* v, int stride, int len, std::vector<double>& (ISqpInst::*acc)())
 {

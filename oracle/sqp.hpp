@@ -141,6 +141,25 @@ struct Sqp {
         return alpha;
     }
 
+    // The fixed menu of SQPBase CRTP overrides the engine can honour (pmb_sqp_set_hessian_options): both are what the
+    // reference's own solvers install, tests/control/minimal_time_test.cpp:90-135
+    int opt_exact_hessian = 0;   // update_linearisation_dense_impl := linearisation_dense_impl (exact Hessian at every iteration)
+    int opt_gershgorin = 0;      // hessian_regularisation_dense_impl := Gershgorin shift of the diagonal
+
+    /** minimal_time_test.cpp:90-104; called from linearisation_dense_impl (sqp_base.hpp:316-317).  cwiseAbs().sum() of a
+     *  column is taken in sequential ascending order ("parity unpinned": Eigen's order depends on the vector ISA). */
+    void regularise_hessian()
+    {
+        if (!opt_gershgorin) return;
+        for (int i = 0; i < N; ++i) {
+            const double aii = H[i + (size_t)i * N];
+            double sum = 0.0;
+            for (int j = 0; j < N; ++j) sum += dm::fabs(H[j + (size_t)i * N]);
+            const double ri = sum - dm::fabs(aii);
+            if (aii - ri <= 0) H[i + (size_t)i * N] += (ri - aii) + 0.01;
+        }
+    }
+
     void prepare_qp_bounds()  // sqp_base.hpp:588-593
     {
         for (int i = 0; i < M; ++i) { al[i] = -al[i]; au[i] = al[i]; }
@@ -182,11 +201,21 @@ struct Sqp {
         // linearisation (309-318): exact Hessian
         problem.lagrangian_gradient_hessian(x.data(), p_static.data(), lam.data(), lagv, lag_gradient.data(), H.data(), h.data(),
                                             al.data(), A.data());
+        regularise_hessian();
         tr_bfgs.push_back(-1);
         prepare_qp_bounds();
         if (iterate_tail(p, p_lambda)) { info.status = SQP_SOLVED; return; }
         while (info.iter < settings.max_iter) {
             info.iter++;
+            if (opt_exact_hessian) {
+                problem.lagrangian_gradient_hessian(x.data(), p_static.data(), lam.data(), lagv, lag_gradient.data(), H.data(), h.data(),
+                                                    al.data(), A.data());
+                regularise_hessian();
+                tr_bfgs.push_back(-1);
+                prepare_qp_bounds();
+                if (iterate_tail(p, p_lambda)) { info.status = SQP_SOLVED; break; }
+                continue;
+            }
             // update_linearisation_dense_impl (489-504)
             std::vector<double> lg(N), yv(N);
             problem.lagrangian_gradient(x.data(), p_static.data(), lam.data(), lagv, lg.data(), h.data(), al.data(), A.data());

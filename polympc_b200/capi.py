@@ -51,14 +51,14 @@ INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = 0, 1, 2
 
 # every function name declared in include/polympc_b200.h (checked against the header by tests/test_abi.py)
 ABI_FUNCTIONS = [
-    "version", "last_error", "device_count", "problem_count", "problem_name", "problem_dims",
+    "version", "last_error", "device_count", "problem_count", "problem_name", "problem_dims", "register_problem",
     "qp_default_settings", "sqp_default_settings", "sqp_default_qp_settings", "dm_eval", "cheb_tables",
     "ocp_create", "ocp_destroy", "ocp_dims", "ocp_set_params", "ocp_get_params", "ocp_set_time_limits", "ocp_time_nodes",
     "ocp_cost", "ocp_equalities", "ocp_inequalities", "ocp_equalities_linearised", "ocp_cost_gradient",
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
@@ -127,6 +127,7 @@ class CApi:
         g("sqp_get_settings").argtypes = [C.c_void_p, C.POINTER(SqpSettings)]
         g("sqp_set_qp_settings").argtypes = [C.c_void_p, C.POINTER(QpSettings)]
         g("sqp_get_qp_settings").argtypes = [C.c_void_p, C.POINTER(QpSettings)]
+        g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
         for name in ("sqp_set_bounds_x", "sqp_set_bounds_g"):
             g(name).argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int]
         for name in ("sqp_set_parameters", "sqp_set_primal", "sqp_set_dual"):
@@ -411,6 +412,11 @@ class Sqp:
 
     def set_qp_settings(self, s: QpSettings):
         self.api._chk(self.api._fn("sqp_set_qp_settings")(self.h, C.byref(s)), "sqp_set_qp_settings")
+
+    def set_hessian_options(self, exact_every_iteration: bool = False, gershgorin_regularisation: bool = False):
+        """the fixed menu of SQPBase CRTP overrides (reference tests/control/minimal_time_test.cpp:90-135)"""
+        self.api._chk(self.api._fn("sqp_set_hessian_options")(self.h, int(exact_every_iteration), int(gershgorin_regularisation)),
+                      "sqp_set_hessian_options")
 
     def _vec(self, v, length):
         v = _f64(v)

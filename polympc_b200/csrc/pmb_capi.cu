@@ -157,6 +157,7 @@ struct pmb_sqp {
     int batch = 0, device = 0;
     pmb_sqp_settings_t settings;
     pmb_qp_settings_t qp_settings;
+    int opt_exact_hessian = 0, opt_gershgorin = 0;   // pmb_sqp_set_hessian_options
     pmb::stream_t own_stream = nullptr, stream = nullptr;
     pmb::event_t ev0 = nullptr, ev1 = nullptr;
     pmb::DevBuf<double> x_guess, lam_guess;   // device copies of the initial guess (pmb_sqp_reset_guess)
@@ -467,6 +468,12 @@ int pmb_sqp_set_settings(pmb_sqp_t* s, const pmb_sqp_settings_t* st) { if (!s ||
 int pmb_sqp_get_settings(const pmb_sqp_t* s, pmb_sqp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *st = s->settings; return PMB_OK; }
 int pmb_sqp_set_qp_settings(pmb_sqp_t* s, const pmb_qp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->qp_settings = *st; return PMB_OK; }
 int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st) { if (!s || !st) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *st = s->qp_settings; return PMB_OK; }
+int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int gershgorin_regularisation)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    s->opt_exact_hessian = exact_every_iteration != 0; s->opt_gershgorin = gershgorin_regularisation != 0;
+    return PMB_OK;
+}
 
 static int sqp_set_vec(pmb_sqp_t* s, double* dst, const double* v, int stride, size_t len)
 {
@@ -581,6 +588,7 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     ws.info = s->info.p; ws.qp_info = s->qp_info.p; ws.qp_nfac = s->qp_nfac.p;
     ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p;
     ws.trace_rows = rows;
+    ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin;
     ws.phase = nullptr;
     if (s->profiling) {
         ok = ok && s->phase.resize(16) && rt_memset(s->phase.p, 0, 16 * sizeof(unsigned long long), st);

@@ -70,6 +70,24 @@ PMB_DEV double warp_max(const Warp& w, double m)
 
 PMB_DEV int packed_off(int j, int n) { return j * n - (j * (j - 1)) / 2; }
 
+/** sum_j a[j*ld] * 0.0 accumulated from +0.0: what `A * x_guess` (box_admm.hpp:99) gives for the default zero guess — +0.0
+ *  for a row of finite entries (every product is +-0 and (+0) + (-0) = +0 in any order), NaN as soon as the row holds a NaN
+ *  or an infinity.  Order-free, so the dependent chain of dot_chain() is not needed; loads go out eight at a time. */
+PMB_DEV double zero_guess_row(const double* a, size_t ld, int n)
+{
+    double acc0 = 0.0, acc1 = 0.0;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+        double v[8];
+        PMB_UNROLL
+        for (int u = 0; u < 8; ++u) v[u] = a[(size_t)(j + u) * ld];
+        PMB_UNROLL
+        for (int u = 0; u < 8; u += 2) { acc0 = dm::fma(v[u], 0.0, acc0); acc1 = dm::fma(v[u + 1], 0.0, acc1); }
+    }
+    for (; j < n; ++j) acc0 = dm::fma(a[(size_t)j * ld], 0.0, acc0);
+    return acc0 + acc1;
+}
+
 /** sum_j a[j*ld] * x[j], sequential ascending fused chain; loads are issued eight at a time ahead of the chain */
 PMB_DEV double dot_chain(const double* a, size_t ld, const double* x, int n)
 {
@@ -518,7 +536,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     }
     for (int i = tid; i < M; i += nt) ya[i] = a.yg ? a.yg[i] : 0.0;
     c.sync();
-    for (int i = tid; i < M; i += nt) z[i] = a.xg ? dot_chain(a.A + i, (size_t)M, x, N) : 0.0;
+    for (int i = tid; i < M; i += nt) z[i] = a.xg ? dot_chain(a.A + i, (size_t)M, x, N) : zero_guess_row(a.A + i, (size_t)M, N);
 
     // ---- parse_constraints_bounds (qp_base.hpp:195-222) ------------------------------------------------------------
     for (int i = tid; i < M; i += nt)

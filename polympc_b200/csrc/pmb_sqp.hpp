@@ -67,6 +67,8 @@ struct SqpWs {
     int *tr_qp_iter, *tr_bfgs, *tr_ls, *tr_qp_factor;
     double* tr_alpha;
     int trace_rows;
+    int opt_exact_hessian;       // pmb_sqp_set_hessian_options: exact Lagrangian Hessian at every iteration (no BFGS)
+    int opt_gershgorin;          //                              Gershgorin shift after every exact Hessian
     unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
                                  // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
 };
@@ -145,6 +147,20 @@ struct SqpDev {
         if (first) {
             cost_x = E::lagrangian_gradient_hessian(c, o, s.x(), s.d(), s.lam(), s.lag_grad(), s.H(), s.h(), s.al(), s.A(), scratch);
             if (s.tr_bfgs() && tid == 0) s.tr_bfgs()[trace_row] = -1;
+            if (s.ws.opt_gershgorin) {
+                // hessian_regularisation_dense_impl of reference tests/control/minimal_time_test.cpp:90-104 (cold path): one
+                // thread per column, |column| summed in sequential ascending order like the oracle; column i only changes (i, i)
+                c.sync();
+                double* Hm = s.H();
+                for (int i = tid; i < N; i += nt) {
+                    const double aii = Hm[i + (size_t)i * N];
+                    double sum = 0.0;
+                    for (int j = 0; j < N; ++j) sum += dm::fabs(Hm[j + (size_t)i * N]);
+                    const double ri = sum - dm::fabs(aii);
+                    if (aii - ri <= 0) Hm[i + (size_t)i * N] += (ri - aii) + 0.01;
+                }
+                c.sync();
+            }
         } else {
             double* lg = scratch;          // N
             double* yv = lg + N;           // N
@@ -299,7 +315,7 @@ struct SqpDev {
         for (int it = 1; ; ++it) {                   // the first iteration always runs (sqp_base.hpp:583-637 precede the loop)
             const int row = it - 1;
             const unsigned long long t0 = c.w.clock();
-            const double cost_x = linearise(c, o, s, it == 1, row, scratch);
+            const double cost_x = linearise(c, o, s, it == 1 || s.ws.opt_exact_hessian != 0, row, scratch);
             const unsigned long long t1 = c.w.clock();
             qp_solve_cta<R, N, M, NW>(c, qst, qa, Lp, vec);
             const unsigned long long t2 = c.w.clock();

@@ -50,7 +50,8 @@ def test_library_contains_sm100a_code():
 
 def test_registry_and_dims(pmb, orc):
     names = pmb.problems()
-    assert names == orc.problems()
+    # dropin_*: reference-style classes compiled through include/polympc_compat/; their oracle twins are the hand-restated models
+    assert [n for n in names if not n.startswith("dropin_")] == orc.problems()
     assert {"mobile_robot_6x2", "cstr_5x2", "kite_12x1", "robot_obstacle_5x2"} <= set(names)
     d = pmb.dims("mobile_robot_6x2")
     assert (d["NX"], d["NU"], d["NN"], d["N"], d["M"], d["DUAL"]) == (3, 2, 13, 65, 39, 104)
@@ -58,8 +59,12 @@ def test_registry_and_dims(pmb, orc):
     assert (d["N"], d["M"]) == (66, 44)
     d = pmb.dims("kite_12x1")
     assert (d["N"], d["M"]) == (208, 169)
+    from parity_cases import ORACLE_TWIN
     for n in names:
-        assert pmb.dims(n) == orc.dims(n)
+        a, b = pmb.dims(n), orc.dims(ORACLE_TWIN.get(n, n))
+        if n in ORACLE_TWIN:            # the drop-in classes travel as an opaque blob: NPARAM counts its 8-byte words
+            a.pop("NPARAM"); b.pop("NPARAM")
+        assert a == b
     with pytest.raises(PmbError):
         pmb.dims("no_such_problem")
 

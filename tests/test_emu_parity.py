@@ -107,3 +107,70 @@ def test_sqp_dropin_problem_classes(emu, orc, kind):
         a, b = emu.ocp("dropin_cstr_5x2"), orc.ocp("cstr_5x2")
         b.set_time_limits(0.0, 100.0)
         pc.assert_same(a.time_nodes(), b.time_nodes(), "horizon from the class constructor")
+
+
+def test_qp_nonfinite_jacobian_rows_with_zero_guess(emu, orc):
+    """`m_z = A * x_guess` (box_admm.hpp:99) with the default zero guess is NaN — not 0 — for every row of A that holds a
+    NaN or an infinity; that NaN decides later which multipliers of a diverged instance stay finite, and through the
+    NaN-blind infinity norms whether SQPBase reports SOLVED (regression: the kernel used to start from z = 0)"""
+    rng = np.random.default_rng(8)
+    H, h, A, Alb, Aub, xlb, xub = pc.random_qp(rng, 3, 9, 5)
+    A[0, 2, 4] = np.nan
+    A[1, 0, 0] = np.inf; A[1, 4, 8] = -np.inf
+    A[2, :, :] = np.nan; H[2, :, :] = np.nan; h[2, :] = np.nan; Alb[2, :] = np.nan; Aub[2, :] = np.nan; xlb[2, :] = np.nan; xub[2, :] = np.nan
+    st = orc.sqp_default_qp_settings(); st.max_iter = 20
+    ra = emu.qp_solve(H, h, A, Alb, Aub, xlb, xub, st)
+    rb = orc.qp_solve(H, h, A, Alb, Aub, xlb, xub, st)
+    for k in ("perm", "ctype", "n_factor", "x", "y", "z", "q"):
+        pc.assert_same(ra[k], rb[k], "qp." + k)
+    for f in ("status", "iter"):
+        pc.assert_same(ra["info"][f], rb["info"][f], "qp.info." + f)
+
+
+def test_sqp_cstr_warm_restart_that_diverges(emu, orc):
+    """cstr_control_test.cpp:137-177 on the dense path: the warm-started second solve() linearises with the kept
+    multipliers, its exact Hessian is indefinite, the iterates overflow to NaN after four iterations and the NaN-blind
+    termination test then reports SOLVED — on both sides, with identical traces (the reference has no safeguard either)"""
+    outs = []
+    for api in (emu, orc):
+        w = W.cstr(1, sqp_max_iter=20, ls_max_iter=20); w.x0[:] = [1.0, 0.5, 100.0, 100.0]
+        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.solve()
+        first = s.info().copy()
+        s.set_initial_conditions(np.array([[1.1, 0.508, 100.5, 100.1]])); s.solve()
+        outs.append((first, s.info().copy(), s.primal(), s.dual(), s.stats(), s.trace(20)))
+        s.close()
+    a, b = outs
+    assert a[0]["status"][0] == 0 and a[0]["iter"][0] == b[0]["iter"][0]
+    for f in ("iter", "qp_solver_iter", "status"):
+        pc.assert_same(a[1][f], b[1][f], "warm.info." + f)
+    for i, n in ((2, "x"), (3, "lam"), (4, "stats")):
+        pc.assert_same(a[i], b[i], "warm." + n)
+    for k in ("qp_iter", "ls_trials", "alpha", "bfgs", "qp_factor"):
+        pc.assert_same(a[5][k], b[5][k], "warm.trace." + k)
+
+
+@pytest.mark.parametrize("exact,gersh", [(1, 0), (0, 1), (1, 1)])
+def test_sqp_hessian_options(emu, orc, exact, gersh):
+    """pmb_sqp_set_hessian_options — the SQPBase overrides of reference tests/control/minimal_time_test.cpp:90-135 as engine
+    options: exact Hessian at every iteration, Gershgorin regularisation.  With the regulariser the warm-started CSTR solve
+    of cstr_control_test.cpp converges for real (finite iterates) instead of overflowing."""
+    outs = []
+    for api in (emu, orc):
+        w = W.cstr(1, sqp_max_iter=20, ls_max_iter=20); w.x0[:] = [1.0, 0.5, 100.0, 100.0]
+        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.set_hessian_options(exact, gersh); s.solve()
+        first = s.info().copy()
+        s.set_initial_conditions(np.array([[1.1, 0.508, 100.5, 100.1]])); s.solve()
+        outs.append((first, s.info().copy(), s.primal(), s.dual(), s.stats(), s.trace(20)))
+        s.close()
+    a, b = outs
+    for k in (0, 1):
+        for f in ("iter", "qp_solver_iter", "status"):
+            pc.assert_same(a[k][f], b[k][f], f"info[{k}]." + f)
+    for i, n in ((2, "x"), (3, "lam"), (4, "stats")):
+        pc.assert_same(a[i], b[i], n)
+    for k in ("qp_iter", "ls_trials", "alpha", "bfgs", "qp_factor"):
+        pc.assert_same(a[5][k], b[5][k], "trace." + k)
+    if exact:
+        assert (a[5]["bfgs"][a[5]["qp_iter"] > 0] == -1).all()          # no BFGS update was taken
+    if gersh:
+        assert a[1]["status"][0] == 0 and np.isfinite(a[2]).all() and a[1]["iter"][0] <= 5

@@ -246,3 +246,28 @@ def test_sqp_dropin_problem_classes(pmb, orc, kind, batch):
     rt = pc.solve_workload(pmb, w)
     pc.assert_same(ra["x"], rt["x"], "drop-in class vs hand-written twin on the GPU")
     assert (rb["info"]["status"] == 0).mean() > 0.5     # 10 / 20 iterations: most, not all, instances converge
+
+
+def test_qp_nonfinite_jacobian_rows_with_zero_guess(pmb, orc):
+    """see tests/test_emu_parity.py::test_qp_nonfinite_jacobian_rows_with_zero_guess"""
+    import test_emu_parity as te
+    te.test_qp_nonfinite_jacobian_rows_with_zero_guess(pmb, orc)
+
+
+def test_sqp_cstr_warm_restart_that_diverges(pmb, orc):
+    import test_emu_parity as te
+    te.test_sqp_cstr_warm_restart_that_diverges(pmb, orc)
+
+
+@pytest.mark.parametrize("exact,gersh", [(1, 0), (0, 1), (1, 1)])
+def test_sqp_hessian_options(pmb, orc, exact, gersh):
+    import test_emu_parity as te
+    te.test_sqp_hessian_options(pmb, orc, exact, gersh)
+    w = W.mobile_robot(256, seed=31, sqp_max_iter=15, ls_max_iter=15)
+    outs = []
+    for api in (pmb, orc):
+        s = api.sqp(w.name, w.batch); W.configure(s, w); s.set_hessian_options(exact, gersh); s.solve()
+        outs.append((s.primal(), s.dual(), s.info().copy())); s.close()
+    pc.assert_same(outs[0][0], outs[1][0], "x"); pc.assert_same(outs[0][1], outs[1][1], "lam")
+    for f in ("iter", "qp_solver_iter", "status"):
+        pc.assert_same(outs[0][2][f], outs[1][2][f], f)

@@ -34,17 +34,19 @@ def test_reference_mpc_wrapper_test_passes_on_the_emulator(emu):
     assert rc == 0 and "0 failed expectations" in out, out
 
 
-def test_reference_cstr_control_test_on_the_emulator(emu):
-    """cstr_control_test.cpp:137-177 compiles and runs unmodified.  Its single assertion (the warm-started SECOND solve ends
-    SOLVED) is known not to hold on the dense / plain-BFGS path this engine implements — the reference test instantiates
-    SPARSE matrices and overrides hessian_update_impl with the OCP's block-BFGS; the oracle's dense
-    restatement behaves the same way (tests/test_oracle_behaviour.py pins the first solve).  Pinned here so that a change
-    of behaviour in either direction is noticed."""
-    rc, out = _run(_binary("emu_cstr_control_test", "emu"))
+def _check_cstr(rc, out):
+    """cstr_control_test.cpp:137-177 compiles and runs unmodified and its assertion (the warm-started SECOND solve ends
+    SOLVED) holds — but read DESIGN.md §2 before trusting it: on the dense / plain-BFGS path (the reference's defaults,
+    which this engine implements; the reference test itself instantiates SPARSE matrices and overrides hessian_update_impl
+    with the OCP's block-BFGS) that second solve diverges to NaN and the reference's NaN-blind
+    termination test reports SOLVED.  tests/test_emu_parity.py::test_sqp_cstr_warm_restart_that_diverges pins exactly that
+    against the oracle."""
     assert "[ RUN      ] ControlTests.CSTRStabilisationTest" in out, out
-    assert out.count("Failure") <= 1, out
-    if rc != 0:
-        assert "cstr_control_test.cpp:177" in out, out
+    assert rc == 0 and "0 failed expectations" in out, out
+
+
+def test_reference_cstr_control_test_on_the_emulator(emu):
+    _check_cstr(*_run(_binary("emu_cstr_control_test", "emu")))
 
 
 @pytest.mark.gpu
@@ -55,8 +57,4 @@ def test_reference_mpc_wrapper_test_passes_on_the_gpu(pmb):
 
 @pytest.mark.gpu
 def test_reference_cstr_control_test_on_the_gpu(pmb):
-    rc, out = _run(_binary("cstr_control_test", "all"))
-    assert "[ RUN      ] ControlTests.CSTRStabilisationTest" in out, out
-    assert out.count("Failure") <= 1, out
-    if rc != 0:
-        assert "cstr_control_test.cpp:177" in out, out
+    _check_cstr(*_run(_binary("cstr_control_test", "all")))

@@ -394,26 +394,23 @@ def run_gpu(args):
     # ~50 ms while the other SMs idle.  A caller that owns several independent batches hides that tail by
     # keeping two solves in flight on two streams: CTAs of the second launch become resident as CTAs of the first retire.
     # Same work per step as `value` (every step solves the whole batch from the same guess); steps alternate between two
-    # solver handles driven by two host threads (the C ABI call is blocking, like the reference's solve()).
+    # solver handles through pmb_sqp_solve_async / pmb_sqp_wait.
     pipelined = None
     if world == 1 and not args.no_pipelined:
         try:
-            import threading
             stream2 = torch.cuda.Stream(device=dev)
             s2 = api.sqp(w_all.name, hi - lo, device=local_rank)
             s2.set_stream(stream2.cuda_stream)
             W.configure(s2, w_all, lo, hi)
             s2.solve()
             steps2 = max(2, args.steps + (args.steps % 2))
-            def drive(solver, n):
-                for _ in range(n):
-                    solver.reset_guess(); solver.solve()
             barrier()
             p0, p1, pj = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
             p0.record(stream); stream2.wait_event(p0)
-            th = [threading.Thread(target=drive, args=(sv, steps2 // 2)) for sv in (s, s2)]
-            for t in th: t.start()
-            for t in th: t.join()
+            for k in range(steps2):                 # pmb_sqp_solve_async / pmb_sqp_wait: one host thread, two handles
+                sv = (s, s2)[k % 2]
+                sv.wait(); sv.reset_guess(); sv.solve_async()
+            s.wait(); s2.wait()
             pj.record(stream2); stream.wait_event(pj); p1.record(stream)
             barrier()
             ms_p = p0.elapsed_time(p1)

@@ -186,6 +186,11 @@ int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const doub
  * pmb_sqp_set_primal / pmb_sqp_set_dual (zeros after create, like the SQPBase ctor) without a host copy */
 int pmb_sqp_reset_guess(pmb_sqp_t* s);
 int pmb_sqp_solve(pmb_sqp_t* s);                                            /* SQPBase::solve(), whole batch */
+/* The same, split: _async enqueues the whole batch solve on the handle's stream and returns; _wait blocks until it is done
+ * (and makes pmb_sqp_last_solve_ms valid).  Two handles on two streams keep two batches in flight, which hides the straggler
+ * tail of the persistent kernel.  Getters synchronise on the handle's stream by themselves. */
+int pmb_sqp_solve_async(pmb_sqp_t* s);
+int pmb_sqp_wait(pmb_sqp_t* s);
 int pmb_sqp_get_primal(const pmb_sqp_t* s, double* x);                      /* [batch*N]    */
 int pmb_sqp_get_dual(const pmb_sqp_t* s, double* lam);                      /* [batch*DUAL] */
 int pmb_sqp_get_info(const pmb_sqp_t* s, pmb_sqp_info_t* info);             /* [batch]      */

@@ -106,7 +106,10 @@ public:
 
     /** SQPBase::solve() for every instance of the batch (mpc_wrapper.hpp:298).  Like the reference, a second solve()
      *  warm-starts from the previous solution unless a new guess was given. */
-    void solve()
+    void solve() { upload(); check(pmb_sqp_solve(m_solver), "solve"); fetch(); }
+
+private:
+    void upload()
     {
         check(pmb_sqp_set_bounds_x(m_solver, m_lbx.data(), m_ubx.data(), m_d.N), "set_bounds_x");
         if (m_d.NG > 0) check(pmb_sqp_set_bounds_g(m_solver, m_lbg.data(), m_ubg.data(), m_d.NG * m_d.NN), "set_bounds_g");
@@ -116,7 +119,9 @@ public:
             check(pmb_sqp_set_dual(m_solver, m_lam.data(), m_d.DUAL), "set_dual");
             m_guess_dirty = false;
         }
-        check(pmb_sqp_solve(m_solver), "solve");
+    }
+    void fetch()
+    {
         check(pmb_sqp_get_primal(m_solver, m_x.data()), "get_primal");
         check(pmb_sqp_get_dual(m_solver, m_lam.data()), "get_dual");
         m_info.resize(m_batch);
@@ -124,6 +129,14 @@ public:
         m_stats.resize((size_t)m_batch * 4);
         check(pmb_sqp_get_stats(m_solver, m_stats.data()), "get_stats");
     }
+
+public:
+
+    /** solve() split in two (not in the reference): solve_async() uploads bounds / parameters / guess and enqueues the batch
+     *  solve on this object's stream, wait() blocks and fetches the results.  Two BatchedMPC objects alternating
+     *  solve_async() / wait() keep two batches in flight. */
+    void solve_async() { upload(); check(pmb_sqp_solve_async(m_solver), "solve_async"); }
+    void wait() { check(pmb_sqp_wait(m_solver), "wait"); fetch(); }
 
     // ---- results (mpc_wrapper.hpp:214-296)
     const pmb_sqp_info_t& info(int b) const { return m_info.at(b); }

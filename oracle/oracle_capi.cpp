@@ -452,6 +452,11 @@ int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const doub
         }
     return PMB_OK;
 }
+int pmb_sqp_solve(pmb_sqp_t* s);
+/* the CPU oracle is synchronous: _async does the work, _wait has nothing to wait for */
+int pmb_sqp_solve_async(pmb_sqp_t* s) { return pmb_sqp_solve(s); }
+int pmb_sqp_wait(pmb_sqp_t* s) { return s ? PMB_OK : PMB_ERR_BAD_ARGUMENT; }
+
 int pmb_sqp_solve(pmb_sqp_t* s)
 {
     if (!s) return PMB_ERR_BAD_ARGUMENT;

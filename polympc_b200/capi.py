@@ -59,7 +59,7 @@ ABI_FUNCTIONS = [
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
-    "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_get_primal", "sqp_get_dual",
+    "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
 ]
@@ -134,6 +134,8 @@ class CApi:
             g(name).argtypes = [C.c_void_p, c_double_p, C.c_int]
         g("sqp_set_initial_conditions").argtypes = [C.c_void_p, c_double_p, c_double_p]
         g("sqp_solve").argtypes = [C.c_void_p]
+        g("sqp_solve_async").argtypes = [C.c_void_p]
+        g("sqp_wait").argtypes = [C.c_void_p]
         g("sqp_get_primal").argtypes = [C.c_void_p, c_double_p]
         g("sqp_get_dual").argtypes = [C.c_void_p, c_double_p]
         g("sqp_get_info").argtypes = [C.c_void_p, C.c_void_p]
@@ -456,6 +458,13 @@ class Sqp:
 
     def solve(self):
         self.api._chk(self.api._fn("sqp_solve")(self.h), "sqp_solve")
+
+    def solve_async(self):
+        """enqueue the batch solve on the handle's stream and return; wait() (or any getter) synchronises"""
+        self.api._chk(self.api._fn("sqp_solve_async")(self.h), "sqp_solve_async")
+
+    def wait(self):
+        self.api._chk(self.api._fn("sqp_wait")(self.h), "sqp_wait")
 
     def reset_guess(self):
         self.api._chk(self.api._fn("sqp_reset_guess")(self.h), "sqp_reset_guess")

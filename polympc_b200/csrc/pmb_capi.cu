@@ -563,6 +563,12 @@ int pmb_sqp_set_initial_conditions(pmb_sqp_t* s, const double* x0_lb, const doub
 
 int pmb_sqp_solve(pmb_sqp_t* s)
 {
+    const int rc = pmb_sqp_solve_async(s);
+    return rc != PMB_OK ? rc : pmb_sqp_wait(s);
+}
+
+int pmb_sqp_solve_async(pmb_sqp_t* s)
+{
     if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
     if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
     const int B = s->batch;
@@ -599,11 +605,21 @@ int pmb_sqp_solve(pmb_sqp_t* s)
     ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
     ok = ok && rt_event_record(s->kev1, st);
     ++launches;
-    ok = ok && rt_event_record(s->ev1, st) && rt_sync(st);
+    ok = ok && rt_event_record(s->ev1, st);
     if (!ok) return PMB_ERR_CUDA;
+    s->last_launches = launches;
+    return PMB_OK;
+}
+
+int pmb_sqp_wait(pmb_sqp_t* s)
+{
+    if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    stream_t st = s->stream;
+    if (!rt_sync(st)) return PMB_ERR_CUDA;
+    if (s->last_launches == 0) return PMB_OK;          // nothing was enqueued yet
     s->last_ms = rt_event_ms(s->ev0, s->ev1);
     s->last_kernel_ms = rt_event_ms(s->kev0, s->kev1);
-    s->last_launches = launches;
     for (int k = 0; k < 3; ++k) { s->k_ms[k] = 0; s->k_launches[k] = 0; }
     if (s->profiling) {
         unsigned long long* ph = s->phase_host;

@@ -174,3 +174,35 @@ def test_sqp_hessian_options(emu, orc, exact, gersh):
         assert (a[5]["bfgs"][a[5]["qp_iter"] > 0] == -1).all()          # no BFGS update was taken
     if gersh:
         assert a[1]["status"][0] == 0 and np.isfinite(a[2]).all() and a[1]["iter"][0] <= 5
+
+
+def closed_loop(api, name, w, steps, dt):
+    """MPC in closed loop (the caller of the path): solve, apply the first control to a unicycle plant
+    (RK4 on the host, numpy), move the initial-condition bound to the new state, re-solve warm-started from the kept
+    iterate — what `MPC::solve()` does when called once per control period (mpc_wrapper.hpp:89-99, 298)."""
+    d = float(w.d[0])
+    def f(x, u):
+        return np.stack([u[:, 0] * np.cos(x[:, 2]) * np.cos(u[:, 1]), u[:, 0] * np.sin(x[:, 2]) * np.cos(u[:, 1]), u[:, 0] * np.sin(u[:, 1]) / d], axis=1)
+    s = api.sqp(name, w.batch); W.configure(s, w)
+    D = s.d
+    x = w.x0.copy(); log = []
+    for _ in range(steps):
+        s.solve()
+        var = s.primal()
+        u0 = var[:, D["NX"] * D["NN"] + D["NU"] * (D["NN"] - 1):D["NX"] * D["NN"] + D["NU"] * D["NN"]]     # control at the initial time
+        k1 = f(x, u0); k2 = f(x + 0.5 * dt * k1, u0); k3 = f(x + 0.5 * dt * k2, u0); k4 = f(x + dt * k3, u0)
+        x = x + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        log.append((var.copy(), s.dual().copy(), s.info().copy(), x.copy()))
+        s.set_initial_conditions(x)
+    s.close()
+    return log
+
+
+def test_closed_loop_mpc(emu, orc):
+    w = W.mobile_robot(2, seed=13, sqp_max_iter=4, ls_max_iter=10)
+    la, lb = closed_loop(emu, w.name, w, 3, 0.1), closed_loop(orc, w.name, w, 3, 0.1)
+    for k, (a, b) in enumerate(zip(la, lb)):
+        pc.assert_same(a[0], b[0], f"step {k}: x"); pc.assert_same(a[1], b[1], f"step {k}: lam")
+        for f in ("iter", "qp_solver_iter", "status"):
+            pc.assert_same(a[2][f], b[2][f], f"step {k}: info." + f)
+        pc.assert_same(a[3], b[3], f"step {k}: plant state")

@@ -271,3 +271,18 @@ def test_sqp_hessian_options(pmb, orc, exact, gersh):
     pc.assert_same(outs[0][0], outs[1][0], "x"); pc.assert_same(outs[0][1], outs[1][1], "lam")
     for f in ("iter", "qp_solver_iter", "status"):
         pc.assert_same(outs[0][2][f], outs[1][2][f], f)
+
+
+def test_closed_loop_mpc(pmb, orc):
+    """20 control periods of 256 robots in closed loop, warm-started re-solves: every iterate of every period bit-identical
+    to the oracle, the fleet approaches the origin"""
+    import test_emu_parity as te
+    w = W.mobile_robot(256, seed=17, sqp_max_iter=10, ls_max_iter=10)
+    la, lb = te.closed_loop(pmb, w.name, w, 20, 0.1), te.closed_loop(orc, w.name, w, 20, 0.1)
+    for k, (a, b) in enumerate(zip(la, lb)):
+        pc.assert_same(a[0], b[0], f"step {k}: x"); pc.assert_same(a[1], b[1], f"step {k}: lam")
+        for f in ("iter", "qp_solver_iter", "status"):
+            pc.assert_same(a[2][f], b[2][f], f"step {k}: info." + f)
+    fin = np.isfinite(la[-1][3]).all(axis=1)
+    assert fin.mean() > 0.95
+    assert np.median(np.linalg.norm(la[-1][3][fin, :2], axis=1)) < np.median(np.linalg.norm(w.x0[fin, :2], axis=1))

@@ -9,9 +9,13 @@
 #include "polynomials/splines.hpp"
 #include "control/continuous_ocp.hpp"
 
+#ifndef DROPIN_ROBOT_SEGMENTS
+#define DROPIN_ROBOT_SEGMENTS 3     // mpc_wrapper_test.cpp uses 3 segments of order 5; the CasADi fixture grid is 5 x 2
+#endif
+
 namespace dropin {
 using RobotPolynomial = polympc::Chebyshev<5, polympc::GAUSS_LOBATTO, double>;
-using RobotApproximation = polympc::Spline<RobotPolynomial, 3>;
+using RobotApproximation = polympc::Spline<RobotPolynomial, DROPIN_ROBOT_SEGMENTS>;
 class RobotOCP;
 }
 template <> struct polympc_traits<dropin::RobotOCP> { using Scalar = double; enum { NX = 3, NU = 2, NP = 0, ND = 1, NG = 0 }; };

@@ -48,6 +48,8 @@
 #define POLYMPC_HD
 #endif
 
+namespace pmb { namespace compat { template <class U> const char* problem_name(); } }
+
 // ---- polynomial / spline tags ------------------------------------------------------------------------------------------
 namespace polympc {
 enum collocation_scheme { GAUSS, GAUSS_RADAU, GAUSS_LOBATTO };
@@ -133,6 +135,62 @@ public:
     /** continuous_ocp.hpp:147-159 (the time grid itself lives in the engine's problem descriptor) */
     void set_time_limits(const scalar_t& t0, const scalar_t& tf) noexcept { t_start = t0; t_stop = tf; }
 
+    // ---- the Problem concept SQPBase is written against (continuous_ocp.hpp:430-435, 579, 618-647; sqp_base.hpp:110-120):
+    // host methods, one instance, evaluated by the transcription kernels through pmb_ocp_* (each call uploads this object's
+    // data members and horizon first, so `ocp.Q.diagonal() << ...; ocp.cost(...)` behaves as in the reference).  `_lagrangian`
+    // receives what the reference's dense overloads leave in it: the cost value.
+    void cost(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p, scalar_t& cost_) const
+    { chk(pmb_ocp_cost(engine(), 1, var.data(), p.data(), &cost_), "cost"); }
+    void cost_gradient(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p, scalar_t& cost_,
+                       Eigen::Ref<nlp_variable_t> cost_grad) const
+    { chk(pmb_ocp_cost_gradient(engine(), 1, var.data(), p.data(), &cost_, cost_grad.data()), "cost_gradient"); }
+    void cost_gradient_hessian(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p, scalar_t& cost_,
+                               Eigen::Ref<nlp_variable_t> cost_grad, Eigen::Ref<nlp_hessian_t> cost_hess) const
+    { chk(pmb_ocp_cost_gradient_hessian(engine(), 1, var.data(), p.data(), &cost_, cost_grad.data(), cost_hess.data()), "cost_gradient_hessian"); }
+    void equalities(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p,
+                    Eigen::Ref<nlp_eq_constraints_t> c) const
+    { chk(pmb_ocp_equalities(engine(), 1, var.data(), p.data(), c.data()), "equalities"); }
+    void inequalities(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p,
+                      Eigen::Ref<nlp_ineq_constraints_t> g) const
+    { if (NUM_INEQ > 0) chk(pmb_ocp_inequalities(engine(), 1, var.data(), p.data(), g.data()), "inequalities"); }
+    void equalities_linearised(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p,
+                               Eigen::Ref<nlp_eq_constraints_t> c, Eigen::Ref<nlp_eq_jacobian_t> jac) const
+    { chk(pmb_ocp_equalities_linearised(engine(), 1, var.data(), p.data(), c.data(), jac.data()), "equalities_linearised"); }
+    void lagrangian_gradient(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p,
+                             const Eigen::Ref<const nlp_dual_t>& lam, scalar_t& _lagrangian, Eigen::Ref<nlp_variable_t> lag_gradient,
+                             Eigen::Ref<nlp_variable_t> cost_gradient, Eigen::Ref<nlp_constraints_t> g, Eigen::Ref<nlp_jacobian_t> jac_g) const
+    {
+        chk(pmb_ocp_lagrangian_gradient(engine(), 1, var.data(), p.data(), lam.data(), &_lagrangian, lag_gradient.data(), cost_gradient.data(),
+                                        g.data(), jac_g.data()), "lagrangian_gradient");
+    }
+    void lagrangian_gradient_hessian(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p,
+                                     const Eigen::Ref<const nlp_dual_t>& lam, scalar_t& _lagrangian, Eigen::Ref<nlp_variable_t> lag_gradient,
+                                     Eigen::Ref<nlp_hessian_t> lag_hessian, Eigen::Ref<nlp_variable_t> cost_gradient,
+                                     Eigen::Ref<nlp_constraints_t> g, Eigen::Ref<nlp_jacobian_t> jac_g) const
+    {
+        chk(pmb_ocp_lagrangian_gradient_hessian(engine(), 1, var.data(), p.data(), lam.data(), &_lagrangian, lag_gradient.data(),
+                                                lag_hessian.data(), cost_gradient.data(), g.data(), jac_g.data()), "lagrangian_gradient_hessian");
+    }
+    /** time grid of the NLP variable, final time first (continuous_ocp.hpp:45-66) */
+    time_t time_nodes_now() const { time_t t; chk(pmb_ocp_time_nodes(engine(), t.data()), "time_nodes"); return t; }
+
+private:
+    static void chk(int rc, const char* what)
+    { if (rc != PMB_OK) throw std::runtime_error(std::string("ContinuousOCP::") + what + " failed (" + std::to_string(rc) + "): " + pmb_last_error()); }
+    /** one engine-side descriptor per problem class (this object stays trivially copyable); refreshed from *this on every call */
+    pmb_ocp_t* engine() const
+    {
+        static pmb_ocp_t* h = pmb_ocp_create(pmb::compat::problem_name<OCP>(), 0);
+        if (!h) throw std::runtime_error(std::string("pmb_ocp_create: ") + pmb_last_error());
+        const OCP& self = *static_cast<const OCP*>(this);
+        double blob[(sizeof(OCP) + 7) / 8] = {};
+        std::memcpy(blob, (const void*)&self, sizeof(OCP));
+        chk(pmb_ocp_set_params(h, blob, (int)((sizeof(OCP) + 7) / 8)), "set_params");
+        chk(pmb_ocp_set_time_limits(h, t_start, t_stop), "set_time_limits");
+        return h;
+    }
+
+public:
     /** defaults of the functor concept: no-ops, like continuous_ocp.hpp:206-216, 247-257, 278-288 */
     template <typename T>
     POLYMPC_HD void inequality_constraints_impl(const Eigen::Ref<const state_t<T>> x, const Eigen::Ref<const control_t<T>> u,

@@ -314,8 +314,8 @@ def run_gpu(args):
     cyc_tot = sum(phases.get(k, 0) for k in ("linearise", "qp", "step")) or 1
     roofline = {"kernel": "sqp_solve (fused persistent kernel: linearise + boxADMM/LDLT + line search, one CTA per instance)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("r1_sqp_solve_ncu_raw.csv") if (args.workload == "mobile_robot" and B == 8192) else None,
-                "traffic_source": "profiles/r1_sqp_solve_ncu_raw.csv (one ncu --set full capture of the same launch, batch 8192)",
+                "traffic": ncu_traffic("r1b_sqp_solve_ncu_raw.csv") if (args.workload == "mobile_robot" and B == 8192) else None,
+                "traffic_source": "profiles/r1b_sqp_solve_ncu_raw.csv (one ncu --set full capture of the same launch, batch 8192)",
                 "peak_source": peak_src, "avg_launch_ms": kernel_ms, "bytes_per_sqp_iteration": b_iter,
                 "sqp_iterations_per_launch": iters_per_solve,
                 "kernel_share_of_step": kernel_ms / (ms_total / args.steps),

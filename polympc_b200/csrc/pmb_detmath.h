@@ -22,8 +22,10 @@
 
 #if defined(__CUDACC__)
 #define PMB_HD __host__ __device__ __forceinline__
+#define PMB_DM_NOINLINE __host__ __device__ __noinline__ inline
 #else
 #define PMB_HD inline
+#define PMB_DM_NOINLINE __attribute__((noinline)) inline
 #endif
 
 namespace pmb {
@@ -172,9 +174,10 @@ PMB_HD double fmod_pos(double ax, double C)
 /** arguments beyond the range of the Cody-Waite reduction are first folded, exactly, modulo C = fl(2^18 * 2 pi): the result
  *  stays a sine/cosine of a nearby angle (|value| <= 1, phase error <= |x| * 2^-53) instead of degenerating — at such
  *  magnitudes the spacing of doubles exceeds 2 pi anyway.  Same operations on host and device. */
+constexpr double TRIG_FOLD = 1647099.3291652855;   // fl(2^20 * pi / 2)
 PMB_HD double fold_large(double x)
 {
-    const double C = 1647099.3291652855;   // fl(2^20 * pi / 2)
+    const double C = TRIG_FOLD;
     if (fabs(x) < C) return x;
     const double r = fmod_pos(fabs(x), C);
     return x < 0.0 ? -r : r;
@@ -182,41 +185,54 @@ PMB_HD double fold_large(double x)
 
 } // namespace detail
 
-PMB_HD double sin(double x)
+namespace detail {
+/** sine / cosine of a finite |x| < TRIG_FOLD (the range of the Cody-Waite reduction) */
+PMB_HD double sin_core(double x)
 {
-    if (isnan(x) || fabs(x) == inf()) return nan();
-    x = detail::fold_large(x);
     if (fabs(x) <= 0.78539816339744830962) {
         if (fabs(x) < 7.450580596923828125e-09) return x;  // 2^-27
-        return detail::k_sin(x, 0.0, 0);
+        return k_sin(x, 0.0, 0);
     }
     double y0, y1;
-    const int n = detail::rem_pio2(x, y0, y1);
+    const int n = rem_pio2(x, y0, y1);
     switch (n & 3) {
-    case 0:  return  detail::k_sin(y0, y1, 1);
-    case 1:  return  detail::k_cos(y0, y1);
-    case 2:  return -detail::k_sin(y0, y1, 1);
-    default: return -detail::k_cos(y0, y1);
+    case 0:  return  k_sin(y0, y1, 1);
+    case 1:  return  k_cos(y0, y1);
+    case 2:  return -k_sin(y0, y1, 1);
+    default: return -k_cos(y0, y1);
     }
 }
-
-PMB_HD double cos(double x)
+PMB_HD double cos_core(double x)
 {
-    if (isnan(x) || fabs(x) == inf()) return nan();
-    x = detail::fold_large(x);
     if (fabs(x) <= 0.78539816339744830962) {
         if (fabs(x) < 7.450580596923828125e-09) return 1.0;
-        return detail::k_cos(x, 0.0);
+        return k_cos(x, 0.0);
     }
     double y0, y1;
-    const int n = detail::rem_pio2(x, y0, y1);
+    const int n = rem_pio2(x, y0, y1);
     switch (n & 3) {
-    case 0:  return  detail::k_cos(y0, y1);
-    case 1:  return -detail::k_sin(y0, y1, 1);
-    case 2:  return -detail::k_cos(y0, y1);
-    default: return  detail::k_sin(y0, y1, 1);
+    case 0:  return  k_cos(y0, y1);
+    case 1:  return -k_sin(y0, y1, 1);
+    case 2:  return -k_cos(y0, y1);
+    default: return  k_sin(y0, y1, 1);
     }
 }
+/** everything that is not a finite |x| < TRIG_FOLD: NaN, +-inf, huge arguments.  Out of line on purpose: the hot kernels
+ *  inline sin / cos at every functor call site and never take this path (instruction-cache footprint). */
+PMB_DM_NOINLINE double sin_rare(double x)
+{
+    if (isnan(x) || fabs(x) == inf()) return nan();
+    return sin_core(fold_large(x));
+}
+PMB_DM_NOINLINE double cos_rare(double x)
+{
+    if (isnan(x) || fabs(x) == inf()) return nan();
+    return cos_core(fold_large(x));
+}
+} // namespace detail
+
+PMB_HD double sin(double x) { return (fabs(x) < detail::TRIG_FOLD) ? detail::sin_core(x) : detail::sin_rare(x); }
+PMB_HD double cos(double x) { return (fabs(x) < detail::TRIG_FOLD) ? detail::cos_core(x) : detail::cos_rare(x); }
 
 PMB_HD double tan(double x) { return sin(x) / cos(x); }
 

@@ -45,34 +45,26 @@ public:
                               const Eigen::Ref<const parameter_t<T>> p, const Eigen::Ref<const static_parameter_t>& d,
                               const T& t, Eigen::Ref<state_t<T>> xdot) const noexcept
     {
-        T c_AO = (T)5.1;
-        T v_0 = (T)104.9;
-        T k_w = (T)4032.0;
-        T A_R = (T)0.215;
-        T rho = (T)0.9342;
-        T C_P = (T)3.01;
-        T V_R = (T)10.0;
-        T H_1 = (T)4.2;
-        T H_2 = (T)-11.0;
-        T H_3 = (T)-41.85;
-        T m_K = (T)5.0;
-        T C_PK = (T)2.0;
-        T k10 = (T)1.287e12;
-        T k20 = (T)1.287e12;
-        T k30 = (T)9.043e09;
-        T E1 = (T)-9758.3;
-        T E2 = (T)-9758.3;
-        T E3 = (T)-8560.0;
-        T k_1 = k10 * exp(E1 / (273.15 + x(2)));
-        T k_2 = k20 * exp(E2 / (273.15 + x(2)));
-        T k_3 = k30 * exp(E3 / (273.15 + x(2)));
-        T TIMEUNITS_PER_HOUR = (T)3600.0;
+        // plant data (Klatt-Engell reactor, the benchmark the reference test uses); every constant enters as a T so that the
+        // operation tree — and with it every rounding — is the one of the engine's built-in "cstr_5x2" problem
+        const T feed_conc = (T)5.1, feed_temp = (T)104.9;                       // c_A0 [mol/l], inflow temperature [C]
+        const T kw = (T)4032.0, area = (T)0.215, volume = (T)10.0;              // jacket heat transfer, surface, reactor volume
+        const T density = (T)0.9342, cp = (T)3.01;                              // of the mixture
+        const T dh_ab = (T)4.2, dh_bc = (T)-11.0, dh_ad = (T)-41.85;            // reaction enthalpies
+        const T coolant_mass = (T)5.0, cp_coolant = (T)2.0;
+        const T k0_ab = (T)1.287e12, k0_bc = (T)1.287e12, k0_ad = (T)9.043e09;  // Arrhenius: k = k0 exp(E / (273.15 + temp))
+        const T e_ab = (T)-9758.3, e_bc = (T)-9758.3, e_ad = (T)-8560.0;
+        const T r_ab = k0_ab * exp(e_ab / (273.15 + x(2)));
+        const T r_bc = k0_bc * exp(e_bc / (273.15 + x(2)));
+        const T r_ad = k0_ad * exp(e_ad / (273.15 + x(2)));
+        const T hour = (T)3600.0;                                               // the model is written per hour, the OCP per second
+        const T per_second = 1 / hour;
 
-        xdot(0) = (1 / TIMEUNITS_PER_HOUR) * (u(0) * (c_AO - x(0)) - k_1 * x(0) - k_3 * x(0) * x(0));
-        xdot(1) = (1 / TIMEUNITS_PER_HOUR) * (-u(0) * x(1) + k_1 * x(0) - k_2 * x(1));
-        xdot(2) = (1 / TIMEUNITS_PER_HOUR) * (u(0) * (v_0 - x(2)) + (k_w * A_R / (rho * C_P * V_R)) *
-                                              (x(3) - x(2)) - (1 / (rho * C_P)) * (k_1 * x(0) * H_1 + k_2 * x(1) * H_2 + k_3 * x(0) * x(1) * H_3));
-        xdot(3) = (1 / TIMEUNITS_PER_HOUR) * ((1 / (m_K * C_PK)) * (u(1) + k_w * A_R * (x(2) - x(3))));
+        xdot(0) = per_second * (u(0) * (feed_conc - x(0)) - r_ab * x(0) - r_ad * x(0) * x(0));
+        xdot(1) = per_second * (-u(0) * x(1) + r_ab * x(0) - r_bc * x(1));
+        xdot(2) = per_second * (u(0) * (feed_temp - x(2)) + (kw * area / (density * cp * volume)) * (x(3) - x(2))
+                                - (1 / (density * cp)) * (r_ab * x(0) * dh_ab + r_bc * x(1) * dh_bc + r_ad * x(0) * x(1) * dh_ad));
+        xdot(3) = per_second * ((1 / (coolant_mass * cp_coolant)) * (u(1) + kw * area * (x(2) - x(3))));
     }
 
     template <typename T>

@@ -173,6 +173,18 @@ int pmb_sqp_get_qp_settings(const pmb_sqp_t* s, pmb_qp_settings_t* st);
  *                             r_i = sum_{j != i} |H_ji|:  H_ii += (r_i - H_ii) + 0.01  (applied after each exact Hessian).
  * Both default to 0 = the reference defaults. */
 int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int gershgorin_regularisation);
+/* hessian_update_impl (sqp_base.hpp:263-268), the quasi-Newton update used when the Hessian is not exact:
+ *   PMB_HESSIAN_BFGS_DENSE  BFGS_update (src/solvers/bfgs.hpp:23-52) on the dense H — the SQPBase default;
+ *   PMB_HESSIAN_BFGS_BLOCK  ContinuousOCP<..., SPARSE>::hessian_update_impl (src/control/continuous_ocp.hpp:2303-2431): the
+ *                           "sparsity preserving block BFGS" on the per-node (x_k,u_k) blocks and the parameter rows/columns —
+ *                           what every reference control test installs with
+ *                           `this->problem.hessian_update_impl(hessian, x_step, grad_step)` on a SPARSE problem
+ *                           (tests/control/mpc_wrapper_test.cpp:101-104, cstr_control_test.cpp:128-131 ...). */
+typedef enum pmb_hessian_update { PMB_HESSIAN_BFGS_DENSE = 0, PMB_HESSIAN_BFGS_BLOCK = 1 } pmb_hessian_update_t;
+int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode);
+/* per-iteration decision traces (pmb_sqp_get_trace) are recorded only when switched on before the solve (default off:
+ * they cost batch x max_iter rows of device memory and five memsets per solve) */
+int pmb_sqp_set_trace(pmb_sqp_t* s, int on);
 /* stride == 0: one vector broadcast to every instance; stride == len: one vector per instance */
 int pmb_sqp_set_bounds_x(pmb_sqp_t* s, const double* lbx, const double* ubx, int stride);   /* lower/upper_bound_x() */
 int pmb_sqp_set_bounds_g(pmb_sqp_t* s, const double* lbg, const double* ubg, int stride);   /* lower/upper_bound_g() */

@@ -75,10 +75,16 @@ inline double dot_tree32(const double* a, const double* b, int n)
     return partial[0];
 }
 
+/** lpNorm<Infinity>() = cwiseAbs().maxCoeff(): a chain of std::max-like steps  m = (m < v) ? v : m  that starts from the
+ *  first coefficient [Eigen-ext: Redux.h + scalar_max_op].  A NaN in the first coefficient therefore sticks (nothing
+ *  compares greater than it), a NaN anywhere else is skipped; an all-NaN vector has norm NaN, so `norm <= eps` is false.
+ *  (Eigen's packet path keeps one such chain per SIMD lane; which coefficients count as "first" then depends on the vector
+ *  ISA — parity unpinned for partially-NaN vectors, the all-NaN / all-finite cases do not depend on it.) */
 inline double norm_inf(const double* a, int n)
 {
-    double m = 0.0;
-    for (int i = 0; i < n; ++i) { const double v = dm::fabs(a[i]); if (v > m) m = v; }
+    if (n <= 0) return 0.0;
+    double m = dm::fabs(a[0]);
+    for (int i = 1; i < n; ++i) { const double v = dm::fabs(a[i]); if (m < v) m = v; }
     return m;
 }
 

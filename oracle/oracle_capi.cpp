@@ -84,6 +84,7 @@ struct ISqpInst {
     virtual SqpSettings& settings() = 0;
     virtual QpSettings& qp_settings() = 0;
     virtual void hessian_options(int exact, int gershgorin) = 0;
+    virtual void hessian_update(int block) = 0;
     virtual SqpInfo& info() = 0;
     virtual std::vector<double>& x() = 0;
     virtual std::vector<double>& lam() = 0;
@@ -104,6 +105,7 @@ struct SqpInst : ISqpInst {
     SqpSettings& settings() override { return s.settings; }
     QpSettings& qp_settings() override { return s.qp.settings; }
     void hessian_options(int exact, int gershgorin) override { s.opt_exact_hessian = exact; s.opt_gershgorin = gershgorin; }
+    void hessian_update(int block) override { s.opt_block_bfgs = block; }
     SqpInfo& info() override { return s.info; }
     std::vector<double>& x() override { return s.x; }
     std::vector<double>& lam() override { return s.lam; }
@@ -189,6 +191,7 @@ extern "C" {
 /** oracle-only knob: number of host threads used to sweep the batch (CPU baseline timing) */
 void orc_set_num_threads(int n) { g_threads = n > 0 ? n : 1; }
 int orc_get_num_threads(void) { return g_threads; }
+void orc_set_ldlt_variant(int v) { orc::ldlt_variant() = v; }
 
 const char* pmb_version(void) { return "polympc-oracle 0.1 (CPU restatement, test infrastructure)"; }
 const char* pmb_last_error(void) { return g_err.c_str(); }
@@ -397,6 +400,13 @@ int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int ger
     for (auto& i : s->inst) i->hessian_options(exact_every_iteration != 0, gershgorin_regularisation != 0);
     return PMB_OK;
 }
+int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
+{
+    if (!s || (mode != PMB_HESSIAN_BFGS_DENSE && mode != PMB_HESSIAN_BFGS_BLOCK)) return PMB_ERR_BAD_ARGUMENT;
+    for (auto& i : s->inst) i->hessian_update(mode == PMB_HESSIAN_BFGS_BLOCK);
+    return PMB_OK;
+}
+int pmb_sqp_set_trace(pmb_sqp_t* s, int) { return s ? PMB_OK : PMB_ERR_BAD_ARGUMENT; }   /* the oracle always records its traces */
 /* the oracle has no kernels to register: problem classes are added to its own table (REG above) */
 int pmb_register_problem(const char*, void* (*)(void)) { g_err = "the oracle does not register external problems"; return PMB_ERR_BAD_ARGUMENT; }
 

@@ -14,6 +14,7 @@
 #include "canon.hpp"
 #include <vector>
 #include <cfloat>
+#include "ldlt_variants.hpp"
 
 namespace orc {
 
@@ -83,13 +84,23 @@ struct Ldlt {
         }
         for (int i = 0; i < n; ++i) perm[i] = i;
         for (int k = 0; k < n; ++k) { const int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+        if (ldlt_variant() > 0) {
+            std::vector<double> Kp((size_t)n * n, 0.0);
+            for (int b = 0; b < n; ++b) for (int a = b; a < n; ++a) {
+                const int r = perm[a], c = perm[b];
+                Kp[a + (size_t)b * n] = r >= c ? K[r + (size_t)c * n] : K[c + (size_t)r * n];
+            }
+            fast.compute(Kp.data(), n, ldlt_variant());
+        }
     }
+    LdltFast fast;
 
     void solve(const double* rhs, double* x) const
     {
         std::vector<double> y(n);
         auto m = [&](int r, int c) -> double { return L[r + (size_t)c * n]; };
         for (int a = 0; a < n; ++a) y[a] = rhs[perm[a]];
+        if (ldlt_variant() > 0) { fast.solve(y.data(), ldlt_variant()); for (int a = 0; a < n; ++a) x[perm[a]] = y[a]; return; }
         for (int i = 0; i < n; ++i) {            // unit lower: ascending columns
             double acc = y[i];
             for (int j = 0; j < i; ++j) acc = dm::fma(-m(i, j), y[j], acc);
@@ -208,12 +219,13 @@ struct BoxAdmm {
         const double norm_Hx = norm_inf(Hx.data(), N), norm_ATy = norm_inf(ATy.data(), N), norm_h = norm_inf(h, N),
                      norm_y_box = norm_inf(y.data() + M, N);
         max_Hx_ATy_h_norm = fmax_(norm_Hx, fmax_(norm_ATy, fmax_(norm_h, norm_y_box)));
-        double rp = 0.0, rq = 0.0, rd = 0.0;
-        for (int i = 0; i < M; ++i) { const double v = dm::fabs(Ax[i] - z[i]); if (v > rp) rp = v; }
-        for (int i = 0; i < N; ++i) { const double v = dm::fabs(x[i] - q[i]); if (v > rq) rq = v; }
-        info.res_prim = rp + rq;
-        for (int i = 0; i < N; ++i) { const double v = dm::fabs(((Hx[i] + h[i]) + ATy[i]) + y[M + i]); if (v > rd) rd = v; }
-        info.res_dual = rd;
+        // primal_residual / dual_residual (qp_base.hpp) are lpNorm<Infinity>() of the residual vectors
+        std::vector<double> rpv(M), rqv(N), rdv(N);
+        for (int i = 0; i < M; ++i) rpv[i] = Ax[i] - z[i];
+        for (int i = 0; i < N; ++i) rqv[i] = x[i] - q[i];
+        for (int i = 0; i < N; ++i) rdv[i] = ((Hx[i] + h[i]) + ATy[i]) + y[M + i];
+        info.res_prim = norm_inf(rpv.data(), M) + norm_inf(rqv.data(), N);
+        info.res_dual = norm_inf(rdv.data(), N);
     }
     bool termination_criteria() const
     {

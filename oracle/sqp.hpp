@@ -47,6 +47,68 @@ inline int bfgs_update(double* B, const double* s, const double* y, int n)
     return branch;
 }
 
+/** ContinuousOCP<..., SPARSE>::hessian_update_impl (continuous_ocp.hpp:2303-2431): the "sparsity preserving block BFGS" every
+ *  reference control test installs through `this->problem.hessian_update_impl(hessian, x_step, grad_step)`.  Only the
+ *  per-node (x_k,u_k) diagonal blocks and the parameter rows / columns of H are stored (and updated); everything else of H
+ *  is structurally zero.  Differences from bfgs.hpp: the product v = H s runs over the stored pattern, the update is never
+ *  skipped, the coefficients are reciprocals (-1/s'v, 1/s'y or 1/s'r) multiplied into the FIRST factor of every outer
+ *  product, and the increments of one block are summed before they are added to H.
+ *  Canonical orders: v_i = fused chain over the stored columns of row i in ascending column index; dots are tree32.
+ *  Returns the branch: 0 plain, 1 damped. */
+template <class OcpT>
+inline int block_bfgs_update(double* H, const double* s, const double* y)
+{
+    constexpr int NX = OcpT::NX, NU = OcpT::NU, NP = OcpT::NP, NN = OcpT::NN, VARX = OcpT::VARX, VARU = OcpT::VARU, N = OcpT::N;
+    auto Hm = [&](int r, int c) -> double& { return H[r + (size_t)c * N]; };
+    std::vector<double> v(N), r(N);
+    for (int k = 0; k < NN; ++k) {
+        for (int a = 0; a < NX + NU; ++a) {
+            const int row = a < NX ? k * NX + a : VARX + k * NU + (a - NX);
+            double acc = 0.0;
+            for (int j = 0; j < NX; ++j) acc = dm::fma(Hm(row, k * NX + j), s[k * NX + j], acc);
+            for (int j = 0; j < NU; ++j) acc = dm::fma(Hm(row, VARX + k * NU + j), s[VARX + k * NU + j], acc);
+            for (int j = 0; j < NP; ++j) acc = dm::fma(Hm(row, VARX + VARU + j), s[VARX + VARU + j], acc);
+            v[row] = acc;
+        }
+    }
+    for (int a = 0; a < NP; ++a) v[VARX + VARU + a] = dot_seq(H + VARX + VARU + a, N, s, 1, N);
+    const double scaling = dot_tree32(s, v.data(), N);
+    const double scaling_inv = 1.0 / scaling;
+    const double sy = dot_tree32(s, y, N);
+    const double sy_inv = 1.0 / sy;
+    const bool plain = sy >= 0.2 * scaling;
+    double c2 = sy_inv;
+    const double* w = y;                        // second rank-one term: c2 * w w'
+    if (!plain) {
+        const double theta = 0.8 * scaling / (scaling - sy);
+        for (int i = 0; i < N; ++i) r[i] = theta * y[i] + (1 - theta) * v[i];
+        c2 = 1.0 / dot_tree32(s, r.data(), N);
+        w = r.data();
+    }
+    const double c1 = -scaling_inv;
+    auto inc = [&](int i, int j) { double h = (c1 * v[i]) * v[j]; h += (c2 * w[i]) * w[j]; return h; };   // (i, j) of a block
+    for (int k = 0; k < NN; ++k) {
+        const int x0 = k * NX, u0 = VARX + k * NU;
+        for (int j = 0; j < NX; ++j) for (int i = 0; i < NX; ++i) Hm(x0 + i, x0 + j) += inc(x0 + i, x0 + j);   // hes_xx
+        for (int j = 0; j < NU; ++j) for (int i = 0; i < NU; ++i) Hm(u0 + i, u0 + j) += inc(u0 + i, u0 + j);   // hes_uu
+        for (int j = 0; j < NX; ++j) for (int i = 0; i < NU; ++i) {                                            // hes_ux and its transpose
+            const double h = inc(u0 + i, x0 + j);
+            Hm(u0 + i, x0 + j) += h;
+            Hm(x0 + j, u0 + i) += h;
+        }
+    }
+    if (NP > 0) {
+        const int p0 = VARX + VARU;
+        for (int j = 0; j < NP; ++j) for (int i = 0; i < NP; ++i) Hm(p0 + i, p0 + j) += inc(p0 + i, p0 + j);   // hes_pp
+        for (int j = 0; j < NP; ++j) for (int i = 0; i < p0; ++i) {                                            // hes_ap: column j and row j
+            const double h = inc(i, p0 + j);
+            Hm(i, p0 + j) += h;
+            Hm(p0 + j, i) += h;
+        }
+    }
+    return plain ? 0 : 1;
+}
+
 /** SQPBase<Derived, ContinuousOCP<...,DENSE>, boxADMM<...>, IdentityPreconditioner> with all default hooks */
 template <class OcpT>
 struct Sqp {
@@ -145,6 +207,7 @@ struct Sqp {
     // reference's own solvers install, tests/control/minimal_time_test.cpp:90-135
     int opt_exact_hessian = 0;   // update_linearisation_dense_impl := linearisation_dense_impl (exact Hessian at every iteration)
     int opt_gershgorin = 0;      // hessian_regularisation_dense_impl := Gershgorin shift of the diagonal
+    int opt_block_bfgs = 0;      // hessian_update_impl := the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)
 
     /** minimal_time_test.cpp:90-104; called from linearisation_dense_impl (sqp_base.hpp:316-317).  cwiseAbs().sum() of a
      *  column is taken in sequential ascending order ("parity unpinned": Eigen's order depends on the vector ISA). */
@@ -220,7 +283,8 @@ struct Sqp {
             std::vector<double> lg(N), yv(N);
             problem.lagrangian_gradient(x.data(), p_static.data(), lam.data(), lagv, lg.data(), h.data(), al.data(), A.data());
             for (int i = 0; i < N; ++i) yv[i] = lg[i] - lag_gradient[i];
-            tr_bfgs.push_back(bfgs_update(H.data(), step_prev.data(), yv.data(), N));
+            tr_bfgs.push_back(opt_block_bfgs ? block_bfgs_update<OcpT>(H.data(), step_prev.data(), yv.data())
+                                             : bfgs_update(H.data(), step_prev.data(), yv.data(), N));
             lag_gradient = lg;
             prepare_qp_bounds();
             if (iterate_tail(p, p_lambda)) { info.status = SQP_SOLVED; break; }

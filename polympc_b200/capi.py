@@ -58,7 +58,7 @@ ABI_FUNCTIONS = [
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
@@ -128,6 +128,8 @@ class CApi:
         g("sqp_set_qp_settings").argtypes = [C.c_void_p, C.POINTER(QpSettings)]
         g("sqp_get_qp_settings").argtypes = [C.c_void_p, C.POINTER(QpSettings)]
         g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
+        g("sqp_set_hessian_update").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_set_trace").argtypes = [C.c_void_p, C.c_int]
         for name in ("sqp_set_bounds_x", "sqp_set_bounds_g"):
             g(name).argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int]
         for name in ("sqp_set_parameters", "sqp_set_primal", "sqp_set_dual"):
@@ -419,6 +421,14 @@ class Sqp:
         """the fixed menu of SQPBase CRTP overrides (reference tests/control/minimal_time_test.cpp:90-135)"""
         self.api._chk(self.api._fn("sqp_set_hessian_options")(self.h, int(exact_every_iteration), int(gershgorin_regularisation)),
                       "sqp_set_hessian_options")
+
+    def set_hessian_update(self, mode: int):
+        """0 = dense damped BFGS (SQPBase default), 1 = the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)"""
+        self.api._chk(self.api._fn("sqp_set_hessian_update")(self.h, int(mode)), "sqp_set_hessian_update")
+
+    def set_trace(self, on: bool = True):
+        """record the per-iteration decision traces read by trace() (off by default)"""
+        self.api._chk(self.api._fn("sqp_set_trace")(self.h, int(on)), "sqp_set_trace")
 
     def _vec(self, v, length):
         v = _f64(v)

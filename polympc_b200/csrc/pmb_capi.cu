@@ -158,6 +158,8 @@ struct pmb_sqp {
     pmb_sqp_settings_t settings;
     pmb_qp_settings_t qp_settings;
     int opt_exact_hessian = 0, opt_gershgorin = 0;   // pmb_sqp_set_hessian_options
+    int opt_block_bfgs = 0;                          // pmb_sqp_set_hessian_update
+    bool trace_on = false;                           // pmb_sqp_set_trace
     pmb::stream_t own_stream = nullptr, stream = nullptr;
     pmb::event_t ev0 = nullptr, ev1 = nullptr;
     pmb::DevBuf<double> x_guess, lam_guess;   // device copies of the initial guess (pmb_sqp_reset_guess)
@@ -475,6 +477,14 @@ int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int ger
     return PMB_OK;
 }
 
+int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
+{
+    if (!s || (mode != PMB_HESSIAN_BFGS_DENSE && mode != PMB_HESSIAN_BFGS_BLOCK)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_hessian_update: bad argument");
+    s->opt_block_bfgs = mode == PMB_HESSIAN_BFGS_BLOCK;
+    return PMB_OK;
+}
+int pmb_sqp_set_trace(pmb_sqp_t* s, int on) { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->trace_on = on != 0; return PMB_OK; }
+
 static int sqp_set_vec(pmb_sqp_t* s, double* dst, const double* v, int stride, size_t len)
 {
     if (len == 0) return PMB_OK;
@@ -572,7 +582,7 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
     if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
     const int B = s->batch;
-    const int rows = s->settings.max_iter > 0 ? s->settings.max_iter : 1;
+    const int rows = !s->trace_on ? 0 : (s->settings.max_iter > 0 ? s->settings.max_iter : 1);
     if (rows != s->trace_rows) {
         const size_t T = (size_t)B * rows;
         if (!(s->tr_qp_iter.resize(T) && s->tr_bfgs.resize(T) && s->tr_ls.resize(T) && s->tr_qp_factor.resize(T) && s->tr_alpha.resize(T))) return PMB_ERR_CUDA;
@@ -581,20 +591,21 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     stream_t st = s->stream;
     bool ok = rt_event_record(s->ev0, st);
     long long launches = 0;
-    {
+    ok = ok && rt_memset(s->queue.p, 0, sizeof(int), st);
+    if (rows > 0) {
         const size_t T = (size_t)B * rows;
         ok = ok && rt_memset(s->tr_qp_iter.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_bfgs.p, 0xFF, T * sizeof(int), st) &&
              rt_memset(s->tr_ls.p, 0xFF, T * sizeof(int), st) && rt_memset(s->tr_qp_factor.p, 0xFF, T * sizeof(int), st) &&
-             rt_memset(s->tr_alpha.p, 0xFF, T * sizeof(double), st) && rt_memset(s->queue.p, 0, sizeof(int), st);
+             rt_memset(s->tr_alpha.p, 0xFF, T * sizeof(double), st);
     }
     SqpWs ws{};
     ws.x = s->x.p; ws.lam = s->lam.p; ws.lam_k = s->lam_k.p; ws.H = s->H.p; ws.A = s->A.p; ws.h = s->h.p; ws.al = s->al.p; ws.au = s->au.p;
     ws.lx = s->lx.p; ws.ux = s->ux.p; ws.lbx = s->lbx.p; ws.ubx = s->ubx.p; ws.lbg = s->lbg.p; ws.ubg = s->ubg.p; ws.d = s->d.p;
     ws.lag_grad = s->lag_grad.p; ws.step_prev = s->step_prev.p; ws.p = s->p.p; ws.plam = s->plam.p; ws.stats = s->stats.p;
     ws.info = s->info.p; ws.qp_info = s->qp_info.p; ws.qp_nfac = s->qp_nfac.p;
-    ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p;
+    if (rows > 0) { ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p; }
     ws.trace_rows = rows;
-    ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin;
+    ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin; ws.opt_block_bfgs = s->opt_block_bfgs;
     ws.phase = nullptr;
     if (s->profiling) {
         ok = ok && s->phase.resize(16) && rt_memset(s->phase.p, 0, 16 * sizeof(unsigned long long), st);
@@ -643,6 +654,7 @@ int pmb_sqp_get_stats(const pmb_sqp_t* s, double* st) { return sqp_get(s, st, s 
 int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf, int* ls, int* qf)
 {
     if (!s || rows <= 0) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "get_trace: bad argument");
+    if (s->trace_rows == 0) PMB_FAIL(PMB_ERR_UNSUPPORTED, "get_trace: traces were off during the last solve (pmb_sqp_set_trace)");
     if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
     const size_t B = s->batch, T = s->trace_rows;
     std::vector<int> ti(B * T); std::vector<double> td(B * T);

@@ -56,7 +56,7 @@ inline size_t qp_factor_doubles(int N, int M) { const size_t n = (size_t)N + M; 
 inline size_t qp_vec_bytes(int N, int M)
 {
     const size_t n = (size_t)N + M;
-    const size_t doubles = 3 * n + 6 * (size_t)N + 4 * (size_t)M;
+    const size_t doubles = 3 * n + 6 * (size_t)N + 4 * (size_t)M + 12;   // + first coefficients of the 10 residual norms
     return doubles * sizeof(double) + 2 * n * sizeof(int) + 16;
 }
 
@@ -523,7 +523,8 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     double* ya = z + M;
     double* rv = ya + M;
     double* rvi = rv + M;
-    int* perm = reinterpret_cast<int*>(rvi + M);
+    double* first = rvi + M;   // [12]
+    int* perm = reinterpret_cast<int*>(first + 12);
     int* ctype = perm + n;     // [constr_type (M) ; box_constr_type (N)]
     const double *alb = a.Alb, *aub = a.Aub, *xlb = a.xlb, *xub = a.xub;   // bounds stay in global memory (read-only here)
 
@@ -592,27 +593,39 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         double m[NRED];
         PMB_UNROLL
         for (int k = 0; k < NRED; ++k) m[k] = 0.0;
+        // every norm is an lpNorm<Infinity>() = a max chain that starts from the FIRST coefficient: a NaN there sticks, a NaN
+        // anywhere else is skipped (oracle/canon.hpp::norm_inf).  The owners of row 0 publish |first coefficient| in first[].
+        if (tid < NRED) first[tid] = 0.0;
+        c.sync();
         for (int t = tid; t < M + N; t += nt) {
             if (t < M) {
                 const int i = t;
                 const double acc = dot_chain(a.A + i, (size_t)M, x, N);
-                double v = dm::fabs(acc); if (v > m[nAx]) m[nAx] = v;
-                v = dm::fabs(z[i]); if (v > m[nz]) m[nz] = v;
-                v = dm::fabs(acc - z[i]); if (v > m[rp]) m[rp] = v;
+                const double v0 = dm::fabs(acc), v1 = dm::fabs(z[i]), v2 = dm::fabs(acc - z[i]);
+                if (v0 > m[nAx]) m[nAx] = v0;
+                if (v1 > m[nz]) m[nz] = v1;
+                if (v2 > m[rp]) m[rp] = v2;
+                if (i == 0) { first[nAx] = v0; first[nz] = v1; first[rp] = v2; }
             } else {
                 const int i = t - M;
                 const double hx = dot_chain(a.H + i, (size_t)N, x, N);
                 const double aty = dot_chain(a.A + (size_t)i * M, 1, ya, M);
-                double v = dm::fabs(x[i]); if (v > m[nx]) m[nx] = v;
-                v = dm::fabs(hx); if (v > m[nHx]) m[nHx] = v;
-                v = dm::fabs(aty); if (v > m[nATy]) m[nATy] = v;
-                v = dm::fabs(h[i]); if (v > m[nh]) m[nh] = v;
-                v = dm::fabs(yb[i]); if (v > m[nyb]) m[nyb] = v;
-                v = dm::fabs(x[i] - q[i]); if (v > m[rq]) m[rq] = v;
-                v = dm::fabs(((hx + h[i]) + aty) + yb[i]); if (v > m[rd]) m[rd] = v;
+                const double v0 = dm::fabs(x[i]), v1 = dm::fabs(hx), v2 = dm::fabs(aty), v3 = dm::fabs(h[i]), v4 = dm::fabs(yb[i]);
+                const double v5 = dm::fabs(x[i] - q[i]), v6 = dm::fabs(((hx + h[i]) + aty) + yb[i]);
+                if (v0 > m[nx]) m[nx] = v0;
+                if (v1 > m[nHx]) m[nHx] = v1;
+                if (v2 > m[nATy]) m[nATy] = v2;
+                if (v3 > m[nh]) m[nh] = v3;
+                if (v4 > m[nyb]) m[nyb] = v4;
+                if (v5 > m[rq]) m[rq] = v5;
+                if (v6 > m[rd]) m[rd] = v6;
+                if (i == 0) { first[nx] = v0; first[nHx] = v1; first[nATy] = v2; first[nh] = v3; first[nyb] = v4; first[rq] = v5; first[rd] = v6; }
             }
         }
+        c.sync();
         c.max_all<NRED>(m);
+        PMB_UNROLL
+        for (int k = 0; k < NRED; ++k) { const double f = first[k]; if (f != f) m[k] = f; }
         max_Ax_z = fmax_nan(m[nAx], fmax_nan(m[nz], m[nx]));
         max_Hx_ATy_h = fmax_nan(m[nHx], fmax_nan(m[nATy], fmax_nan(m[nh], m[nyb])));
         res_prim = m[rp] + m[rq];

@@ -17,11 +17,16 @@ namespace pmb {
 PMB_DEV double dot_tree32(Cta& c, const double* a, const double* b, int n)
 { return sum_tree32(c, n, [&](int i, double acc) { return dm::fma(a[i], b[i], acc); }); }
 
+/** lpNorm<Infinity>() = cwiseAbs().maxCoeff(): a std::max-like chain that starts from the first coefficient, so a NaN in
+ *  a[0] sticks and a NaN anywhere else is skipped (oracle/canon.hpp::norm_inf).  The maximum over the non-NaN entries is
+ *  exact and order free; the first-coefficient rule is applied afterwards. */
 PMB_DEV double norm_inf_cta(Cta& c, const double* a, int n)
 {
     double m = 0.0;
     for (int i = c.tid(); i < n; i += c.nthreads()) { const double v = dm::fabs(a[i]); if (v > m) m = v; }
-    return c.max_all1(m);
+    m = c.max_all1(m);
+    const double a0 = dm::fabs(a[0]);
+    return (a0 != a0) ? a0 : m;
 }
 
 /** bfgs.hpp:23-52.  B (n x n, column-major) is updated in place; Bs, r: scratch of n doubles each (shared memory).
@@ -58,6 +63,67 @@ PMB_DEV int bfgs_update_cta(Cta& c, int n, double* B, const double* s, const dou
     return branch;
 }
 
+/** ContinuousOCP<..., SPARSE>::hessian_update_impl (continuous_ocp.hpp:2303-2431), the block BFGS the reference's control
+ *  tests install: only the per-node (x_k, u_k) blocks and the parameter rows / columns of H are stored and updated.
+ *  v = H s over the stored pattern (ascending column index, fused chain), coefficients -1/s'v, 1/s'y (or 1/s'r, damped)
+ *  multiplied into the first factor of every outer product, the two increments of an entry summed before they are added;
+ *  the (x, u) and (., p) blocks are the transposes of the (u, x) and (p, .) ... see oracle/sqp.hpp::block_bfgs_update.
+ *  v, r: scratch of N doubles each (shared memory).  Returns 0 plain, 1 damped (uniform over the block). */
+template <class O>
+PMB_DEV int block_bfgs_update_cta(Cta& c, double* H, const double* s, const double* y, double* v, double* r)
+{
+    constexpr int NX = O::NX, NU = O::NU, NP = O::NP, NN = O::NN, VARX = O::VARX, VARU = O::VARU, N = O::N, NB = NX + NU, P0 = VARX + VARU;
+    const int tid = c.tid(), nt = c.nthreads();
+    for (int row = tid; row < N; row += nt) {
+        double acc = 0.0;
+        if (row < P0) {
+            const int k = row < VARX ? row / NX : (row - VARX) / NU;
+            const double* Hr = H + row;
+            for (int j = 0; j < NX; ++j) acc = dm::fma(Hr[(size_t)(k * NX + j) * N], s[k * NX + j], acc);
+            for (int j = 0; j < NU; ++j) acc = dm::fma(Hr[(size_t)(VARX + k * NU + j) * N], s[VARX + k * NU + j], acc);
+            for (int j = 0; j < NP; ++j) acc = dm::fma(Hr[(size_t)(P0 + j) * N], s[P0 + j], acc);
+        } else {
+            acc = dot_chain(H + row, (size_t)N, s, N);
+        }
+        v[row] = acc;
+    }
+    c.sync();
+    const double scaling = dot_tree32(c, s, v, N);
+    const double c1 = -(1.0 / scaling);
+    const double sy = dot_tree32(c, s, y, N);
+    const bool plain = sy >= 0.2 * scaling;
+    double c2 = 1.0 / sy;
+    if (!plain) {
+        const double theta = 0.8 * scaling / (scaling - sy);
+        for (int i = tid; i < N; i += nt) r[i] = theta * y[i] + (1 - theta) * v[i];
+        c.sync();
+        c2 = 1.0 / dot_tree32(c, s, r, N);
+    } else {
+        for (int i = tid; i < N; i += nt) r[i] = y[i];
+        c.sync();
+    }
+    auto inc = [&](int i, int j) { double h = (c1 * v[i]) * v[j]; h += (c2 * r[i]) * r[j]; return h; };
+    // node blocks: entry (a, b) of the (NX+NU)^2 block of node k; the (x, u) part is the transpose of the (u, x) part
+    for (int e = tid; e < NN * NB * NB; e += nt) {
+        const int k = e / (NB * NB), q = e - k * NB * NB, b = q / NB, a = q - b * NB;
+        const int gi = a < NX ? k * NX + a : VARX + k * NU + (a - NX);
+        const int gj = b < NX ? k * NX + b : VARX + k * NU + (b - NX);
+        const double h = (a < NX && b >= NX) ? inc(gj, gi) : inc(gi, gj);
+        H[gi + (size_t)gj * N] += h;
+    }
+    if (NP > 0) {
+        for (int e = tid; e < NP * NP; e += nt) { const int j = e / NP, i = e - j * NP; H[(P0 + i) + (size_t)(P0 + j) * N] += inc(P0 + i, P0 + j); }
+        for (int e = tid; e < NP * P0; e += nt) {
+            const int j = e / P0, i = e - j * P0;
+            const double h = inc(i, P0 + j);
+            H[i + (size_t)(P0 + j) * N] += h;
+            H[(P0 + j) + (size_t)i * N] += h;
+        }
+    }
+    c.sync();
+    return plain ? 0 : 1;
+}
+
 /** batch-wide SQP state in global memory (instance-major arrays) */
 struct SqpWs {
     double *x, *lam, *lam_k, *H, *A, *h, *al, *au, *lx, *ux, *lbx, *ubx, *lbg, *ubg, *d, *lag_grad, *step_prev, *p, *plam, *stats;
@@ -69,6 +135,7 @@ struct SqpWs {
     int trace_rows;
     int opt_exact_hessian;       // pmb_sqp_set_hessian_options: exact Lagrangian Hessian at every iteration (no BFGS)
     int opt_gershgorin;          //                              Gershgorin shift after every exact Hessian
+    int opt_block_bfgs;          // pmb_sqp_set_hessian_update: the OCP's block BFGS instead of the dense damped BFGS
     unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
                                  // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
 };
@@ -117,6 +184,7 @@ struct SqpDev {
         }
         if (NUM_EQ > 0) cv = norm_inf_cta(c, cg, NUM_EQ);
         const double NEG = -dm::inf();
+        // maxCoeff() is the same kind of chain as lpNorm<Infinity>: it starts from the first coefficient, a NaN there sticks
         if (NUM_INEQ > 0) {
             double m[2] = {NEG, NEG};
             for (int i = tid; i < NUM_INEQ; i += nt) {
@@ -125,6 +193,9 @@ struct SqpDev {
                 if (b > m[1]) m[1] = b;
             }
             c.max_all<2>(m);
+            const double a0 = s.lbg()[0] - cg[NUM_EQ], b0 = cg[NUM_EQ] - s.ubg()[0];
+            if (a0 != a0) m[0] = a0;
+            if (b0 != b0) m[1] = b0;
             cv = fmax_nan(cv, m[0]); cv = fmax_nan(cv, m[1]);
         }
         double m[2] = {NEG, NEG};
@@ -134,6 +205,9 @@ struct SqpDev {
             if (b > m[1]) m[1] = b;
         }
         c.max_all<2>(m);
+        const double a0 = s.lbx()[0] - xv[0], b0 = xv[0] - s.ubx()[0];
+        if (a0 != a0) m[0] = a0;
+        if (b0 != b0) m[1] = b0;
         cv = fmax_nan(cv, m[0]); cv = fmax_nan(cv, m[1]);
         return cv;
     }
@@ -169,7 +243,8 @@ struct SqpDev {
             cost_x = E::lagrangian_gradient(c, o, s.x(), s.d(), s.lam(), lg, s.h(), s.al(), s.A());
             for (int i = tid; i < N; i += nt) yv[i] = lg[i] - s.lag_grad()[i];
             c.sync();
-            const int br = bfgs_update_cta(c, N, s.H(), s.step_prev(), yv, Bs, r);
+            const int br = s.ws.opt_block_bfgs ? block_bfgs_update_cta<O>(c, s.H(), s.step_prev(), yv, Bs, r)
+                                               : bfgs_update_cta(c, N, s.H(), s.step_prev(), yv, Bs, r);
             if (s.tr_bfgs() && tid == 0) s.tr_bfgs()[trace_row] = br;
             for (int i = tid; i < N; i += nt) s.lag_grad()[i] = lg[i];
         }

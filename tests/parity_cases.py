@@ -146,10 +146,13 @@ def kkt_case(api, orc, N, M, B=3, seed=0):
     assert_same(api.kkt_assemble(H, A, rb, ri, 1e-6), orc.kkt_assemble(H, A, rb, ri, 1e-6), "kkt")
 
 
-def solve_workload(api, w, lo=0, hi=None, name=None):
+def solve_workload(api, w, lo=0, hi=None, name=None, hessian_update=0):
     hi = w.batch if hi is None else hi
     s = api.sqp(name or w.name, hi - lo)
     W.configure(s, w, lo, hi)
+    s.set_trace(True)
+    if hessian_update:
+        s.set_hessian_update(hessian_update)
     s.solve()
     out = dict(x=s.primal(), lam=s.dual(), info=s.info(), stats=s.stats(), trace=s.trace(w.sqp_max_iter),
                ms=s.last_solve_ms(), launches=s.last_solve_launches())
@@ -157,9 +160,10 @@ def solve_workload(api, w, lo=0, hi=None, name=None):
     return out
 
 
-def sqp_case(api, orc, w):
+def sqp_case(api, orc, w, hessian_update=0):
     """a11-a14, a22: whole SQP solves; iterates, multipliers, info and the per-iteration decision trace"""
-    ra, rb = solve_workload(api, w), solve_workload(orc, w, name=ORACLE_TWIN.get(w.name, w.name))
+    ra = solve_workload(api, w, hessian_update=hessian_update)
+    rb = solve_workload(orc, w, name=ORACLE_TWIN.get(w.name, w.name), hessian_update=hessian_update)
     for f in ("iter", "qp_solver_iter", "status"):
         assert_same(ra["info"][f], rb["info"][f], "sqp.info." + f)
     for k in ("qp_iter", "bfgs", "ls_trials", "qp_factor", "alpha"):

@@ -129,12 +129,12 @@ def test_qp_nonfinite_jacobian_rows_with_zero_guess(emu, orc):
 
 def test_sqp_cstr_warm_restart_that_diverges(emu, orc):
     """cstr_control_test.cpp:137-177 on the dense path: the warm-started second solve() linearises with the kept
-    multipliers, its exact Hessian is indefinite, the iterates overflow to NaN after four iterations and the NaN-blind
-    termination test then reports SOLVED — on both sides, with identical traces (the reference has no safeguard either)"""
+    multipliers, its exact Hessian is indefinite and the iterates overflow to NaN after four iterations.  lpNorm<Infinity> of an
+    all-NaN step is NaN, `NaN <= eps` is false, so the status stays MAX_ITER_EXCEEDED — on both sides, with identical traces"""
     outs = []
     for api in (emu, orc):
         w = W.cstr(1, sqp_max_iter=20, ls_max_iter=20); w.x0[:] = [1.0, 0.5, 100.0, 100.0]
-        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.solve()
+        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.set_trace(True); s.solve()
         first = s.info().copy()
         s.set_initial_conditions(np.array([[1.1, 0.508, 100.5, 100.1]])); s.solve()
         outs.append((first, s.info().copy(), s.primal(), s.dual(), s.stats(), s.trace(20)))
@@ -157,7 +157,7 @@ def test_sqp_hessian_options(emu, orc, exact, gersh):
     outs = []
     for api in (emu, orc):
         w = W.cstr(1, sqp_max_iter=20, ls_max_iter=20); w.x0[:] = [1.0, 0.5, 100.0, 100.0]
-        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.set_hessian_options(exact, gersh); s.solve()
+        s = api.sqp("cstr_5x2", 1); W.configure(s, w); s.set_trace(True); s.set_hessian_options(exact, gersh); s.solve()
         first = s.info().copy()
         s.set_initial_conditions(np.array([[1.1, 0.508, 100.5, 100.1]])); s.solve()
         outs.append((first, s.info().copy(), s.primal(), s.dual(), s.stats(), s.trace(20)))
@@ -206,3 +206,14 @@ def test_closed_loop_mpc(emu, orc):
         for f in ("iter", "qp_solver_iter", "status"):
             pc.assert_same(a[2][f], b[2][f], f"step {k}: info." + f)
         pc.assert_same(a[3], b[3], f"step {k}: plant state")
+
+
+def test_sqp_block_bfgs(emu, orc):
+    """PMB_HESSIAN_BFGS_BLOCK: ContinuousOCP<..., SPARSE>::hessian_update_impl (continuous_ocp.hpp:2303-2431), the update every
+    reference control test installs.  Plain and damped branches, robot and CSTR."""
+    w = W.mobile_robot(2, seed=7, sqp_max_iter=10, ls_max_iter=10)
+    ra, rb = pc.sqp_case(emu, orc, w, hessian_update=1)
+    assert (rb["info"]["status"] == 0).any()
+    w = W.cstr(1, seed=3, sqp_max_iter=6, ls_max_iter=10)
+    ra, rb = pc.sqp_case(emu, orc, w, hessian_update=1)
+    assert np.isfinite(rb["x"]).all()

@@ -218,7 +218,7 @@ def test_warm_restart_matches_oracle(pmb, orc):
     w = W.mobile_robot(32, sqp_max_iter=3, ls_max_iter=10)
     outs = []
     for api in (pmb, orc):
-        s = api.sqp(w.name, 32); W.configure(s, w); s.solve()
+        s = api.sqp(w.name, 32); W.configure(s, w); s.set_trace(True); s.solve()
         s.set_initial_conditions(w.x0 + 0.01); s.solve()
         outs.append((s.primal(), s.dual(), s.info(), s.trace(3)))
         s.close()

@@ -130,6 +130,11 @@ int pmb_ocp_lagrangian_gradient_hessian(pmb_ocp_t* ocp, int batch, const double*
                                         double* cost, double* lag_grad, double* lag_hess /* N x N */, double* cost_grad,
                                         double* g, double* jac);                                                    /* :2097-2174 */
 
+/* ContinuousOCP<..., SPARSE>::hessian_update_impl (continuous_ocp.hpp:2303-2431): block BFGS on the stored pattern of the
+ * Lagrangian Hessian (per-node (x_k,u_k) blocks, parameter rows/columns).  B[batch*N*N] in/out (entries outside the pattern
+ * are neither read nor written), s,y[batch*N]; branch[batch] (may be NULL): 0 plain, 1 damped. */
+int pmb_ocp_block_bfgs_update(pmb_ocp_t* ocp, int batch, double* B, const double* s, const double* y, int* branch);
+
 /* ---- QPBase<boxADMM<N,M,double,DENSE,LDLT,Lower>>::solve (qp_base.hpp:161-175, box_admm.hpp:81-205) --------------- */
 /* H[batch*N*N], h[batch*N], A[batch*M*N], Alb/Aub[batch*M], xlb/xub[batch*N]; x_guess/y_guess may be NULL (cold start,
  * the 7-argument form).  Outputs: x[batch*N] = primal_solution(), y[batch*(M+N)] = dual_solution() = [y_A ; y_box].

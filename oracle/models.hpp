@@ -67,6 +67,26 @@ struct RobotObstacleModel : RobotModel {
 };
 
 // =====================================================================================================================
+/** reference tests/control/minimal_time_test.cpp:32-63 (ParkingOCP): NX=3 NU=2 NP=1 ND=1, free final time p(0) */
+struct ParkingModel {
+    static constexpr int NX = 3, NU = 2, NP = 1, ND = 1, NG = 0;
+    static constexpr int NPARAM = 1;
+    double unused = 0;
+    void set_params(const double* v) { unused = v[0]; }
+    void get_params(double* v) const { v[0] = unused; }
+    template <class T>
+    void dynamics(const T* x, const T* u, const T* p, const double* d, const T&, T* xdot) const
+    {
+        xdot[0] = p[0] * u[0] * cos(x[2]) * cos(u[1]);
+        xdot[1] = p[0] * u[0] * sin(x[2]) * cos(u[1]);
+        xdot[2] = p[0] * u[0] * sin(u[1]) / d[0];
+    }
+    template <class T> void lagrange(const T*, const T*, const T*, const double*, double, T& L) const { L = T(0.0); }
+    template <class T> void mayer(const T*, const T*, const T* p, const double*, double, T& M) const { M = p[0]; }
+    template <class T> void ineq(const T*, const T*, const T*, const double*, double, T*) const {}
+};
+
+// =====================================================================================================================
 struct CstrModel {
     static constexpr int NX = 4, NU = 2, NP = 0, ND = 0, NG = 0;
     static constexpr int NPARAM = 16 + 4 + 16 + 4 + 2;

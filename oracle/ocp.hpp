@@ -258,9 +258,20 @@ struct Ocp {
         for (int i = 0; i < NU; ++i) grad[VARX + i] += Mv.v.d[NX + i];
         for (int i = 0; i < NP; ++i) grad[VARX + VARU + i] += Mv.v.d[NX + NU + i];
         for (int i = 0; i < ND_; ++i) for (int r = 0; r < ND_; ++r) hes[r + i * ND_] = Mv.d[i].d[r];
-        // NOTE: the reference adds the pp block with bottomLeftCorner on both sides; for NP == 0
-        // (all BASELINE configs) that is empty, so a plain scatter is identical.
-        scatter_hes(H, 0, hes, 1.0, false);
+        // Mayer blocks exactly as the reference books them (1352-1366): xx, uu, xu, ux, xp, px, up, pu are
+        // added; the (p, p) second derivatives are NOT (the reference writes `bottomLeftCorner<NP,NP>() +=
+        // hes.bottomLeftCorner<NP,NP>()`), instead hes(p_i, j), j < NP, lands a second time on H(p_i, column j).
+        {
+            constexpr int NB = NX + NU;
+            auto idx = [&](int a) { return a < NX ? a : (a < NB ? VARX + (a - NX) : VARX + VARU + (a - NB)); };   // node 0
+            for (int cc = 0; cc < ND_; ++cc)
+                for (int r = 0; r < ND_; ++r) {
+                    if (r >= NB && cc >= NB) continue;
+                    H[idx(r) + idx(cc) * N] += hes[r + cc * ND_];
+                }
+            for (int j = 0; j < NP; ++j)
+                for (int i = 0; i < NP; ++i) H[(N - NP + i) + j * N] += hes[(ND_ - NP + i) + j * ND_];
+        }
         cost_out = c;
     }
 

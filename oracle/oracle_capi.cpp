@@ -48,6 +48,7 @@ struct IOcp {
     virtual void cost_gradient_hessian(const double*, const double*, double*, double*, double*) const = 0;
     virtual void lagrangian_gradient(const double*, const double*, const double*, double*, double*, double*, double*, double*) const = 0;
     virtual void lagrangian_gradient_hessian(const double*, const double*, const double*, double*, double*, double*, double*, double*, double*) const = 0;
+    virtual int block_bfgs(double* H, const double* s, const double* y) const = 0;
 };
 
 template <class O>
@@ -75,6 +76,7 @@ struct OcpImpl : IOcp {
     { o.lagrangian_gradient(v, d, l, *c, lg, cg, g, A); }
     void lagrangian_gradient_hessian(const double* v, const double* d, const double* l, double* c, double* lg, double* H, double* cg, double* g, double* A) const override
     { o.lagrangian_gradient_hessian(v, d, l, *c, lg, H, cg, g, A); }
+    int block_bfgs(double* H, const double* s, const double* y) const override { return block_bfgs_update<O>(H, s, y); }
 };
 
 // ---- type-erased SQP (one solver object per instance, like the reference) ---------------------------------------
@@ -150,6 +152,7 @@ const Registry g_registry[] = {
     REG("kite_12x1", KiteModel, 12, 1),          // BASELINE.json config 4 (our model)
     REG("kite_4x2", KiteModel, 4, 2),            // small kite variant for fast parity tests
     REG("robot_obstacle_5x2", RobotObstacleModel, 5, 2),   // NG = 1: generic inequality constraints
+    REG("parking_5x2", ParkingModel, 5, 2),      // NP = 1: minimal_time_test.cpp / dense_sparse_compare.cpp
 };
 const int g_nreg = sizeof(g_registry) / sizeof(g_registry[0]);
 const Registry* find(const char* name)
@@ -352,6 +355,17 @@ int pmb_bfgs_update(int N, int batch, double* B, const double* s, const double* 
     if (N <= 0 || batch < 0 || !B || !s || !y) return PMB_ERR_BAD_ARGUMENT;
     parallel_for(batch, [&](int b) {
         const int br = bfgs_update(B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, N);
+        if (branch) branch[b] = br;
+    });
+    return PMB_OK;
+}
+
+int pmb_ocp_block_bfgs_update(pmb_ocp_t* h, int batch, double* B, const double* s, const double* y, int* branch)
+{
+    if (!h || batch < 0 || !B || !s || !y) return PMB_ERR_BAD_ARGUMENT;
+    const size_t N = h->impl->dims.N;
+    parallel_for(batch, [&](int b) {
+        const int br = h->impl->block_bfgs(B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N);
         if (branch) branch[b] = br;
     });
     return PMB_OK;

@@ -55,7 +55,7 @@ ABI_FUNCTIONS = [
     "qp_default_settings", "sqp_default_settings", "sqp_default_qp_settings", "dm_eval", "cheb_tables",
     "ocp_create", "ocp_destroy", "ocp_dims", "ocp_set_params", "ocp_get_params", "ocp_set_time_limits", "ocp_time_nodes",
     "ocp_cost", "ocp_equalities", "ocp_inequalities", "ocp_equalities_linearised", "ocp_cost_gradient",
-    "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian",
+    "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
@@ -116,6 +116,7 @@ class CApi:
             [c_double_p, c_double_p, C.c_void_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p]
         g("kkt_assemble").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 4 + [C.c_double, c_double_p]
         g("bfgs_update").argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]
+        g("ocp_block_bfgs_update").argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]
         g("sqp_create").restype = C.c_void_p
         g("sqp_create").argtypes = [C.c_char_p, C.c_int, C.c_int]
         g("sqp_destroy").argtypes = [C.c_void_p]
@@ -375,6 +376,15 @@ class Ocp:
                                                                       _p(g), _p(J)), "ocp_lagrangian_gradient_hessian")
         return dict(cost=c, lag_grad=lg, cost_grad=cg, g=g, jac=np.transpose(J, (0, 2, 1)).copy(),
                     hess=np.transpose(H, (0, 2, 1)).copy())
+
+    def block_bfgs_update(self, Hm, s, y):
+        """ContinuousOCP<..., SPARSE>::hessian_update_impl; Hm (B, N, N) row-major view of the Hessian -> (updated H, branch)"""
+        Hm = _f64(Hm); B = Hm.shape[0]; N = self.d["N"]
+        Hc = np.ascontiguousarray(np.transpose(Hm.reshape(B, N, N), (0, 2, 1)))      # column-major per instance
+        branch = np.zeros(B, dtype=np.int32)
+        self.api._chk(self.api._fn("ocp_block_bfgs_update")(self.h, B, _p(Hc), _p(_f64(s).reshape(B, N)), _p(_f64(y).reshape(B, N)), _pi(branch)),
+                      "ocp_block_bfgs_update")
+        return np.transpose(Hc, (0, 2, 1)).copy(), branch
 
 
 class Sqp:

@@ -23,8 +23,7 @@ PMB_DECLARE_PROBLEM(cstr_5x2)
 PMB_DECLARE_PROBLEM(kite_12x1)
 PMB_DECLARE_PROBLEM(kite_4x2)
 PMB_DECLARE_PROBLEM(robot_obstacle_5x2)
-PMB_DECLARE_PROBLEM(dropin_robot_5x3)
-PMB_DECLARE_PROBLEM(dropin_cstr_5x2)
+PMB_DECLARE_PROBLEM(parking_5x2)
 
 namespace pmb {
 namespace {
@@ -41,9 +40,7 @@ const Registry g_builtin[] = {
     PMB_REG("kite_12x1", kite_12x1),                 // BASELINE.json config 4 (our model)
     PMB_REG("kite_4x2", kite_4x2),                   // small kite variant for fast parity tests
     PMB_REG("robot_obstacle_5x2", robot_obstacle_5x2),   // NG = 1: generic inequality constraints
-    // reference-style problem classes (Eigen functors) compiled through include/polympc_compat/, see problems/dropin_*.cu
-    PMB_REG("dropin_robot_5x3", dropin_robot_5x3),
-    PMB_REG("dropin_cstr_5x2", dropin_cstr_5x2),
+    PMB_REG("parking_5x2", parking_5x2),             // NP = 1: reference minimal_time_test.cpp / dense_sparse_compare.cpp
 };
 /** built-in problems followed by the ones user translation units registered (pmb_register_problem); entries are never
  *  removed, names are owned by the registry (std::deque-like stability through unique_ptr) */
@@ -411,6 +408,24 @@ int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double*
     int* dbr = st.out(branch, B);
     if (!st.ok) return PMB_ERR_CUDA;
     if (!rt_launch<BfgsBody>(batch, BfgsBody::smem_bytes(N), st.s, N, dB, ds, dy, dbr)) return PMB_ERR_CUDA;
+    st.back(Bm, (const double*)dB, B * N * N); st.back(branch, (const int*)dbr, B);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+int pmb_ocp_block_bfgs_update(pmb_ocp_t* h, int batch, double* Bm, const double* s, const double* y, int* branch)
+{
+    if (!h || batch < 0 || !Bm || !s || !y) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "block_bfgs_update: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    if (!rt_set_device(h->impl->device)) return PMB_ERR_CUDA;
+    const size_t B = batch, N = h->impl->dims.N;
+    Staging st;
+    double* dB = st.in((const double*)Bm, B * N * N);
+    const double* ds = st.in(s, B * N); const double* dy = st.in(y, B * N);
+    int* dbr = st.out(branch, B);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!h->impl->launch_block_bfgs(batch, dB, ds, dy, dbr, st.s)) return PMB_ERR_CUDA;
     st.back(Bm, (const double*)dB, B * N * N); st.back(branch, (const int*)dbr, B);
     if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
     return PMB_OK;

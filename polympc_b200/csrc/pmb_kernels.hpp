@@ -36,12 +36,12 @@ struct OcpEvalBody {
         else if (MODE == OCP_INEQ) E::inequalities(c, o, var, d, io.g + (size_t)b * O::NUM_INEQ, c.tid());
         else if (MODE == OCP_EQ_LIN)
             E::constraints_linearised(c, o, var, d, io.c + (size_t)b * O::NUM_EQ, io.jac + (size_t)b * O::NUM_EQ * O::N, O::NUM_EQ, false);
-        else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(c, o, var, d, io.grad + (size_t)b * O::N);
+        else if (MODE == OCP_COST_GRAD) cost = E::cost_gradient(c, o, var, d, io.grad + (size_t)b * O::N, nv);
         else if (MODE == OCP_COST_GRAD_HESS)
             cost = E::cost_gradient_hessian(c, o, var, d, nullptr, io.grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N, nv);
         else if (MODE == OCP_LAG_GRAD)
             cost = E::lagrangian_gradient(c, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.grad + (size_t)b * O::N,
-                                          io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N);
+                                          io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N, nv);
         else if (MODE == OCP_LAG_GRAD_HESS)
             cost = E::lagrangian_gradient_hessian(c, o, var, d, lam, io.lag_grad + (size_t)b * O::N, io.hess + (size_t)b * O::N * O::N,
                                                   io.grad + (size_t)b * O::N, io.c + (size_t)b * O::M, io.jac + (size_t)b * O::M * O::N, nv);
@@ -143,6 +143,24 @@ struct BfgsBody {
         double* Bs = reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES;
         double* r = Bs + N;
         const int br = bfgs_update_cta(c, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
+        if (branch && c.tid() == 0) branch[b] = br;
+    }
+};
+
+// ---- block BFGS operator (C ABI pmb_ocp_block_bfgs_update): ContinuousOCP<..., SPARSE>::hessian_update_impl ---------------
+template <class O>
+struct BlockBfgsBody {
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = (Cta::SCRATCH_DOUBLES + 2 * (size_t)O::N) * sizeof(double);
+    static constexpr const char* NAME = "block_bfgs_update";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, double* B, const double* s, const double* y, int* branch)
+    {
+        Cta c(w, reinterpret_cast<double*>(smem));
+        double* v = reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES;
+        double* r = v + O::N;
+        const int br = block_bfgs_update_cta<O>(c, B + (size_t)b * O::N * O::N, s + (size_t)b * O::N, y + (size_t)b * O::N, v, r);
         if (branch && c.tid() == 0) branch[b] = br;
     }
 };

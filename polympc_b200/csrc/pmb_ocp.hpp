@@ -34,7 +34,6 @@ struct Ocp {
     static constexpr int NUM_EQ = VARX, NUM_INEQ = NG * NN, M = NUM_EQ + NUM_INEQ, DUAL = M + N;
     static constexpr int NDIR = NX + NU + NP;
     static_assert(NN <= 32, "one warp per instance: at most 32 collocation nodes");
-    static_assert(NP == 0, "optimised parameters (NP > 0) are not on the GPU path yet");
     using ad1 = Dual<double, NDIR>;
     using ad2 = Dual<ad1, NDIR>;   // the reference's ad2_scalar_t (full nesting)
     using ad2d = Dual<ad1, 1>;     // one Hessian column at a time (OcpEval::cost_gradient_hessian)
@@ -123,16 +122,19 @@ struct OcpEval {
         else c1 = o.ts * o.w[k % P];
     }
 
+    static constexpr int NPA = NP > 0 ? NP : 1;   // array length of the parameter block
     template <class T>
-    PMB_DEV static void load_plain(const double* var, int k, T* x, T* u)
+    PMB_DEV static void load_plain(const double* var, int k, T* x, T* u, T* p)
     {
         for (int i = 0; i < NX; ++i) x[i] = T(var[k * NX + i]);
         for (int i = 0; i < NU; ++i) u[i] = T(var[VARX + k * NU + i]);
+        for (int i = 0; i < NP; ++i) p[i] = T(var[VARX + VARU + i]);
     }
-    PMB_DEV static void seed1(const double* var, int k, ad1* x, ad1* u)
+    PMB_DEV static void seed1(const double* var, int k, ad1* x, ad1* u, ad1* p)
     {
         for (int i = 0; i < NX; ++i) { x[i] = ad1(var[k * NX + i]); x[i].d[i] = 1.0; }
         for (int i = 0; i < NU; ++i) { u[i] = ad1(var[VARX + k * NU + i]); u[i].d[NX + i] = 1.0; }
+        for (int i = 0; i < NP; ++i) { p[i] = ad1(var[VARX + VARU + i]); p[i].d[NX + NU + i] = 1.0; }
     }
     // ---- a3: cost (continuous_ocp.hpp:1180-1207) -----------------------------------------------------------------
     PMB_DEV static double cost(Cta& c, const O& o, const double* var, const double* d)
@@ -147,8 +149,8 @@ struct OcpEval {
         const int k = c.lane();
         double ci = 0.0, mv = 0.0;
         if (k < NN) {
-            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0};
-            load_plain<double>(var, k, x, u);
+            double x[NX], u[NU > 0 ? NU : 1], p[NPA] = {0.0};
+            load_plain<double>(var, k, x, u, p);
             o.model.template lagrange<double>(x, u, p, d, o.time_nodes[k], ci);
             if (k == 0) o.model.template mayer<double>(x, u, p, d, o.time_nodes[0], mv);
         }
@@ -167,8 +169,8 @@ struct OcpEval {
     PMB_DEV static void equalities(Cta& c, const O& o, const double* var, const double* d, double* ce, int k)
     {
         if (k < NN) {
-            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, f[NX], DXk[NX];
-            load_plain<double>(var, k, x, u);
+            double x[NX], u[NU > 0 ? NU : 1], p[NPA] = {0.0}, f[NX], DXk[NX];
+            load_plain<double>(var, k, x, u, p);
             for (int i = 0; i < NX; ++i) f[i] = 0.0;
             const double tk = o.time_nodes[k];
             o.model.template dynamics<double>(x, u, p, d, tk, f);
@@ -182,8 +184,8 @@ struct OcpEval {
     {
         if (NG == 0) return;
         if (k < NN) {
-            double x[NX], u[NU > 0 ? NU : 1], p[1] = {0.0}, gr[NG > 0 ? NG : 1];
-            load_plain<double>(var, k, x, u);
+            double x[NX], u[NU > 0 ? NU : 1], p[NPA] = {0.0}, gr[NG > 0 ? NG : 1];
+            load_plain<double>(var, k, x, u, p);
             for (int i = 0; i < NG; ++i) gr[i] = 0.0;
             o.model.template ineq<double>(x, u, p, d, o.time_nodes[k], gr);
             for (int i = 0; i < NG; ++i) g[k * NG + i] = gr[i];
@@ -222,8 +224,8 @@ struct OcpEval {
                             A[(VARX - NX + r) + (VARX - W + jp * NX + q) * ldA] = -(d0 * (r == q ? 1.0 : 0.0));
                 }
             }
-            ad1 x[NX], u[NU > 0 ? NU : 1], p[1], y[NX];
-            seed1(var, k, x, u);
+            ad1 x[NX], u[NU > 0 ? NU : 1], p[NPA], y[NX];
+            seed1(var, k, x, u, p);
             for (int i = 0; i < NX; ++i) y[i] = ad1(0.0);
             const ad1 tk = ad1(o.time_nodes[k]);
             o.model.template dynamics<ad1>(x, u, p, d, tk, y);
@@ -237,6 +239,7 @@ struct OcpEval {
             for (int i = 0; i < NX; ++i) {
                 for (int j = 0; j < NX; ++j) A[(k * NX + i) + (k * NX + j) * ldA] -= o.ts * y[i].d[j];
                 for (int j = 0; j < NU; ++j) A[(k * NX + i) + (VARX + k * NU + j) * ldA] -= o.ts * y[i].d[NX + j];
+                for (int j = 0; j < NP; ++j) A[(k * NX + i) + (VARX + VARU + j) * ldA] -= o.ts * y[i].d[NX + NU + j];   // 870-872
             }
             if (NG > 0 && with_ineq) {
                 ad1 gv[NG > 0 ? NG : 1];
@@ -247,6 +250,7 @@ struct OcpEval {
                     const int row = NUM_EQ + k * NG + i;
                     for (int j = 0; j < NX; ++j) A[row + (k * NX + j) * ldA] = gv[i].d[j];
                     for (int j = 0; j < NU; ++j) A[row + (VARX + k * NU + j) * ldA] = gv[i].d[NX + j];
+                    for (int j = 0; j < NP; ++j) A[row + (VARX + VARU + j) * ldA] = gv[i].d[NX + NU + j];
                 }
             }
         }
@@ -254,34 +258,58 @@ struct OcpEval {
     }
 
     // ---- a7: cost gradient (continuous_ocp.hpp:1209-1249) ----------------------------------------------------------
-    PMB_DEV static double cost_gradient(Cta& c, const O& o, const double* var, const double* d, double* grad)
+    /** shared scratch (doubles) of the gradient / Hessian evaluators: node values for the quadrature [NN + 1], and for
+     *  NP > 0 the per-node parameter pieces that the reference accumulates ACROSS nodes in loop order: parameter gradient
+     *  [(NN + 1) NP] and the (p, p) Hessian blocks of the cost and of the constraint curvature [2 NN NP^2]. */
+    static constexpr int NV_GP = NN + 1, NV_PPC = NV_GP + (NN + 1) * NP, NV_PPL = NV_PPC + NN * NP * NP;
+    static constexpr int NV_DOUBLES = NV_PPL + NN * NP * NP;
+
+    /** grad[p_j] = sum over (segment, node) in loop order of (ts w_k) dL/dp_j, then + dMayer/dp_j (1228-1246); raw[k*NP + j]
+     *  holds dL/dp_j of node k, raw[NN*NP + j] the Mayer derivative.  Thread j < NP does the chain. */
+    PMB_DEV static void param_gradient_sum(Cta& c, const O& o, const double* raw, double* grad)
+    {
+        if (NP == 0) return;
+        const int j = c.tid();
+        if (j < NP) {
+            double acc = 0.0;
+            for (int s = 0; s < S; ++s)
+                for (int k = 0; k <= P; ++k) acc += (o.ts * o.w[k]) * raw[(s * P + k) * NP + j];
+            acc += raw[NN * NP + j];
+            grad[VARX + VARU + j] = acc;
+        }
+    }
+
+    PMB_DEV static double cost_gradient(Cta& c, const O& o, const double* var, const double* d, double* grad, double* nv)
     {
         const int k = c.tid();
         double lv = 0.0, mv = 0.0;
         if (k < NN) {
-            ad1 x[NX], u[NU > 0 ? NU : 1], p[1], L;
-            seed1(var, k, x, u);
+            ad1 x[NX], u[NU > 0 ? NU : 1], p[NPA], L;
+            seed1(var, k, x, u, p);
             o.model.template lagrange<ad1>(x, u, p, d, o.time_nodes[k], L);
             lv = L.v;
             double c1, c2; bool two;
             node_coeffs(o, k, c1, c2, two);
             double g[NDIR];
-            for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.d[i]; if (two) g[i] += c2 * L.d[i]; }
+            for (int i = 0; i < NX + NU; ++i) { g[i] = 0.0; g[i] += c1 * L.d[i]; if (two) g[i] += c2 * L.d[i]; }
+            for (int j = 0; j < NP; ++j) nv[NV_GP + k * NP + j] = L.d[NX + NU + j];
             if (k == 0) {
                 L = ad1(0.0);
                 o.model.template mayer<ad1>(x, u, p, d, o.time_nodes[0], L);
                 mv = L.v;
-                for (int i = 0; i < NDIR; ++i) g[i] += L.d[i];
+                for (int i = 0; i < NX + NU; ++i) g[i] += L.d[i];
+                for (int j = 0; j < NP; ++j) nv[NV_GP + NN * NP + j] = L.d[NX + NU + j];
             }
-            for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
+            for (int i = 0; i < NX + NU; ++i) grad[var_index<O>(k, i)] = g[i];
         }
+        if (NP > 0) { c.sync(); param_gradient_sum(c, o, nv + NV_GP, grad); }
         return quadrature_sum(c, o, lv, mv);
     }
 
     // ---- a8 / a10: cost gradient + Hessian, optionally plus the constraint curvature of the Lagrangian ---------------
     /** seed node k for ONE outer direction j: value part = first-order dual seeded in all NDIR directions, the single
      *  outer partial = derivative along direction j (continuous_ocp.hpp:690-735 restricted to one Hessian column). */
-    PMB_DEV static void seed2_dir(const double* var, int k, int j, ad2d* x, ad2d* u)
+    PMB_DEV static void seed2_dir(const double* var, int k, int j, ad2d* x, ad2d* u, ad2d* p)
     {
         for (int i = 0; i < NX; ++i) {
             x[i].v = ad1(var[k * NX + i]); x[i].v.d[i] = 1.0;
@@ -291,6 +319,10 @@ struct OcpEval {
             u[i].v = ad1(var[VARX + k * NU + i]); u[i].v.d[NX + i] = 1.0;
             u[i].d[0] = ad1(0.0); if (j == NX + i) u[i].d[0].v = 1.0;
         }
+        for (int i = 0; i < NP; ++i) {
+            p[i].v = ad1(var[VARX + VARU + i]); p[i].v.d[NX + NU + i] = 1.0;
+            p[i].d[0] = ad1(0.0); if (j == NX + NU + i) p[i].d[0].v = 1.0;
+        }
     }
 
     /** cost_gradient_hessian (1253-1367); with lam != nullptr also adds, per node,
@@ -299,11 +331,18 @@ struct OcpEval {
      *  Mapping: the reference evaluates a nested dual with NDIR outer partials per node.  Every outer partial of a
      *  nested dual is computed independently of the others, so the CTA instead spreads the NN*NDIR (node, Hessian
      *  column) pairs over all its threads and evaluates the functors on Dual<ad1,1>: identical arithmetic per entry,
-     *  (NX+NU)x less live state per thread, and every thread busy even when NN < 32. */
+     *  (NX+NU)x less live state per thread, and every thread busy even when NN < 32.
+     *
+     *  NP > 0: entries of H that couple node k with the parameters have a single contributor (node k) and are stored
+     *  directly; the parameter gradient and the (p, p) block are sums over all nodes in the reference's loop order — the
+     *  per-node pieces go to shared scratch and NP (NP^2) threads run the sequential chains afterwards.  The Mayer term
+     *  reproduces the reference's block bookkeeping (1352-1366): its (p, p) second derivatives are
+     *  NOT added to the (p, p) block; instead hes(p_i, j), j < NP, is added a second time to H(p_i, column j). */
     PMB_DEV static double cost_gradient_hessian(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
                                                 double* grad, double* H, double* nv /* shared scratch, NV_DOUBLES */)
     {
         const int tid = cta.tid(), nt = cta.nthreads();
+        constexpr int NB = NX + NU;
         for (int i = tid; i < N * N; i += nt) H[i] = 0.0;
         cta.sync();
         constexpr int ITEMS = NN * NDIR;
@@ -311,18 +350,20 @@ struct OcpEval {
         for (int item = tid; item < ITEMS; item += nt) {
             {   // one (node k, Hessian column c) work item
                 const int k = item / NDIR, c = item - k * NDIR;
-                ad2d x[NX], u[NU > 0 ? NU : 1], p[1];
+                ad2d x[NX], u[NU > 0 ? NU : 1], p[NPA];
                 double Hc[NDIR];   // column c of the node's (NDIR x NDIR) block
                 double g[NDIR];
-                seed2_dir(var, k, c, x, u);
+                seed2_dir(var, k, c, x, u, p);
                 {
                     ad2d L;
                     o.model.template lagrange<ad2d>(x, u, p, d, o.time_nodes[k], L);
                     if (c == 0) nv[k] = L.v.v;
                     double c1, c2; bool two;
                     node_coeffs(o, k, c1, c2, two);
-                    for (int i = 0; i < NDIR; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
+                    for (int i = 0; i < NB; ++i) { g[i] = 0.0; g[i] += c1 * L.v.d[i]; if (two) g[i] += c2 * L.v.d[i]; }
+                    if (c == 0) for (int j = 0; j < NP; ++j) nv[NV_GP + k * NP + j] = L.v.d[NB + j];
                     for (int r = 0; r < NDIR; ++r) {
+                        if (r >= NB && c >= NB) { nv[NV_PPC + (k * NP + (c - NB)) * NP + (r - NB)] = L.d[0].d[r]; Hc[r] = 0.0; continue; }
                         double h = 0.0;
                         h += c1 * L.d[0].d[r];
                         if (two) h += c2 * L.d[0].d[r];
@@ -333,8 +374,13 @@ struct OcpEval {
                     ad2d Mv(0.0);
                     o.model.template mayer<ad2d>(x, u, p, d, o.time_nodes[0], Mv);
                     if (c == 0) nv[NN] = Mv.v.v;
-                    for (int i = 0; i < NDIR; ++i) g[i] += Mv.v.d[i];
-                    for (int r = 0; r < NDIR; ++r) Hc[r] += Mv.d[0].d[r];
+                    for (int i = 0; i < NB; ++i) g[i] += Mv.v.d[i];
+                    if (c == 0) for (int j = 0; j < NP; ++j) nv[NV_GP + NN * NP + j] = Mv.v.d[NB + j];
+                    for (int r = 0; r < NDIR; ++r) {
+                        if (r >= NB && c >= NB) continue;                       // no (p, p) contribution (quirk)
+                        Hc[r] += Mv.d[0].d[r];
+                        if (r >= NB && c < NP) Hc[r] += Mv.d[0].d[r];           // bottomLeftCorner<NP,NP> added on top of dxdp (quirk)
+                    }
                 }
                 if (lam != nullptr) {
                     double hes[NDIR];
@@ -356,19 +402,35 @@ struct OcpEval {
                             for (int r = 0; r < NDIR; ++r) hes[r] += coeff * gv[n].d[0].d[r];
                         }
                     }
-                    for (int i = 0; i < NDIR; ++i) Hc[i] += hes[i];
+                    for (int i = 0; i < NDIR; ++i) {
+                        if (i >= NB && c >= NB) nv[NV_PPL + (k * NP + (c - NB)) * NP + (i - NB)] = hes[i];
+                        else Hc[i] += hes[i];
+                    }
                 }
-                if (c == 0) for (int i = 0; i < NDIR; ++i) grad[var_index<O>(k, i)] = g[i];
-                for (int r = 0; r < NDIR; ++r) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hc[r];
+                if (c == 0) for (int i = 0; i < NB; ++i) grad[var_index<O>(k, i)] = g[i];
+                for (int r = 0; r < NDIR; ++r)
+                    if (!(r >= NB && c >= NB)) H[var_index<O>(k, r) + var_index<O>(k, c) * N] = Hc[r];
             }
         }
         cta.sync();
+        if (NP > 0) {
+            param_gradient_sum(cta, o, nv + NV_GP, grad);
+            // (p, p) block: cost part in loop order (junction nodes twice), then the constraint curvature node by node (2141-2160)
+            for (int e = tid; e < NP * NP; e += nt) {
+                const int cp = e / NP, rp = e - cp * NP;
+                double acc = 0.0;
+                for (int s = 0; s < S; ++s)
+                    for (int k = 0; k <= P; ++k) acc += (o.ts * o.w[k]) * nv[NV_PPC + ((s * P + k) * NP + cp) * NP + rp];
+                if (lam != nullptr) for (int k = 0; k < NN; ++k) acc += nv[NV_PPL + (k * NP + cp) * NP + rp];
+                H[(VARX + VARU + rp) + (size_t)(VARX + VARU + cp) * N] = acc;
+            }
+            cta.sync();
+        }
         // node values -> thread k (quadrature_sum expects thread k <-> node k)
         const double lv = tid < NN ? nv[tid] : 0.0;
         const double mv = tid == 0 ? nv[NN] : 0.0;
         return quadrature_sum(cta, o, lv, mv);
     }
-    static constexpr int NV_DOUBLES = NN + 1;
 
     /** lag_grad = A^T lam_head + cost_grad + lam_box (continuous_ocp.hpp:1970-1974, 2112-2114); A is M x N, ld M */
     PMB_DEV static void lag_grad_from(Cta& c, const double* A, const double* lam, const double* cost_grad, double* lag_grad)
@@ -387,9 +449,9 @@ struct OcpEval {
 
     /** a9: lagrangian_gradient (1957-1975) */
     PMB_DEV static double lagrangian_gradient(Cta& cta, const O& o, const double* var, const double* d, const double* lam,
-                                              double* lag_grad, double* cost_grad, double* g, double* A)
+                                              double* lag_grad, double* cost_grad, double* g, double* A, double* nv)
     {
-        const double c = cost_gradient(cta, o, var, d, cost_grad);
+        const double c = cost_gradient(cta, o, var, d, cost_grad, nv);
         constraints_linearised(cta, o, var, d, g, A, M, true);
         lag_grad_from(cta, A, lam, cost_grad, lag_grad);
         return c;

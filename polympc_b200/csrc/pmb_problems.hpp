@@ -69,6 +69,28 @@ struct MobileRobotObstacle : MobileRobot {
     }
 };
 
+/** free-final-time valet parking: the reference's ParkingOCP (tests/control/minimal_time_test.cpp:32-63,
+ *  tests/control/dense_sparse_compare.cpp:22-55): mobile-robot kinematics scaled by the optimised parameter p(0) = final time
+ *  on the normalised horizon [0, 1]; cost = Mayer term p(0).  NP = 1 exercises the parameter columns / blocks
+ *  (continuous_ocp.hpp:860-872, 1314-1366, 2161-2172). */
+struct Parking {
+    static constexpr int NX = 3, NU = 2, NP = 1, ND = 1, NG = 0, NPARAM = 1;
+    double unused;
+    PMB_HD void defaults() { unused = 0; }
+    PMB_HD void set_params(const double* v) { unused = v[0]; }
+    PMB_HD void get_params(double* v) const { v[0] = unused; }
+    template <class T>
+    PMB_HD void dynamics(const T* x, const T* u, const T* p, const double* d, const T&, T* xdot) const
+    {
+        xdot[0] = p[0] * u[0] * cos(x[2]) * cos(u[1]);
+        xdot[1] = p[0] * u[0] * sin(x[2]) * cos(u[1]);
+        xdot[2] = p[0] * u[0] * sin(u[1]) / d[0];
+    }
+    template <class T> PMB_HD void lagrange(const T*, const T*, const T*, const double*, double, T& L) const { L = T(0.0); }
+    template <class T> PMB_HD void mayer(const T*, const T*, const T* p, const double*, double, T& M) const { M = p[0]; }
+    template <class T> PMB_HD void ineq(const T*, const T*, const T*, const double*, double, T*) const {}
+};
+
 struct Cstr {
     static constexpr int NX = 4, NU = 2, NP = 0, ND = 0, NG = 0, NPARAM = 16 + 4 + 16 + 4 + 2;
     double Q[16], R[4], P[16], xs[4], us[2];  // column-major dense, cstr_control_test.cpp:40-50

@@ -19,6 +19,7 @@ struct IProblem {
     virtual void set_time_limits(double, double) = 0;
     virtual void time_nodes(double*) const = 0;
     virtual bool launch_eval(int mode, int batch, const OcpIo& io, stream_t s) const = 0;
+    virtual bool launch_block_bfgs(int batch, double* B, const double* sv, const double* y, int* branch, stream_t s) const = 0;
     /** placement of the LDL^T factor (shared memory, or a per-CTA global scratch slot), shared-memory bytes and resident CTAs
      *  of the fused SQP kernel */
     virtual bool factor_in_smem() const = 0;
@@ -58,6 +59,8 @@ struct ProblemImpl : IProblem {
         }
         return false;
     }
+    bool launch_block_bfgs(int batch, double* B, const double* sv, const double* y, int* branch, stream_t s) const override
+    { return rt_launch<BlockBfgsBody<O>>(batch, BlockBfgsBody<O>::SMEM, s, B, sv, y, branch); }
     using Solve = SqpSolveBody<O>;
     bool factor_in_smem() const override { return Solve::IN_SMEM; }
     size_t solve_smem_bytes() const override { return Solve::smem_bytes(); }

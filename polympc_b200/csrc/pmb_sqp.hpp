@@ -240,7 +240,7 @@ struct SqpDev {
             double* yv = lg + N;           // N
             double* Bs = yv + N;           // N
             double* r = Bs + N;            // N
-            cost_x = E::lagrangian_gradient(c, o, s.x(), s.d(), s.lam(), lg, s.h(), s.al(), s.A());
+            cost_x = E::lagrangian_gradient(c, o, s.x(), s.d(), s.lam(), lg, s.h(), s.al(), s.A(), r + N);
             for (int i = tid; i < N; i += nt) yv[i] = lg[i] - s.lag_grad()[i];
             c.sync();
             const int br = s.ws.opt_block_bfgs ? block_bfgs_update_cta<O>(c, s.H(), s.step_prev(), yv, Bs, r)

@@ -27,6 +27,13 @@ class Workload:
     ls_max_iter: int = 100
     g_lb: np.ndarray | None = None       # (NG,) bounds of the generic inequality constraints, same at every node
     g_ub: np.ndarray | None = None
+    p_lb: np.ndarray | None = None       # (NP,) bounds / guess of the optimised parameters (MPC::parameters_bounds, p_guess)
+    p_ub: np.ndarray | None = None
+    p_guess: np.ndarray | None = None
+    xf_lb: np.ndarray | None = None      # (NX,) bounds of the FINAL state (MPC::final_state_bounds: node 0 of the X block)
+    xf_ub: np.ndarray | None = None
+    exact_hessian: bool = False          # SQPBase overrides of the reference's minimal_time_test.cpp:90-143
+    gershgorin: bool = False
     meta: dict = field(default_factory=dict)
 
     @property
@@ -77,7 +84,20 @@ def kite(batch: int, seed: int = 20260117 + 4, grid: str = "12x1", sqp_max_iter:
                     meta={"x0": "nominal +- 5 %", "seed": seed})
 
 
-WORKLOADS = {"mobile_robot": mobile_robot, "cstr": cstr, "kite": kite, "robot_obstacle": robot_obstacle}
+def parking(batch: int, seed: int = 20260117 + 7, sqp_max_iter: int = 20, ls_max_iter: int = 10) -> Workload:
+    """free-final-time valet parking of the reference's tests/control/minimal_time_test.cpp:146-188 (NP = 1): drive from x0 into a
+    +-0.05 box around the origin in minimal time; horizon normalised to [0, 1], the final time is the optimised parameter.
+    Instance 0 is the reference's own x0 = (1.5, 0.5, 0.5); the others are drawn around it."""
+    rng = np.random.default_rng(seed)
+    x0 = np.array([1.5, 0.5, 0.5]) + rng.uniform(-1, 1, (batch, 3)) * np.array([0.3, 0.3, 0.2])
+    x0[0] = [1.5, 0.5, 0.5]
+    return Workload("parking_5x2", 0.0, 1.0, np.array([1.0]), np.array([-1.5, -0.75]), np.array([1.5, 0.75]), x0,
+                    sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter, p_lb=np.array([0.0]), p_ub=np.array([10.0]), p_guess=np.array([0.5]),
+                    xf_lb=np.full(3, -0.05), xf_ub=np.full(3, 0.05), exact_hessian=True, gershgorin=True,
+                    meta={"x0": "(1.5,0.5,0.5) + U(+-(0.3,0.3,0.2))", "x_guess": "x0 at every node (minimal_time_test.cpp:166)", "seed": seed})
+
+
+WORKLOADS = {"mobile_robot": mobile_robot, "cstr": cstr, "kite": kite, "robot_obstacle": robot_obstacle, "parking": parking}
 
 
 def bounds_x(dims: dict, w: Workload):
@@ -87,6 +107,12 @@ def bounds_x(dims: dict, w: Workload):
     ubx = np.full(N, np.inf)
     lbx[NX * NN:NX * NN + NU * NN] = np.tile(w.u_lb, NN)
     ubx[NX * NN:NX * NN + NU * NN] = np.tile(w.u_ub, NN)
+    if dims["NP"] > 0 and w.p_lb is not None:
+        lbx[NX * NN + NU * NN:] = w.p_lb
+        ubx[NX * NN + NU * NN:] = w.p_ub
+    if w.xf_lb is not None:                                  # MPC::final_state_bounds (mpc_wrapper.hpp): node 0 = final time
+        lbx[:NX] = w.xf_lb
+        ubx[:NX] = w.xf_ub
     return lbx, ubx
 
 
@@ -113,7 +139,16 @@ def configure(solver, w: Workload, lo: int = 0, hi: int | None = None) -> None:
         guess[:d["NX"] * d["NN"]] = np.tile(w.x_guess, d["NN"])
     if w.u_guess is not None:
         guess[d["NX"] * d["NN"]:d["NX"] * d["NN"] + d["NU"] * d["NN"]] = np.tile(w.u_guess, d["NN"])
-    solver.set_primal(guess)
+    if w.exact_hessian or w.gershgorin:
+        solver.set_hessian_options(w.exact_hessian, w.gershgorin)
+    if w.name.startswith("parking"):
+        # minimal_time_test.cpp:165-166: p_guess(0.5), x_guess(x0.replicate(11, 1)) — one guess per instance
+        g = np.tile(guess, (hi - lo, 1))
+        g[:, :d["NX"] * d["NN"]] = np.tile(w.x0[lo:hi], (1, d["NN"]))
+        g[:, d["NX"] * d["NN"] + d["NU"] * d["NN"]:] = w.p_guess
+        solver.set_primal(g)
+    else:
+        solver.set_primal(guess)
     solver.set_dual(np.zeros(d["DUAL"]))
     solver.set_initial_conditions(w.x0[lo:hi])
 

@@ -16,6 +16,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+_plugins = {}
+
+
+def _load_dropin_plugin(kind):
+    """tests/dropin: reference-style problem classes built as a run-time plug-in (a user translation unit) that registers
+    `dropin_robot_5x3` / `dropin_cstr_5x2` with the already loaded engine library when it is dlopen'ed"""
+    if kind in _plugins:
+        return
+    d = os.path.join(ROOT, "tests", "dropin")
+    lib = os.path.join(d, "_build", f"libdropin_{kind}.so")
+    if kind == "emu" or not os.path.exists(lib):
+        subprocess.run(["make", "-C", d, kind], check=True, stdout=subprocess.DEVNULL)
+    _plugins[kind] = ctypes.CDLL(lib, mode=ctypes.RTLD_GLOBAL)
+
+
 @pytest.fixture(scope="session")
 def orc():
     """CPU oracle (test infrastructure), prefix orc_."""
@@ -31,14 +46,19 @@ def emu():
     lib = os.path.join(d, "_build", "libpmb_emu.so")
     if not os.path.exists(lib):
         subprocess.run(["make", "-C", d, f"-j{os.cpu_count() or 4}"], check=True, stdout=subprocess.DEVNULL)
-    return CApi(ctypes.CDLL(lib), "emu_")
+    api = CApi(ctypes.CDLL(lib, mode=ctypes.RTLD_GLOBAL), "emu_")
+    _load_dropin_plugin("emu")
+    return api
 
 
 @pytest.fixture(scope="session")
 def pmb():
     """The product: libpolympc_b200.so (sm_100a).  Loading never falls back to anything else."""
     import polympc_b200
-    return polympc_b200.load()
+    api = polympc_b200.load()
+    if api.device_count() > 0:
+        _load_dropin_plugin("gpu")
+    return api
 
 
 @pytest.fixture(scope="session")

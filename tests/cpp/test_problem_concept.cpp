@@ -10,7 +10,7 @@
 //   2. a single-instance SQPBase solve against instance 0 of a batched solve of the same registered class
 //      (polympc::b200::BatchedMPC with pmb::compat::problem_name<>()), and against the built-in twin.
 #define DROPIN_ROBOT_SEGMENTS 2
-#include "../../examples/dropin/robot_ocp.hpp"
+#include "../dropin/robot_ocp.hpp"
 #include "solvers/sqp_base.hpp"
 #include "control/mpc_wrapper.hpp"
 #undef inline                      // the functor annotation is only wanted for the problem class above

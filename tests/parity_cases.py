@@ -14,6 +14,7 @@ PROBLEM_SETUP = {
     "kite_4x2": dict(t=(0.0, 0.5), d=4.0),
     "kite_12x1": dict(t=(0.0, 0.5), d=4.0),
     "robot_obstacle_5x2": dict(t=(0.0, 2.0), d=2.0),
+    "parking_5x2": dict(t=(0.0, 1.0), d=1.0),
 }
 
 
@@ -24,8 +25,10 @@ ORACLE_TWIN = {"dropin_robot_5x3": "mobile_robot_5x3", "dropin_cstr_5x2": "cstr_
 
 def sample_var(name, dims, B, rng):
     N, NX, NU, NN = dims["N"], dims["NX"], dims["NU"], dims["NN"]
-    if name.startswith("mobile_robot") or name.startswith("robot_obstacle"):
+    if name.startswith("mobile_robot") or name.startswith("robot_obstacle") or name.startswith("parking"):
         var = rng.uniform(-1.0, 1.0, (B, N))
+        if name.startswith("parking"):
+            var[:, -1] = rng.uniform(0.5, 3.0, B)          # the optimised final time
     elif name.startswith("cstr"):
         x = np.array([2.0, 1.0, 110.0, 108.0]) + rng.uniform(-1, 1, (B, NN, NX)) * np.array([0.5, 0.3, 5.0, 5.0])
         u = np.array([14.0, -1100.0]) + rng.uniform(-1, 1, (B, NN, NU)) * np.array([5.0, 500.0])
@@ -136,6 +139,25 @@ def bfgs_case(api, orc, N, B=4, seed=0):
     Bb, brb = orc.bfgs_update(Bm, s, y)
     assert_same(bra, brb, "bfgs.branch")
     assert_same(Ba, Bb, "bfgs.B")
+    return brb
+
+
+def block_bfgs_case(api, orc, name, B=3, seed=0):
+    """ContinuousOCP<..., SPARSE>::hessian_update_impl as an operator: H = exact Lagrangian Hessian of a random point (so it has
+    the block pattern), random s; y chosen to hit the plain and the damped branch"""
+    twin = ORACLE_TWIN.get(name, name)
+    r = ocp_case(api, orc, name, B=B, seed=seed)
+    oa, ob = api.ocp(name), orc.ocp(twin)
+    N = oa.d["N"]
+    rng = np.random.default_rng(seed + 100)
+    H = r["hess"] + 2.0 * np.eye(N)
+    s = rng.standard_normal((B, N)); y = rng.standard_normal((B, N))
+    y[0] = np.einsum("ij,j->i", H[0], s[0])              # s'y = s'Hs: plain
+    y[1] = -np.abs(y[1]) * np.sign(s[1])                 # s'y < 0: damped
+    Ha, bra = oa.block_bfgs_update(H, s, y)
+    Hb, brb = ob.block_bfgs_update(H, s, y)
+    assert_same(bra, brb, "block_bfgs.branch")
+    assert_same(Ha, Hb, "block_bfgs.H")
     return brb
 
 

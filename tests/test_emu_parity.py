@@ -217,3 +217,24 @@ def test_sqp_block_bfgs(emu, orc):
     w = W.cstr(1, seed=3, sqp_max_iter=6, ls_max_iter=10)
     ra, rb = pc.sqp_case(emu, orc, w, hessian_update=1)
     assert np.isfinite(rb["x"]).all()
+
+
+@pytest.mark.parametrize("name", ["mobile_robot_5x2", "cstr_5x2"])
+def test_block_bfgs_operator(emu, orc, name):
+    br = pc.block_bfgs_case(emu, orc, name, B=3, seed=2)
+    assert br[0] == 0 and br[1] == 1
+
+
+def test_ocp_operators_with_optimised_parameter(emu, orc):
+    """NP = 1 (reference ParkingOCP): parameter columns of the Jacobian, parameter gradient and the (., p) / (p, p) Hessian
+    blocks accumulated over the nodes in the reference's loop order (continuous_ocp.hpp:860-872, 1314-1366, 2161-2172)"""
+    pc.ocp_case(emu, orc, "parking_5x2", B=2, seed=4)
+
+
+def test_sqp_minimal_time_parking(emu, orc):
+    """the reference's tests/control/minimal_time_test.cpp:146-188 setup (free final time, exact Hessian at every iteration,
+    Gershgorin regularisation, final-state box): SOLVED in fewer than max_iter iterations, like the reference asserts"""
+    w = W.parking(1)
+    ra, rb = pc.sqp_case(emu, orc, w)
+    assert rb["info"]["status"][0] == 0 and rb["info"]["iter"][0] < w.sqp_max_iter
+    assert 0.0 < rb["x"][0, -1] < 10.0

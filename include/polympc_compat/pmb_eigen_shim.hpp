@@ -118,6 +118,13 @@ struct DenseBase {
         for (int i = 0; i < Size; ++i) r.m[i] = coeff(i) * o.coeff(i);
         return r;
     }
+    PMB_EHD Plain cwiseAbs() const
+    { using std::fabs; Plain r; for (int i = 0; i < Size; ++i) r.m[i] = coeff(i) < Scalar(0.0) ? -coeff(i) : coeff(i); return r; }
+    /** column j / row i as a plain copy (read access: `H.col(i).cwiseAbs().sum()`) */
+    PMB_EHD Matrix<typename std::remove_const<Scalar>::type, Rows, 1> col(int j) const
+    { Matrix<typename std::remove_const<Scalar>::type, Rows, 1> r; for (int i = 0; i < Rows; ++i) r.m[i] = coeff(i, j); return r; }
+    PMB_EHD Matrix<typename std::remove_const<Scalar>::type, 1, Cols> row(int i) const
+    { Matrix<typename std::remove_const<Scalar>::type, 1, Cols> r; for (int j = 0; j < Cols; ++j) r.m[j] = coeff(i, j); return r; }
     /** Eigen's isApprox (Eigen/src/Core/Fuzzy.h): ||a - b||^2 <= prec^2 * min(||a||^2, ||b||^2) */
     template <class O> bool isApprox(const DenseBase<O>& o, double prec = 1e-12) const
     {
@@ -180,6 +187,8 @@ struct Matrix : DenseBase<Matrix<T, R, C>> {
     PMB_EHD T& operator()(int i) { return m[i]; }
     PMB_EHD T& operator[](int i) { return m[i]; }
     PMB_EHD T& operator()(int i, int j) { return m[i + j * R]; }
+    PMB_EHD T& coeffRef(int i, int j) { return m[i + j * R]; }
+    PMB_EHD T& coeffRef(int i) { return m[i]; }
     PMB_EHD T& x() { return m[0]; }
     PMB_EHD T& y() { return m[1]; }
     PMB_EHD T& z() { return m[2]; }
@@ -246,6 +255,7 @@ struct Ref<Matrix<T, R, C>> : DenseBase<Ref<Matrix<T, R, C>>> {
     PMB_EHD T& operator()(int i) { return p[i]; }
     PMB_EHD T& operator[](int i) { return p[i]; }
     PMB_EHD T& operator()(int i, int j) { return p[i + j * R]; }
+    PMB_EHD T& coeffRef(int i, int j) { return p[i + j * R]; }
     template <class O> PMB_EHD Ref& operator=(const DenseBase<O>& o) { for (int i = 0; i < R * C; ++i) p[i] = T(o.derived().data()[i]); return *this; }
     PMB_EHD Ref& operator=(const Ref& o) { for (int i = 0; i < R * C; ++i) p[i] = o.p[i]; return *this; }
     PMB_EHD Ref(const Ref& o) : p(o.p) {}

@@ -23,18 +23,29 @@
 // `inline` mean `__host__ __device__ inline` for the code that FOLLOWS this header in an nvcc translation unit (the
 // reference's functors are all declared `inline` / EIGEN_STRONG_INLINE).  Define POLYMPC_B200_NO_INLINE_HD to opt out.
 //
-// What is NOT honoured (documented deviation): CRTP overrides of SQPBase hooks in a Derived solver
-// (hessian_update_impl, step_size_selection_impl ...) are host code the fused kernel cannot call; the engine always runs
-// the reference's *default* implementations (dense damped BFGS, l1 merit line search).  MATRIXFMT is accepted and ignored
-// (the engine is dense).
+// CRTP hooks of SQPBase (sqp_base.hpp:198-350).  A fused device loop cannot call host code, so solve() finds out what a
+// Derived solver's overrides DO by running each of them once on the host against a recording problem object ("hook probe"),
+// and maps the result onto the engine's menu:
+//   hessian_update_impl              default (dense damped BFGS)  |  forwarded to problem.hessian_update_impl — the OCP's block
+//                                    BFGS when MATRIXFMT == SPARSE (continuous_ocp.hpp:2303-2431), dense BFGS when DENSE
+//   update_linearisation_*_impl      default (gradient + quasi-Newton update)  |  forwarded to linearisation_*_impl (exact
+//                                    Hessian at every iteration, minimal_time_test.cpp:124-143)
+//   hessian_regularisation_*_impl    default (none)  |  the Gershgorin shift of minimal_time_test.cpp:90-122
+// Anything else — an override that does something the menu does not have, an overridden step_size_selection_impl /
+// constraints_violation_impl / max_constraints_violation_impl / termination_criteria_impl, a non-null iteration_callback, a
+// preconditioner other than Identity, a QP solver other than boxADMM — is REFUSED: solve() prints what it found to stderr and
+// returns with status INVALID_SETTINGS instead of silently running a different algorithm.
+// MATRIXFMT == SPARSE selects the SPARSE *semantics* (block-diagonal quasi-Newton update); storage on the device is dense.
 #pragma once
 #include "pmb_eigen_shim.hpp"
 #include "../polympc_b200.h"
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
+#include <initializer_list>
 #include <iostream>
 #include <limits>
 #include <stdexcept>
@@ -48,7 +59,17 @@
 #define POLYMPC_HD
 #endif
 
-namespace pmb { namespace compat { template <class U> const char* problem_name(); } }
+namespace pmb { namespace compat {
+template <class U> const char* problem_name();
+/** recording of what a Derived solver's hooks call while solve() probes them on the host (thread local) */
+struct HookProbe {
+    enum Event { LAG_GRAD = 1, LAG_GRAD_HESS = 2, HESS_UPDATE_DEFAULT = 3, HESS_UPDATE_OCP = 4 };
+    int events[16]; int n = 0;
+    void push(int e) { if (n < 16) events[n++] = e; }
+    bool is(std::initializer_list<int> want) const { if ((int)want.size() != n) return false; int k = 0; for (int e : want) if (events[k++] != e) return false; return true; }
+};
+inline HookProbe*& active_probe() { static thread_local HookProbe* p = nullptr; return p; }
+} }
 
 // ---- polynomial / spline tags ------------------------------------------------------------------------------------------
 namespace polympc {
@@ -82,7 +103,8 @@ public:
 typedef std::chrono::time_point<std::chrono::system_clock> time_point;
 inline time_point get_time() { return std::chrono::system_clock::now(); }
 struct IdentityPreconditioner {};
-template <typename Scalar, int N, int M, int FMT> struct RuizEquilibration {};   // accepted as a type; not on the GPU path
+template <typename T> POLYMPC_HD inline void ignore_unused_var(const T&) noexcept {}   // src/utils/helpers.hpp
+template <typename Scalar, int N, int M, int FMT> struct RuizEquilibration {};   // a tag only: SQPBase::solve() refuses it (not on the GPU path)
 } // namespace polympc
 
 enum MEMORY { DENSE = 0, SPARSE = 1 };
@@ -110,7 +132,6 @@ public:
         DUAL_SIZE = NUM_EQ + NUM_INEQ + NUM_BOX,
         is_sparse = (MatrixFormat == SPARSE) ? 1 : 0, is_dense = is_sparse ? 0 : 1, MATRIXFMT = MatrixFormat
     };
-    static_assert(NP == 0, "optimised parameters (NP > 0) are not on the GPU path yet");
     template <typename scalar_t> using state_t = Eigen::Matrix<scalar_t, NX, 1>;
     template <typename scalar_t> using control_t = Eigen::Matrix<scalar_t, NU, 1>;
     template <typename scalar_t> using parameter_t = Eigen::Matrix<scalar_t, NP, 1>;
@@ -160,6 +181,7 @@ public:
                              const Eigen::Ref<const nlp_dual_t>& lam, scalar_t& _lagrangian, Eigen::Ref<nlp_variable_t> lag_gradient,
                              Eigen::Ref<nlp_variable_t> cost_gradient, Eigen::Ref<nlp_constraints_t> g, Eigen::Ref<nlp_jacobian_t> jac_g) const
     {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::LAG_GRAD); return; }
         chk(pmb_ocp_lagrangian_gradient(engine(), 1, var.data(), p.data(), lam.data(), &_lagrangian, lag_gradient.data(), cost_gradient.data(),
                                         g.data(), jac_g.data()), "lagrangian_gradient");
     }
@@ -168,8 +190,18 @@ public:
                                      Eigen::Ref<nlp_hessian_t> lag_hessian, Eigen::Ref<nlp_variable_t> cost_gradient,
                                      Eigen::Ref<nlp_constraints_t> g, Eigen::Ref<nlp_jacobian_t> jac_g) const
     {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::LAG_GRAD_HESS); return; }
         chk(pmb_ocp_lagrangian_gradient_hessian(engine(), 1, var.data(), p.data(), lam.data(), &_lagrangian, lag_gradient.data(),
                                                 lag_hessian.data(), cost_gradient.data(), g.data(), jac_g.data()), "lagrangian_gradient_hessian");
+    }
+    /** hessian_update_impl (continuous_ocp.hpp:676-686): DENSE = BFGS_update, SPARSE = the block BFGS of 2303-2431; evaluated by
+     *  the engine's operators (pmb_bfgs_update / pmb_ocp_block_bfgs_update) */
+    void hessian_update_impl(Eigen::Ref<nlp_hessian_t> hessian, const Eigen::Ref<const nlp_variable_t> s,
+                             const Eigen::Ref<const nlp_variable_t> y) const
+    {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::HESS_UPDATE_OCP); return; }
+        if (MatrixFormat == SPARSE) chk(pmb_ocp_block_bfgs_update(engine(), 1, hessian.data(), s.data(), y.data(), nullptr), "hessian_update_impl");
+        else chk(pmb_bfgs_update(VAR_SIZE, 1, hessian.data(), s.data(), y.data(), nullptr), "hessian_update_impl");
     }
     /** time grid of the NLP variable, final time first (continuous_ocp.hpp:45-66) */
     time_t time_nodes_now() const { time_t t; chk(pmb_ocp_time_nodes(engine(), t.data()), "time_nodes"); return t; }
@@ -227,20 +259,83 @@ struct qp_solver_settings_t {
     Scalar adaptive_rho_tolerance = 5;
     int adaptive_rho_interval = 25;
 };
-/** QP solver type tags: the engine's inner solver is always boxADMM + dense LDL^T; the template arguments are accepted so
- *  that `boxADMM<VAR_SIZE, NUM_EQ, scalar_t, MATRIXFMT, linear_solver_traits<FMT>::default_solver>` spells the same */
+/** QP solver types.  boxADMM<> is the engine's inner solver (boxADMM + dense pivoted LDL^T, csrc/pmb_qp.hpp); the template
+ *  arguments are accepted so that `boxADMM<VAR_SIZE, NUM_EQ, scalar_t, MATRIXFMT, linear_solver_traits<FMT>::default_solver>`
+ *  spells the same.  Used stand-alone it is the QPBase object concept (qp_base.hpp:148-175): solve() with 7 or 9 arguments runs
+ *  ONE instance through pmb_qp_solve on the device; primal_solution(), dual_solution() = [y_A ; y_box], info(), settings(). */
+typedef enum { SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, UNINITIALIZED, INFEASIBLE, INCONSISTENT } status_t;   // qp_base.hpp:55-62
+template <typename Scalar>
+struct qp_solver_info_t { status_t status = UNINITIALIZED; int iter = 0; int rho_updates = 0; Scalar rho_estimate = 0, res_prim = 1, res_dual = 1; };
+
 template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
           template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
 struct boxADMM {
+    static constexpr bool pmb_engine_inner_solver = true;   // SQPBase::solve() refuses QP solver types without this tag
+    using scalar_t = Scalar;
+    using settings_t = qp_solver_settings_t<Scalar>;
+    using info_t = qp_solver_info_t<Scalar>;
+    using qp_var_t = Eigen::Matrix<Scalar, N, 1>;
+    using qp_dual_t = Eigen::Matrix<Scalar, N + M, 1>;
+    using qp_dual_a_t = Eigen::Matrix<Scalar, M, 1>;
+    using qp_hessian_t = Eigen::Matrix<Scalar, N, N>;
+    using qp_constraint_t = Eigen::Matrix<Scalar, M, N>;
+    settings_t m_settings;
+    info_t m_info;
+    qp_var_t m_x;
+    qp_dual_t m_y;
+    int iter{0};                                  // box_admm.hpp:44 (public in the reference, read by its tests)
+    boxADMM() { m_x.setZero(); m_y.setZero(); }
+    settings_t& settings() noexcept { return m_settings; }
+    const settings_t& settings() const noexcept { return m_settings; }
+    const info_t& info() const noexcept { return m_info; }
+    const qp_var_t& primal_solution() const noexcept { return m_x; }
+    qp_var_t& primal_solution() noexcept { return m_x; }
+    const qp_dual_t& dual_solution() const noexcept { return m_y; }
+    qp_dual_t& dual_solution() noexcept { return m_y; }
+
+    /** QPBase::solve, 7 arguments (cold start, qp_base.hpp:161-166) and 9 arguments (with guesses, 168-175) */
+    status_t solve(const Eigen::Ref<const qp_hessian_t>& H, const Eigen::Ref<const qp_var_t>& h, const Eigen::Ref<const qp_constraint_t>& A,
+                   const Eigen::Ref<const qp_dual_a_t>& Alb, const Eigen::Ref<const qp_dual_a_t>& Aub,
+                   const Eigen::Ref<const qp_var_t>& xlb, const Eigen::Ref<const qp_var_t>& xub)
+    { return run(H.data(), h.data(), A.data(), Alb.data(), Aub.data(), xlb.data(), xub.data(), nullptr, nullptr); }
+    status_t solve(const Eigen::Ref<const qp_hessian_t>& H, const Eigen::Ref<const qp_var_t>& h, const Eigen::Ref<const qp_constraint_t>& A,
+                   const Eigen::Ref<const qp_dual_a_t>& Alb, const Eigen::Ref<const qp_dual_a_t>& Aub,
+                   const Eigen::Ref<const qp_var_t>& xlb, const Eigen::Ref<const qp_var_t>& xub,
+                   const Eigen::Ref<const qp_var_t>& x_guess, const Eigen::Ref<const qp_dual_t>& y_guess)
+    { return run(H.data(), h.data(), A.data(), Alb.data(), Aub.data(), xlb.data(), xub.data(), x_guess.data(), y_guess.data()); }
+
+private:
+    status_t run(const Scalar* H, const Scalar* h, const Scalar* A, const Scalar* Alb, const Scalar* Aub, const Scalar* xlb,
+                 const Scalar* xub, const Scalar* xg, const Scalar* yg)
+    {
+        pmb_qp_settings_t q; pmb_qp_default_settings(&q);
+        const settings_t& s = m_settings;
+        q.rho = s.rho; q.sigma = s.sigma; q.alpha = s.alpha; q.eps_rel = s.eps_rel; q.eps_abs = s.eps_abs; q.max_iter = s.max_iter;
+        q.check_termination = s.check_termination; q.warm_start = s.warm_start; q.adaptive_rho = s.adaptive_rho;
+        q.adaptive_rho_tolerance = s.adaptive_rho_tolerance; q.adaptive_rho_interval = s.adaptive_rho_interval;
+        q.reuse_pattern = s.reuse_pattern; q.verbose = s.verbose;
+        pmb_qp_info_t inf;
+        const int rc = pmb_qp_solve(N, M, 1, H, h, A, Alb, Aub, xlb, xub, xg, yg, &q, m_x.data(), m_y.data(), &inf, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc != PMB_OK) throw std::runtime_error(std::string("boxADMM::solve failed (") + std::to_string(rc) + "): " + pmb_last_error());
+        const int prev_updates = m_info.rho_updates;           // accumulates across solves (box_admm.hpp:395)
+        m_info.status = (status_t)inf.status; m_info.iter = inf.iter; m_info.rho_updates = prev_updates + inf.rho_updates;
+        iter = inf.iter;
+        m_info.rho_estimate = inf.rho_estimate; m_info.res_prim = inf.res_prim; m_info.res_dual = inf.res_dual;
+        return m_info.status;
+    }
+};
+/** the OSQP-style ADMM of src/solvers/admm.hpp (box constraints stacked under A, a (2N+M) KKT system) is NOT built: it is a
+ *  distinct type without the engine tag, so SQPBase::solve() refuses it instead of running boxADMM in its place */
+template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
+          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
+struct ADMM {
+    static constexpr bool pmb_engine_inner_solver = false;
     using scalar_t = Scalar;
     using settings_t = qp_solver_settings_t<Scalar>;
     settings_t m_settings;
     settings_t& settings() noexcept { return m_settings; }
     const settings_t& settings() const noexcept { return m_settings; }
 };
-template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
-          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
-struct ADMM : boxADMM<N, M, Scalar, MatrixType, LinearSolver, LinearSolver_UpLo> {};
 
 // ---- device side: adapter from the Eigen-style functors to the engine's functor concept ---------------------------------
 #if defined(__CUDACC__) || defined(PMB_EMU)
@@ -373,11 +468,17 @@ public:
     using nlp_settings_t = sqp_settings_t<scalar_t>;
     using nlp_info_t = sqp_info_t;
 
-    /** engine-side replacements for the two CRTP overrides the reference's own solvers install
-     *  (tests/control/minimal_time_test.cpp:90-135); host overrides in Derived are never called by the fused kernel */
-    struct engine_options_t { bool exact_hessian_every_iteration = false; bool gershgorin_regularisation = false; };
+    /** what the hook probe found (see the header comment); filled by the first solve(), readable afterwards */
+    struct engine_options_t {
+        bool exact_hessian_every_iteration = false;   // update_linearisation_*_impl forwards to linearisation_*_impl
+        bool gershgorin_regularisation = false;       // hessian_regularisation_*_impl is the Gershgorin shift
+        bool block_bfgs = false;                      // hessian_update_impl forwards to the SPARSE problem's block BFGS
+        bool probed = false;
+        std::string refused;                          // non-empty: why solve() refuses to run (status INVALID_SETTINGS)
+    };
     engine_options_t m_engine_options;
     engine_options_t& engine_options() noexcept { return m_engine_options; }
+    const engine_options_t& engine_options() const noexcept { return m_engine_options; }
 
     Problem problem;
     nlp_settings_t m_settings;
@@ -387,6 +488,8 @@ public:
     nlp_dual_t m_lam;
     nlp_ineq_constraints_t m_lbg, m_ubg;
     parameter_t m_p;
+    nlp_hessian_t m_H;              // host mirror used by the hook probe only (user overrides read this->m_H.rows())
+    nlp_variable_t m_lag_gradient;
 
     SQPBase()
     {
@@ -437,13 +540,171 @@ public:
     void solve(const Eigen::Ref<const nlp_variable_t>& x_guess, const Eigen::Ref<const nlp_dual_t>& lam_guess)   // sqp_base.hpp:558-566
     { m_x = x_guess; m_lam = lam_guess; solve_impl(); }
 
+    // ---- CRTP hooks, default implementations (sqp_base.hpp:263-350).  The fused kernel runs their device twins; on the host
+    // they exist so that user solvers which override or call them compile, and so that solve() can probe the overrides.
+    Derived& derived() noexcept { return *static_cast<Derived*>(this); }
+    void hessian_update(Eigen::Ref<nlp_hessian_t> hessian, const Eigen::Ref<const nlp_variable_t>& x_step,
+                        const Eigen::Ref<const nlp_variable_t>& grad_step) noexcept
+    { derived().hessian_update_impl(hessian, x_step, grad_step); }
+    /** default: dense damped BFGS (bfgs.hpp:23-52) */
+    void hessian_update_impl(Eigen::Ref<nlp_hessian_t> hessian, const Eigen::Ref<const nlp_variable_t>& x_step,
+                             const Eigen::Ref<const nlp_variable_t>& grad_step) noexcept
+    {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::HESS_UPDATE_DEFAULT); return; }
+        pmb_bfgs_update(VAR_SIZE, 1, hessian.data(), x_step.data(), grad_step.data(), nullptr);
+    }
+    void hessian_regularisation_dense_impl(Eigen::Ref<nlp_hessian_t>) noexcept {}
+    void hessian_regularisation_sparse_impl(Eigen::Ref<nlp_hessian_t>) noexcept {}
+    void linearisation_dense_impl(const Eigen::Ref<const nlp_variable_t>& x, const Eigen::Ref<const parameter_t>& p,
+                                  const Eigen::Ref<const nlp_dual_t>& lam, Eigen::Ref<nlp_variable_t> cost_grad,
+                                  Eigen::Ref<nlp_hessian_t> lag_hessian, Eigen::Ref<nlp_jacobian_t> A, Eigen::Ref<nlp_constraints_t> b) noexcept
+    {
+        scalar_t lag(0.0);
+        problem.lagrangian_gradient_hessian(x, p, lam, lag, m_lag_gradient, lag_hessian, cost_grad, b, A);
+        derived().hessian_regularisation_dense_impl(m_H);          // the member, like sqp_base.hpp:316-317
+    }
+    void linearisation_sparse_impl(const Eigen::Ref<const nlp_variable_t>& x, const Eigen::Ref<const parameter_t>& p,
+                                   const Eigen::Ref<const nlp_dual_t>& lam, Eigen::Ref<nlp_variable_t> cost_grad,
+                                   nlp_hessian_t& lag_hessian, nlp_jacobian_t& A, Eigen::Ref<nlp_constraints_t> b) noexcept
+    {
+        scalar_t lag(0.0);
+        problem.lagrangian_gradient_hessian(x, p, lam, lag, m_lag_gradient, lag_hessian, cost_grad, b, A);
+        derived().hessian_regularisation_sparse_impl(m_H);
+    }
+    void update_linearisation_dense_impl(const Eigen::Ref<const nlp_variable_t>& x, const Eigen::Ref<const parameter_t>& p,
+                                         const Eigen::Ref<const nlp_variable_t>& x_step, const Eigen::Ref<const nlp_dual_t>& lam,
+                                         Eigen::Ref<nlp_variable_t> cost_grad, Eigen::Ref<nlp_hessian_t> lag_hessian,
+                                         Eigen::Ref<nlp_jacobian_t> A, Eigen::Ref<nlp_constraints_t> b) noexcept
+    {
+        scalar_t lag(0.0);
+        nlp_variable_t lag_grad;
+        problem.lagrangian_gradient(x, p, lam, lag, lag_grad, cost_grad, b, A);
+        hessian_update(lag_hessian, x_step, nlp_variable_t(lag_grad - m_lag_gradient));
+        m_lag_gradient = lag_grad;
+    }
+    void update_linearisation_sparse_impl(const Eigen::Ref<const nlp_variable_t>& x, const Eigen::Ref<const parameter_t>& p,
+                                          const Eigen::Ref<const nlp_variable_t>& x_step, const Eigen::Ref<const nlp_dual_t>& lam,
+                                          Eigen::Ref<nlp_variable_t> cost_grad, nlp_hessian_t& lag_hessian, nlp_jacobian_t& A,
+                                          Eigen::Ref<nlp_constraints_t> b) noexcept
+    {
+        scalar_t lag(0.0);
+        nlp_variable_t lag_grad;
+        problem.lagrangian_gradient(x, p, lam, lag, lag_grad, cost_grad, b, A);
+        hessian_update(lag_hessian, x_step, nlp_variable_t(lag_grad - m_lag_gradient));
+        m_lag_gradient = lag_grad;
+    }
+    /** defaults of the hooks that have no engine-side alternative: overriding any of them is refused */
+    scalar_t step_size_selection_impl(const Eigen::Ref<const nlp_variable_t>&) noexcept { return scalar_t(1); }
+    scalar_t constraints_violation_impl(const Eigen::Ref<const nlp_variable_t>&) const noexcept { return scalar_t(0); }
+    scalar_t max_constraints_violation_impl(const Eigen::Ref<const nlp_variable_t>&) const noexcept { return scalar_t(0); }
+    bool termination_criteria_impl(const Eigen::Ref<const nlp_variable_t>&) noexcept { return false; }
+
 private:
+    // `&Derived::name` names the base's member (type `R (SQPBase::*)(...)`) unless Derived declares its own: comparing the
+    // member-pointer types detects an override without calling it; an overloaded / templated override makes the expression
+    // ill-formed and lands in the `true` fallback
+#define PMB_COMPAT_OVERRIDES(NAME)                                                                                            \
+    template <class D, class = void> struct overrides_##NAME : std::true_type {};                                             \
+    template <class D> struct overrides_##NAME<D, decltype(void(&D::NAME))>                                                   \
+        : std::integral_constant<bool, !std::is_same<decltype(&D::NAME), decltype(&SQPBase::NAME)>::value> {};
+    PMB_COMPAT_OVERRIDES(step_size_selection_impl)
+    PMB_COMPAT_OVERRIDES(constraints_violation_impl)
+    PMB_COMPAT_OVERRIDES(max_constraints_violation_impl)
+    PMB_COMPAT_OVERRIDES(termination_criteria_impl)
+    PMB_COMPAT_OVERRIDES(linearisation_dense_impl)
+    PMB_COMPAT_OVERRIDES(linearisation_sparse_impl)
+#undef PMB_COMPAT_OVERRIDES
+
+    /** Gershgorin shift of the reference's minimal_time_test.cpp:90-104 on the host (probe comparison only) */
+    static void host_gershgorin(nlp_hessian_t& H)
+    {
+        for (int i = 0; i < VAR_SIZE; ++i) {
+            const scalar_t aii = H(i, i);
+            scalar_t sum = 0;
+            for (int j = 0; j < VAR_SIZE; ++j) sum += std::fabs(H(j, i));
+            const scalar_t ri = sum - std::fabs(aii);
+            if (aii - ri <= 0) H(i, i) += (ri - aii) + scalar_t(0.01);
+        }
+    }
+    static bool same(const nlp_hessian_t& a, const nlp_hessian_t& b, scalar_t tol)
+    { for (int i = 0; i < VAR_SIZE * VAR_SIZE; ++i) if (!(std::fabs(a.data()[i] - b.data()[i]) <= tol * (1 + std::fabs(b.data()[i])))) return false; return true; }
+
+    /** run the overridable hooks once on the host against the recording problem and map what they do onto the engine menu */
+    void probe_hooks()
+    {
+        using P = pmb::compat::HookProbe;
+        engine_options_t& eo = m_engine_options;
+        eo = engine_options_t();
+        eo.probed = true;
+        auto refuse = [&](const std::string& why) { if (eo.refused.empty()) eo.refused = why; };
+        if (overrides_step_size_selection_impl<Derived>::value) refuse("Derived::step_size_selection_impl overrides the l1-merit line search");
+        if (overrides_constraints_violation_impl<Derived>::value) refuse("Derived::constraints_violation_impl is overridden");
+        if (overrides_max_constraints_violation_impl<Derived>::value) refuse("Derived::max_constraints_violation_impl is overridden");
+        if (overrides_termination_criteria_impl<Derived>::value) refuse("Derived::termination_criteria_impl is overridden");
+        if (overrides_linearisation_dense_impl<Derived>::value || overrides_linearisation_sparse_impl<Derived>::value)
+            refuse("Derived::linearisation_*_impl is overridden (only the exact AD linearisation exists on the device)");
+        if (!std::is_same<Preconditioner, polympc::IdentityPreconditioner>::value)
+            refuse("a preconditioner other than IdentityPreconditioner was requested (RuizEquilibration is not built)");
+        if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is not boxADMM (the OSQP-style ADMM is not built)");
+        if (m_settings.iteration_callback != nullptr) refuse("settings().iteration_callback is set: a host callback cannot fire inside the fused device loop");
+
+        // test data: a symmetric matrix whose Gershgorin discs partly reach into the negative half plane, so that a Gershgorin
+        // regulariser has something to do on some columns and nothing on others.  The diagonal is integer valued on purpose:
+        // the reference's own regulariser (minimal_time_test.cpp:98, 113) calls an unqualified `abs(aii)`, which is the C
+        // library's int abs(int) on some tool chains — on integers both readings agree.
+        nlp_hessian_t Hp;
+        for (int j = 0; j < VAR_SIZE; ++j)
+            for (int i = 0; i < VAR_SIZE; ++i)
+                Hp(i, j) = (i == j) ? ((i % 4 == 0) ? scalar_t(1000) : ((i % 4 == 1) ? scalar_t(-2) : ((i % 4 == 2) ? scalar_t(0) : scalar_t(1))))
+                                    : scalar_t(0.5) / scalar_t(1 + ((i + j) % 7));
+        nlp_variable_t xs, cg; xs.setConstant(scalar_t(0.1)); cg.setZero();
+        nlp_dual_t lam; lam.setZero();
+        nlp_constraints_t b; b.setZero();
+        std::vector<scalar_t> Abuf((size_t)(NUM_EQ + NUM_INEQ) * VAR_SIZE, scalar_t(0));
+        nlp_jacobian_t& A = *reinterpret_cast<nlp_jacobian_t*>(Abuf.data());
+
+        // (1) what does the update of the linearisation do?
+        P rec;
+        pmb::compat::active_probe() = &rec;
+        m_H = Hp; m_lag_gradient.setZero();
+        if (Problem::is_sparse) derived().update_linearisation_sparse_impl(xs, m_p, xs, lam, cg, m_H, A, b);
+        else derived().update_linearisation_dense_impl(xs, m_p, xs, lam, cg, m_H, A, b);
+        pmb::compat::active_probe() = nullptr;
+        nlp_hessian_t Hafter = m_H;
+        bool regularised_in_update = false;
+        if (rec.is({P::LAG_GRAD, P::HESS_UPDATE_DEFAULT})) eo.block_bfgs = false;
+        else if (rec.is({P::LAG_GRAD, P::HESS_UPDATE_OCP})) eo.block_bfgs = Problem::is_sparse;     // DENSE problem: plain BFGS (continuous_ocp.hpp:681-686)
+        else if (rec.is({P::LAG_GRAD_HESS})) { eo.exact_hessian_every_iteration = true; regularised_in_update = true; }
+        else refuse("Derived::update_linearisation_*_impl / hessian_update_impl does something the engine has no device twin for "
+                    "(expected: gradient + BFGS, gradient + problem.hessian_update_impl, or the exact linearisation)");
+        if (!regularised_in_update && !same(Hafter, Hp, 0)) refuse("Derived::hessian_update_impl modifies the Hessian on its own");
+
+        // (2) what does the regularisation hook do?  (called by linearisation_*_impl after every exact Hessian)
+        m_H = Hp;
+        if (Problem::is_sparse) derived().hessian_regularisation_sparse_impl(m_H);
+        else derived().hessian_regularisation_dense_impl(m_H);
+        nlp_hessian_t Hg = Hp;
+        host_gershgorin(Hg);
+        if (same(m_H, Hp, 0)) eo.gershgorin_regularisation = false;
+        else if (same(m_H, Hg, 1e-12)) eo.gershgorin_regularisation = true;
+        else refuse("Derived::hessian_regularisation_*_impl is neither the default (none) nor the Gershgorin shift");
+        if (regularised_in_update && !eo.gershgorin_regularisation && !same(Hafter, Hp, 0)) refuse("the exact linearisation override also modifies the Hessian");
+    }
+
     pmb_sqp_t* m_handle = nullptr;
     double m_stats[4] = {0, 0, 0, 0};
     static void check(int rc, const char* what)
     { if (rc != PMB_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + pmb_last_error()); }
     void solve_impl()
     {
+        probe_hooks();
+        if (!m_engine_options.refused.empty()) {
+            std::cerr << "polympc_b200: SQPBase::solve() REFUSED — " << m_engine_options.refused
+                      << ".  The fused sm_100a SQP loop runs the reference's default hooks plus a fixed menu (block BFGS, exact "
+                         "Hessian at every iteration, Gershgorin regularisation); it will not silently run a different algorithm.\n";
+            m_info.iter = 0; m_info.qp_solver_iter = 0; m_info.status.value = sqp_status_t::INVALID_SETTINGS;
+            return;
+        }
 #if defined(__CUDACC__) || defined(PMB_EMU)
         if (!m_handle) {
             m_handle = pmb_sqp_create(pmb::compat::problem_name<Problem>(), 1, 0);
@@ -471,6 +732,7 @@ private:
         check(pmb_sqp_set_qp_settings(m_handle, &q), "set_qp_settings");
         check(pmb_sqp_set_hessian_options(m_handle, m_engine_options.exact_hessian_every_iteration, m_engine_options.gershgorin_regularisation),
               "set_hessian_options");
+        check(pmb_sqp_set_hessian_update(m_handle, m_engine_options.block_bfgs ? PMB_HESSIAN_BFGS_BLOCK : PMB_HESSIAN_BFGS_DENSE), "set_hessian_update");
         check(pmb_sqp_set_bounds_x(m_handle, m_lbx.data(), m_ubx.data(), VAR_SIZE), "set_bounds_x");
         if (NUM_INEQ > 0) check(pmb_sqp_set_bounds_g(m_handle, m_lbg.data(), m_ubg.data(), NUM_INEQ), "set_bounds_g");
         if (Problem::ND > 0) check(pmb_sqp_set_parameters(m_handle, m_p.data(), Problem::ND), "set_parameters");
@@ -485,6 +747,15 @@ private:
         m_info.status.value = inf.status == PMB_SQP_SOLVED ? sqp_status_t::SOLVED
                             : (inf.status == PMB_SQP_MAX_ITER_EXCEEDED ? sqp_status_t::MAX_ITER_EXCEEDED : sqp_status_t::INVALID_SETTINGS);
         check(pmb_sqp_get_stats(m_handle, m_stats), "get_stats");
+        if (std::getenv("POLYMPC_B200_REPORT")) {     // one line per solve for harnesses that cannot change the calling code
+            bool finite = true;
+            for (int i = 0; i < VAR_SIZE; ++i) finite = finite && std::isfinite(m_x(i));
+            for (int i = 0; i < NUM_CONSTR; ++i) finite = finite && std::isfinite(m_lam(i));
+            std::cerr << "polympc_b200: solve status=" << (int)m_info.status.value << " iter=" << m_info.iter << " qp_iter=" << m_info.qp_solver_iter
+                      << " finite=" << (finite ? 1 : 0) << " block_bfgs=" << (m_engine_options.block_bfgs ? 1 : 0)
+                      << " exact_hessian=" << (m_engine_options.exact_hessian_every_iteration ? 1 : 0)
+                      << " gershgorin=" << (m_engine_options.gershgorin_regularisation ? 1 : 0) << "\n";
+        }
     }
 };
 
@@ -534,6 +805,12 @@ public:
     void constraints_bounds(const Eigen::Ref<const constraint_t>& lbg, const Eigen::Ref<const constraint_t>& ubg) noexcept
     { for (int k = 0; k < num_nodes; ++k) { put(m_solver.lower_bound_g(), k * ng, lbg); put(m_solver.upper_bound_g(), k * ng, ubg); } }
     void set_static_parameters(const Eigen::Ref<const static_param>& param) noexcept { put(m_solver.parameters(), 0, param); }
+    /** optimised parameters (mpc_wrapper.hpp:137-160): box bounds and guess of the tail of the NLP variable */
+    void parameters_bounds(const Eigen::Ref<const parameter_t>& lbp, const Eigen::Ref<const parameter_t>& ubp) noexcept
+    { put(m_solver.lower_bound_x(), varx_size + varu_size, lbp); put(m_solver.upper_bound_x(), varx_size + varu_size, ubp); }
+    void p_guess(const Eigen::Ref<const parameter_t>& g) noexcept { put(m_solver.primal_solution(), varx_size + varu_size, g); }
+    void x_guess(const Eigen::VecDyn<scalar_t>& g) noexcept { for (int i = 0; i < varx_size; ++i) m_solver.primal_solution()(i) = g.v[i]; }
+    void u_guess(const Eigen::VecDyn<scalar_t>& g) noexcept { for (int i = 0; i < varu_size; ++i) m_solver.primal_solution()(varx_size + i) = g.v[i]; }
     void x_guess(const Eigen::Ref<const traj_state_t>& g) noexcept { put(m_solver.primal_solution(), 0, g); }
     void u_guess(const Eigen::Ref<const traj_control_t>& g) noexcept { put(m_solver.primal_solution(), varx_size, g); }
     void lam_guess(const Eigen::Ref<const dual_var_t>& g) noexcept { put(m_solver.dual_solution(), 0, g); }
@@ -567,7 +844,7 @@ public:
     parameter_t solution_p() const noexcept { return get<np>(m_solver.primal_solution(), varx_size + varu_size); }
     dual_var_t solution_dual() const noexcept { return m_solver.dual_solution(); }
 
-    void solve() noexcept { m_solver.solve(); }
+    void solve() { m_solver.solve(); }   // not noexcept: an engine failure (CUDA error, missing device) throws instead of std::terminate
 
 private:
     template <class Dst, class Src> static void put(Dst& dst, int off, const Src& src) { for (int i = 0; i < (int)Src::Size; ++i) dst(off + i) = src(i); }

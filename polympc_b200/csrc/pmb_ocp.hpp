@@ -417,7 +417,7 @@ struct OcpEval {
             param_gradient_sum(cta, o, nv + NV_GP, grad);
             // (p, p) block: cost part in loop order (junction nodes twice), then the constraint curvature node by node (2141-2160)
             for (int e = tid; e < NP * NP; e += nt) {
-                const int cp = e / NP, rp = e - cp * NP;
+                const int cp = e / NPA, rp = e - cp * NPA;
                 double acc = 0.0;
                 for (int s = 0; s < S; ++s)
                     for (int k = 0; k <= P; ++k) acc += (o.ts * o.w[k]) * nv[NV_PPC + ((s * P + k) * NP + cp) * NP + rp];

@@ -112,7 +112,8 @@ PMB_DEV int block_bfgs_update_cta(Cta& c, double* H, const double* s, const doub
         H[gi + (size_t)gj * N] += h;
     }
     if (NP > 0) {
-        for (int e = tid; e < NP * NP; e += nt) { const int j = e / NP, i = e - j * NP; H[(P0 + i) + (size_t)(P0 + j) * N] += inc(P0 + i, P0 + j); }
+        constexpr int NPd = NP > 0 ? NP : 1;
+        for (int e = tid; e < NP * NP; e += nt) { const int j = e / NPd, i = e - j * NPd; H[(P0 + i) + (size_t)(P0 + j) * N] += inc(P0 + i, P0 + j); }
         for (int e = tid; e < NP * P0; e += nt) {
             const int j = e / P0, i = e - j * P0;
             const double h = inc(i, P0 + j);

@@ -1,0 +1,96 @@
+// tests/cpp/test_hook_refusal.cpp — TEST INFRASTRUCTURE.  The source-compatibility layer must never run an algorithm the
+// user did not write: SQPBase::solve() probes the CRTP hooks of the Derived solver (include/polympc_compat/polympc_compat.hpp)
+// and either maps them onto the engine's menu or refuses loudly (stderr + status INVALID_SETTINGS).  Each case below is a
+// solver a PolyMPC user could write against sqp_base.hpp:198-350; none of the refused ones ever reaches the device.
+#include "../dropin/robot_ocp.hpp"
+#include "solvers/sqp_base.hpp"
+#include "solvers/box_admm.hpp"
+#include "solvers/admm.hpp"
+#include "solvers/qp_preconditioners.hpp"
+#include "control/mpc_wrapper.hpp"
+
+#include <cstdio>
+
+static int g_fail = 0;
+#define EXPECT(c) do { if (!(c)) { ++g_fail; std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+
+using OCP = dropin::RobotOCP;
+using BoxQP = boxADMM<OCP::VAR_SIZE, OCP::NUM_EQ + OCP::NUM_INEQ, double>;
+#define SOLVER_TYPES(S, Q)                                   \
+    using Base = SQPBase<S<Problem, QPSolver>, Problem, Q>;   \
+    using typename Base::scalar_t; using typename Base::nlp_variable_t; using typename Base::nlp_hessian_t;
+
+// (a) all defaults: accepted, dense BFGS
+template <typename Problem, typename QPSolver = BoxQP> class Plain : public SQPBase<Plain<Problem, QPSolver>, Problem, QPSolver> {};
+
+// (b) hessian_update_impl forwarded to the problem: accepted (DENSE problem => dense BFGS, continuous_ocp.hpp:681-686)
+template <typename Problem, typename QPSolver = BoxQP>
+class Forwarding : public SQPBase<Forwarding<Problem, QPSolver>, Problem, QPSolver> {
+public:
+    SOLVER_TYPES(Forwarding, QPSolver)
+    void hessian_update_impl(Eigen::Ref<nlp_hessian_t> H, const Eigen::Ref<const nlp_variable_t>& s, const Eigen::Ref<const nlp_variable_t>& y) noexcept
+    { this->problem.hessian_update_impl(H, s, y); }
+};
+
+// (c) a home-made SR1 update: refused
+template <typename Problem, typename QPSolver = BoxQP>
+class Sr1 : public SQPBase<Sr1<Problem, QPSolver>, Problem, QPSolver> {
+public:
+    SOLVER_TYPES(Sr1, QPSolver)
+    void hessian_update_impl(Eigen::Ref<nlp_hessian_t> H, const Eigen::Ref<const nlp_variable_t>& s, const Eigen::Ref<const nlp_variable_t>& y) noexcept
+    { for (int i = 0; i < Problem::VAR_SIZE; ++i) H(i, i) += y(i) * y(i) / (1.0 + s(i) * s(i)); }
+};
+
+// (d) a custom line search: refused
+template <typename Problem, typename QPSolver = BoxQP>
+class FullStep : public SQPBase<FullStep<Problem, QPSolver>, Problem, QPSolver> {
+public:
+    SOLVER_TYPES(FullStep, QPSolver)
+    scalar_t step_size_selection_impl(const Eigen::Ref<const nlp_variable_t>&) noexcept { return scalar_t(1); }
+};
+
+// (e) a regulariser that is not the Gershgorin shift: refused
+template <typename Problem, typename QPSolver = BoxQP>
+class ShiftAll : public SQPBase<ShiftAll<Problem, QPSolver>, Problem, QPSolver> {
+public:
+    SOLVER_TYPES(ShiftAll, QPSolver)
+    void hessian_regularisation_dense_impl(Eigen::Ref<nlp_hessian_t> H) noexcept { for (int i = 0; i < Problem::VAR_SIZE; ++i) H(i, i) += 1.0; }
+};
+
+// (f) Ruiz preconditioner requested: refused; (g) OSQP-style ADMM requested: refused
+using Ruiz = polympc::RuizEquilibration<double, OCP::VAR_SIZE, OCP::NUM_EQ, DENSE>;
+template <typename Problem, typename QPSolver = BoxQP> class WithRuiz : public SQPBase<WithRuiz<Problem, QPSolver>, Problem, QPSolver, Ruiz> {};
+using OsqpAdmm = ADMM<OCP::VAR_SIZE, OCP::NUM_EQ + OCP::NUM_INEQ, double>;
+template <typename Problem, typename QPSolver = OsqpAdmm> class WithAdmm : public SQPBase<WithAdmm<Problem, QPSolver>, Problem, QPSolver> {};
+
+static void on_iteration(void*) {}
+
+template <class S> static int run(S& s, const char* what)
+{
+    s.settings().max_iter = 3; s.settings().line_search_max_iter = 3;
+    s.get_problem().set_time_limits(0, 2);
+    s.parameters()(0) = 2.0;
+    s.solve();
+    std::printf("%-28s status=%d refused='%s'\n", what, (int)s.info().status.value, s.engine_options().refused.c_str());
+    return (int)s.info().status.value;
+}
+
+int main(int argc, char** argv)
+{
+    const bool have_engine = argc > 1;      // the accepted cases need the engine (emulator or GPU); the refused ones never touch it
+    if (have_engine) {
+        Plain<OCP> a; EXPECT(run(a, "defaults") != sqp_status_t::INVALID_SETTINGS); EXPECT(!a.engine_options().block_bfgs);
+        Forwarding<OCP> b; EXPECT(run(b, "forward to problem (DENSE)") != sqp_status_t::INVALID_SETTINGS); EXPECT(!b.engine_options().block_bfgs);
+        EXPECT(a.primal_solution().isApprox(b.primal_solution(), 0.0) || true);
+        bool same = true; for (int i = 0; i < OCP::VAR_SIZE; ++i) same = same && a.primal_solution()(i) == b.primal_solution()(i);
+        EXPECT(same);                         // DENSE problem: the forwarded update IS the default BFGS
+    }
+    { Sr1<OCP> s; EXPECT(run(s, "home-made SR1") == sqp_status_t::INVALID_SETTINGS); }
+    { FullStep<OCP> s; EXPECT(run(s, "custom line search") == sqp_status_t::INVALID_SETTINGS); }
+    { ShiftAll<OCP> s; EXPECT(run(s, "custom regulariser") == sqp_status_t::INVALID_SETTINGS); }
+    { WithRuiz<OCP> s; EXPECT(run(s, "RuizEquilibration") == sqp_status_t::INVALID_SETTINGS); }
+    { WithAdmm<OCP> s; EXPECT(run(s, "OSQP-style ADMM") == sqp_status_t::INVALID_SETTINGS); }
+    { Plain<OCP> s; s.settings().iteration_callback = &on_iteration; EXPECT(run(s, "iteration_callback") == sqp_status_t::INVALID_SETTINGS); }
+    std::printf("%d failures\n", g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -187,6 +187,19 @@ int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int ger
  *                           (tests/control/mpc_wrapper_test.cpp:101-104, cstr_control_test.cpp:128-131 ...). */
 typedef enum pmb_hessian_update { PMB_HESSIAN_BFGS_DENSE = 0, PMB_HESSIAN_BFGS_BLOCK = 1 } pmb_hessian_update_t;
 int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode);
+/* Arithmetic of the KKT linear algebra inside boxADMM (csrc/pmb_qp.hpp vs csrc/pmb_qp_fast.hpp).  Both run the same
+ * algorithm with the same pivot permutation (Eigen::LDLT's diagonal rule):
+ *   PMB_ARITH_EXACT  every fp64 operation in the order of the CPU oracle: results are bit-identical to it (default);
+ *   PMB_ARITH_FAST   tile-blocked LDL^T on the fp64 tensor cores, explicit inverse of the unit-lower factor, triangular solves as
+ *                    streaming mat-vecs: results agree with the oracle to rounding (<= 1e-10 rel-inf per SQP iteration; how
+ *                    that propagates over a whole solve is measured in bench.py's `parity` object).
+ * pmb_set_default_arithmetic sets the process-wide default (used by pmb_qp_solve and inherited by new SQP handles);
+ * pmb_sqp_set_arithmetic switches one handle; PMB_ERR_UNSUPPORTED when the tile workspace does not fit in shared memory. */
+typedef enum pmb_arithmetic { PMB_ARITH_EXACT = 0, PMB_ARITH_FAST = 1 } pmb_arithmetic_t;
+int pmb_set_default_arithmetic(int mode);
+int pmb_get_default_arithmetic(void);
+int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode);
+int pmb_sqp_get_arithmetic(const pmb_sqp_t* s);
 /* per-iteration decision traces (pmb_sqp_get_trace) are recorded only when switched on before the solve (default off:
  * they cost batch x max_iter rows of device memory and five memsets per solve) */
 int pmb_sqp_set_trace(pmb_sqp_t* s, int on);

@@ -58,7 +58,7 @@ ABI_FUNCTIONS = [
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
@@ -131,6 +131,9 @@ class CApi:
         g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
         g("sqp_set_hessian_update").argtypes = [C.c_void_p, C.c_int]
         g("sqp_set_trace").argtypes = [C.c_void_p, C.c_int]
+        g("set_default_arithmetic").argtypes = [C.c_int]
+        g("sqp_set_arithmetic").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_get_arithmetic").argtypes = [C.c_void_p]
         for name in ("sqp_set_bounds_x", "sqp_set_bounds_g"):
             g(name).argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int]
         for name in ("sqp_set_parameters", "sqp_set_primal", "sqp_set_dual"):
@@ -224,6 +227,10 @@ class CApi:
 
     def sqp(self, name: str, batch: int, device: int = 0) -> "Sqp":
         return Sqp(self, name, batch, device)
+
+    def set_default_arithmetic(self, mode: int):
+        """process-wide default arithmetic: used by qp_solve and inherited by new Sqp handles (0 exact, 1 fast)"""
+        self._chk(self._fn("set_default_arithmetic")(int(mode)), "set_default_arithmetic")
 
     # -- QP
     def qp_solve(self, H, h, A, Alb, Aub, xlb, xub, settings: QpSettings, x_guess=None, y_guess=None, extras=True):
@@ -436,6 +443,10 @@ class Sqp:
         """0 = dense damped BFGS (SQPBase default), 1 = the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)"""
         self.api._chk(self.api._fn("sqp_set_hessian_update")(self.h, int(mode)), "sqp_set_hessian_update")
 
+    def set_arithmetic(self, mode: int):
+        """0 = PMB_ARITH_EXACT (bit-identical to the oracle), 1 = PMB_ARITH_FAST (fp64 tensor-core LDL^T, rounding-level differences)"""
+        self.api._chk(self.api._fn("sqp_set_arithmetic")(self.h, int(mode)), "sqp_set_arithmetic")
+
     def set_trace(self, on: bool = True):
         """record the per-iteration decision traces read by trace() (off by default)"""
         self.api._chk(self.api._fn("sqp_set_trace")(self.h, int(on)), "sqp_set_trace")
@@ -496,8 +507,9 @@ class Sqp:
         """raw profiling counters of the last solve (see pmb_sqp_get_phase_cycles)"""
         cyc = np.zeros(16, dtype=np.uint64)
         self.api._chk(self.api._fn("sqp_get_phase_cycles")(self.h, cyc.ctypes.data_as(C.POINTER(C.c_ulonglong))), "sqp_get_phase_cycles")
-        names = ("linearise", "qp", "step", "sqp_iterations", "qp_pivot", "qp_gather", "qp_factor", "qp_solve", "qp_update", "qp_resid", "admm_trips")
-        return {k: int(cyc[i]) for i, k in enumerate(names)}
+        names = ("linearise", "qp", "step", "sqp_iterations", "qp_pivot", "qp_gather", "qp_factor", "qp_solve", "qp_update", "qp_resid", "admm_trips",
+                 "_reserved", "fast_factor_diag", "fast_factor_panel", "fast_factor_trailing", "fast_factor_invert")
+        return {k: int(cyc[i]) for i, k in enumerate(names) if not k.startswith("_")}
 
     def kernel_times(self):
         """{kernel name: (milliseconds, launches)} of the last solve (profiling must be on)"""

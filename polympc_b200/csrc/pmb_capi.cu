@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -99,24 +100,43 @@ struct Staging {
 constexpr size_t SMEM_CTA_MAX = 227 * 1024;   // B200: opt-in dynamic shared memory per CTA
 
 /** launches the persistent boxADMM kernel over `batch` instances; `queue` is a zeroed device counter */
-template <int R, bool IN_SMEM> bool launch_qp_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb,
+template <int R, bool IN_SMEM, bool FAST = false> bool launch_qp_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb,
                                                 int batch, int* queue, DevBuf<double>& scratch)
 {
+    using Body = QpBody<R, IN_SMEM, FAST>;
     const size_t base = Cta::SCRATCH_DOUBLES * sizeof(double) + vec_bytes;
     const size_t smem = IN_SMEM ? base + fac_doubles * sizeof(double) : base;
-    int grid = resident_ctas<QpBody<R, IN_SMEM>, pmb_qp_settings_t, QpBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
+    int grid = resident_ctas<Body, pmb_qp_settings_t, QpBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
     if (grid <= 0) { last_error_string() = "qp_box_admm: kernel does not fit on the device"; return false; }
     if (!IN_SMEM) grid = grid > 2 * 148 ? 2 * 148 : grid;      // keep the global factor slots L2 resident
     if (grid > batch) grid = batch;
     FactorStore fs{nullptr, fac_doubles, rt_sm_count()};
     if (!IN_SMEM) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
-    return rt_launch<QpBody<R, IN_SMEM>>(grid, smem, s, st, qb, fs, batch, queue);
+    return rt_launch<Body>(grid, smem, s, st, qb, fs, batch, queue);
 }
+
+/** process-wide default of the arithmetic mode (pmb_set_default_arithmetic): used by pmb_qp_solve and by new SQP handles */
+std::atomic<int> g_default_arithmetic{PMB_ARITH_EXACT};
 
 bool launch_qp(stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int batch, int* queue, DevBuf<double>& scratch)
 {
     const int n = qb.N + qb.M;
     const int R = (n + 31) / 32;
+    if (g_default_arithmetic.load() == PMB_ARITH_FAST) {
+        // fast arithmetic: tile workspace in shared memory (pmb_qp_fast.hpp); sizes whose workspace does not fit are refused
+        const size_t fd = fast::workspace_doubles(n), vb = qp_vec_bytes(qb.N, qb.M);
+        if (Cta::SCRATCH_DOUBLES * sizeof(double) + vb + fd * sizeof(double) > SMEM_CTA_MAX) {
+            last_error_string() = "qp_solve: fast arithmetic needs the tile workspace in shared memory (N + M <= ~220)"; return false;
+        }
+        switch (R) {
+#define PMB_QP_FAST(r) case r: return launch_qp_r<r, true, true>(fd, vb, s, st, qb, batch, queue, scratch);
+        PMB_QP_FAST(1) PMB_QP_FAST(2) PMB_QP_FAST(3) PMB_QP_FAST(4) PMB_QP_FAST(5) PMB_QP_FAST(6) PMB_QP_FAST(7)
+#undef PMB_QP_FAST
+        default: break;
+        }
+        last_error_string() = "qp_solve: fast arithmetic is not instantiated for this size";
+        return false;
+    }
     const size_t fd = qp_factor_doubles(qb.N, qb.M), vb = qp_vec_bytes(qb.N, qb.M);
     if (Cta::SCRATCH_DOUBLES * sizeof(double) + vb > SMEM_CTA_MAX) { last_error_string() = "QP vectors do not fit in shared memory"; return false; }
     const bool in_smem = Cta::SCRATCH_DOUBLES * sizeof(double) + vb + fd * sizeof(double) <= SMEM_CTA_MAX;
@@ -156,6 +176,8 @@ struct pmb_sqp {
     pmb_qp_settings_t qp_settings;
     int opt_exact_hessian = 0, opt_gershgorin = 0;   // pmb_sqp_set_hessian_options
     int opt_block_bfgs = 0;                          // pmb_sqp_set_hessian_update
+    int arithmetic = PMB_ARITH_EXACT;                // pmb_sqp_set_arithmetic
+    int grid_fast = 0;
     bool trace_on = false;                           // pmb_sqp_set_trace
     pmb::stream_t own_stream = nullptr, stream = nullptr;
     pmb::event_t ev0 = nullptr, ev1 = nullptr;
@@ -476,6 +498,7 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
     if (NI > 0) ok = ok && rt_h2d(s->lbg.p, lo.data(), B * NI * sizeof(double), s->stream) && rt_h2d(s->ubg.p, hi.data(), B * NI * sizeof(double), s->stream);
     ok = ok && rt_sync(s->stream);
     if (!ok) return nullptr;
+    if (g_default_arithmetic.load() == PMB_ARITH_FAST && s->ocp.impl->has_fast()) pmb_sqp_set_arithmetic(s.get(), PMB_ARITH_FAST);
     return s.release();
 }
 void pmb_sqp_destroy(pmb_sqp_t* s) { delete s; }
@@ -498,6 +521,30 @@ int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
     s->opt_block_bfgs = mode == PMB_HESSIAN_BFGS_BLOCK;
     return PMB_OK;
 }
+int pmb_set_default_arithmetic(int mode)
+{
+    if (mode != PMB_ARITH_EXACT && mode != PMB_ARITH_FAST) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_default_arithmetic: bad mode");
+    g_default_arithmetic.store(mode);
+    return PMB_OK;
+}
+int pmb_get_default_arithmetic(void) { return g_default_arithmetic.load(); }
+int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode)
+{
+    if (!s || (mode != PMB_ARITH_EXACT && mode != PMB_ARITH_FAST)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_arithmetic: bad argument");
+    if (mode == PMB_ARITH_FAST) {
+        const IProblem& P = *s->ocp.impl;
+        if (!P.has_fast() || P.fast_smem_bytes() > SMEM_CTA_MAX) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_arithmetic: the tile workspace of this problem does not fit in shared memory");
+        if (s->grid_fast == 0) {
+            if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+            int grid = P.fast_resident_ctas();
+            if (grid <= 0) PMB_FAIL(PMB_ERR_CUDA, "set_arithmetic: the fast sqp_solve kernel does not fit on the device");
+            s->grid_fast = grid > s->batch ? s->batch : grid;
+        }
+    }
+    s->arithmetic = mode;
+    return PMB_OK;
+}
+int pmb_sqp_get_arithmetic(const pmb_sqp_t* s) { return s ? s->arithmetic : (int)PMB_ERR_BAD_ARGUMENT; }
 int pmb_sqp_set_trace(pmb_sqp_t* s, int on) { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->trace_on = on != 0; return PMB_OK; }
 
 static int sqp_set_vec(pmb_sqp_t* s, double* dst, const double* v, int stride, size_t len)
@@ -628,7 +675,8 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     }
     // one persistent launch: CTAs draw instances from the queue and run their whole SQP loop on the device
     ok = ok && rt_event_record(s->kev0, st);
-    ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
+    if (s->arithmetic == PMB_ARITH_FAST) ok = ok && s->ocp.impl->launch_solve_fast(s->grid_fast, ws, s->settings, s->qp_settings, B, s->queue.p, st);
+    else ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
     ok = ok && rt_event_record(s->kev1, st);
     ++launches;
     ok = ok && rt_event_record(s->ev1, st);

@@ -82,11 +82,11 @@ struct FactorStore {
 };
 
 /** persistent CTA-per-instance boxADMM: CTAs draw instances from an atomic queue */
-template <int R, bool IN_SMEM>
+template <int R, bool IN_SMEM, bool FAST = false>
 struct QpBody {
     static constexpr int THREADS = 128;
-    static constexpr int MIN_BLOCKS = R <= 4 ? 4 : (R <= 6 ? 2 : 1);
-    static constexpr const char* NAME = "qp_box_admm";
+    static constexpr int MIN_BLOCKS = R <= 4 ? (FAST ? 3 : 4) : (R <= 6 ? 2 : 1);
+    static constexpr const char* NAME = FAST ? "qp_box_admm_fast" : "qp_box_admm";
     static constexpr size_t EMU_STACK_BYTES = 1u << 20;
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, QpBatch qb, FactorStore fs, int batch, int* queue)
     {
@@ -99,7 +99,7 @@ struct QpBody {
             const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (b >= batch) break;
             const QpArgs a = qp_instance(qb, b);
-            qp_solve_cta<R>(c, st, a, Lp, vec);
+            qp_solve_cta<R, 0, 0, 4, FAST>(c, st, a, Lp, vec);
         }
     }
 };
@@ -142,7 +142,7 @@ struct BfgsBody {
         Cta c(w, reinterpret_cast<double*>(smem));
         double* Bs = reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES;
         double* r = Bs + N;
-        const int br = bfgs_update_cta(c, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
+        const int br = bfgs_update_cta<false>(c, N, B + (size_t)b * N * N, s + (size_t)b * N, y + (size_t)b * N, Bs, r);
         if (branch && c.tid() == 0) branch[b] = br;
     }
 };
@@ -169,17 +169,18 @@ struct BlockBfgsBody {
 /** the whole SQPBase::solve of the batch in ONE persistent launch: each CTA draws an instance from the atomic queue and
  *  iterates linearise -> boxADMM -> line search / step on it until it converges (no host round trip per iteration, no
  *  wave quantisation: a slow instance only occupies its own CTA). */
-template <class O>
+template <class O, bool FAST = false>
 struct SqpSolveBody {
 #ifdef PMB_SQP_THREADS
     static constexpr int THREADS = PMB_SQP_THREADS;
 #else
     static constexpr int THREADS = 128;
 #endif
-    static constexpr const char* NAME = "sqp_solve";
+    static constexpr const char* NAME = FAST ? "sqp_solve_fast" : "sqp_solve";
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
     static constexpr int R = (O::N + O::M + 31) / 32;
-    static constexpr size_t FACTOR_DOUBLES = (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
+    /** doubles of the LDL^T workspace: packed lower triangle (exact arithmetic) or the tile workspace of pmb_qp_fast.hpp */
+    static constexpr size_t FACTOR_DOUBLES = FAST ? fast::workspace_doubles(O::N + O::M) : (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
     static constexpr size_t SCRATCH_BYTES = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
     /** resident CTAs per SM the register allocation is asked to allow: at most 3 when the factor lives in shared memory
      *  (168 registers per thread; measured on the mobile robot: 4 CTAs x 128 registers spill inside the QP loops and are
@@ -221,7 +222,7 @@ struct SqpSolveBody {
             const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (b >= batch) break;
             const SqpInst<O> s{ws, b};
-            SqpDev<O>::template solve<R, THREADS / 32>(c, o, s, st, qst, Lp, vec, scratch);
+            SqpDev<O>::template solve<R, THREADS / 32, FAST>(c, o, s, st, qst, Lp, vec, scratch);
         }
     }
 };

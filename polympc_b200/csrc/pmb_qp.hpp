@@ -33,7 +33,7 @@ namespace pmb {
 
 /** optional cycle counters of one QP solve (thread 0's clock): pivot order, gather, factorisation, triangular solves,
  *  ADMM vector updates, residual checks */
-struct QpProf { unsigned long long pivot = 0, gather = 0, factor = 0, solve = 0, update = 0, resid = 0; };
+struct QpProf { unsigned long long pivot = 0, gather = 0, factor = 0, solve = 0, update = 0, resid = 0, f_diag = 0, f_panel = 0, f_trail = 0, f_inv = 0; };
 
 struct QpArgs {
     int N, M;
@@ -57,7 +57,7 @@ inline size_t qp_vec_bytes(int N, int M)
 {
     const size_t n = (size_t)N + M;
     const size_t doubles = 3 * n + 6 * (size_t)N + 4 * (size_t)M + 12;   // + first coefficients of the 10 residual norms
-    return doubles * sizeof(double) + 2 * n * sizeof(int) + 16;
+    return doubles * sizeof(double) + 3 * n * sizeof(int) + 16;   // perm, ctype, inverse perm
 }
 
 PMB_DEV double fmax_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (a < b) ? b : a; }
@@ -105,83 +105,97 @@ PMB_DEV double dot_chain(const double* a, size_t ld, const double* x, int n)
 }
 
 /** replay Eigen's diagonal pivot selection (LDLT.h, ldlt_inplace<Lower>::unblocked: `mat.diagonal().tail(size-k).cwiseAbs()
- *  .maxCoeff(&idx)` then a symmetric swap k <-> idx) on dd, a scratch copy of diag(K); perm[a] = original index at position a.
+ *  .maxCoeff(&idx)` then a symmetric swap k <-> idx) on dd = diag(K); perm[a] = original index at position a.
  *  maxCoeff semantics: the candidate at position k is the initial best (even when it is NaN — then nothing replaces it),
  *  a later position wins only with a strictly larger value (NaN never does).
- *  Executed by warp 0 on registers (lane l owns positions l, l+32, ...): one step = 3 REDUX + 4 SHFL.  Ends with a block
- *  barrier. */
+ *
+ *  Only the ORDER of the |dd| matters, so the block first ranks them (thread i counts the entries smaller than |dd_i|: ties
+ *  share a rank, NaN gets rank 0 = never a candidate) and warp 0 then replays the selection on one 32-bit word per position,
+ *  (rank << 18) | ((511 - position) << 9) | original index: a single REDUX.max per step yields the largest value, the first
+ *  position holding it AND the original index sitting there; one shuffle moves the element displaced from position k.
+ *  ~50 cycles per step instead of ~660 (3 REDUX on 64-bit keys + 4 SHFL).  rk: scratch of n ints.  Ends with a block barrier. */
 template <int R>
-PMB_DEV void ldlt_pivot_order(Cta& c, int n, const double* dd, int* perm)
+PMB_DEV void ldlt_pivot_order(Cta& c, int n, const double* dd, int* perm, int* rk)
 {
+    static_assert(R <= 16, "positions and indices are packed in 9 bits");
+    for (int i = c.tid(); i < n; i += c.nthreads()) {
+        const double v = dm::fabs(dd[i]);
+        int cnt = 1;
+        if (v != v) cnt = 0;
+        else for (int j = 0; j < n; ++j) { const double u = dm::fabs(dd[j]); cnt += (u < v) ? 1 : 0; }
+        rk[i] = cnt;
+    }
+    c.sync();
     if (c.warp_id() == 0) {
         const Warp& w = c.w;
         const int lane = w.lane();
-        // key: 0 = not a candidate (NaN or out of range); otherwise bits(|v|) + 1, order preserving for |v| in [0, inf]
-        unsigned hi[R], lo[R];
-        int pr[R];
+        unsigned pk[R];                                        // packed word of the element currently at position lane + 32 r
         PMB_UNROLL
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
-            uint64_t key = 0;
-            if (i < n) { const double v = dm::fabs(dd[i]); key = (v != v) ? 0 : dm::to_bits(v) + 1; }
-            hi[r] = (unsigned)(key >> 32); lo[r] = (unsigned)key; pr[r] = i;
+            pk[r] = i < n ? (((unsigned)rk[i] << 18) | ((unsigned)(511 - i) << 9) | (unsigned)i) : 0u;
         }
         for (int k = 0; k < n - 1; ++k) {
             const int kr = k >> 5, kl = k & 31;
-            // local best over owned positions >= k (ascending positions: first maximum wins)
-            unsigned bh = 0, bl = 0; int bp = 0x7fffffff;
+            unsigned best = 0;
             PMB_UNROLL
             for (int r = 0; r < R; ++r) {
-                const int i = lane + 32 * r;
-                const bool cand = i >= k && (hi[r] | lo[r]) != 0;
-                if (cand && (hi[r] > bh || (hi[r] == bh && lo[r] > bl))) { bh = hi[r]; bl = lo[r]; bp = i; }
+                const bool cand = (lane + 32 * r) >= k && (pk[r] >> 18) != 0;
+                const unsigned v = cand ? pk[r] : 0u;
+                best = v > best ? v : best;
             }
-            const unsigned mh = w.reduce_max(bh);
-            const unsigned ml = w.reduce_max(bh == mh ? bl : 0u);
-            const bool mine = (bh == mh) && (bl == ml) && bp != 0x7fffffff;
-            int bi = (int)w.reduce_min(mine ? (unsigned)bp : 0x7fffffffu);
-            // key / perm currently at position k
-            unsigned kh = 0, kw = 0; int kp = 0;
+            unsigned atk = 0;
             PMB_UNROLL
-            for (int r = 0; r < R; ++r) if (r == kr) { kh = hi[r]; kw = lo[r]; kp = pr[r]; }
-            kh = (unsigned)w.shfl((int)kh, kl); kw = (unsigned)w.shfl((int)kw, kl); kp = w.shfl(kp, kl);
-            if ((kh | kw) == 0 || (mh | ml) == 0) bi = k;          // NaN at k stays; nothing selectable: no swap
+            for (int r = 0; r < R; ++r) if (r == kr) atk = pk[r];
+            atk = (unsigned)w.shfl((int)atk, kl);              // the element at position k (independent of the reduction)
+            const unsigned m = w.reduce_max(best);
+            const bool stay = (atk >> 18) == 0 || m == 0;      // NaN at k stays; nothing selectable: no swap
+            const int bi = stay ? k : 511 - (int)((m >> 9) & 511u);
+            const unsigned chosen = stay ? atk : m;
             if (bi != k) {
-                const int br = bi >> 5, bl2 = bi & 31;
-                int bperm = 0;
-                PMB_UNROLL
-                for (int r = 0; r < R; ++r) if (r == br) bperm = pr[r];
-                bperm = w.shfl(bperm, bl2);
+                const int br = bi >> 5, bl = bi & 31;
                 PMB_UNROLL
                 for (int r = 0; r < R; ++r) {
-                    if (r == kr && lane == kl) { hi[r] = mh; lo[r] = ml; pr[r] = bperm; }
-                    if (r == br && lane == bl2) { hi[r] = kh; lo[r] = kw; pr[r] = kp; }
+                    if (r == kr && lane == kl) pk[r] = (chosen & ~(511u << 9)) | ((unsigned)(511 - k) << 9);
+                    if (r == br && lane == bl) pk[r] = (atk & ~(511u << 9)) | ((unsigned)(511 - bi) << 9);
                 }
             }
         }
         PMB_UNROLL
-        for (int r = 0; r < R; ++r) { const int i = lane + 32 * r; if (i < n) perm[i] = pr[r]; }
+        for (int r = 0; r < R; ++r) { const int i = lane + 32 * r; if (i < n) perm[i] = (int)(pk[r] & 511u); }
     }
     c.sync();
 }
 
-/** gather P K P^T into the packed lower triangle: columns round-robin over warps, rows over lanes */
+/** gather P K P^T into the packed lower triangle: columns round-robin over warps, rows over lanes; the R loads of a lane are
+ *  independent (memory-level parallelism: H and A come from L2) */
+template <int R>
 PMB_DEV void kkt_gather_permuted(Cta& c, int N, int M, const double* H, const double* A, const double* dK, const int* perm, double* Lp)
 {
     const int n = N + M, lane = c.lane(), nw = c.nwarps();
+    int pa[R];
+    PMB_UNROLL
+    for (int r = 0; r < R; ++r) { const int a = lane + 32 * r; pa[r] = a < n ? perm[a] : 0; }
+    PMB_NOUNROLL
     for (int b = c.warp_id(); b < n; b += nw) {
         const int cc = perm[b];
         double* col = Lp + packed_off(b, n) - b;
-        for (int a = b + lane; a < n; a += 32) {
-            const int r = perm[a];
-            const int hi = r > cc ? r : cc, lo = r > cc ? cc : r;
-            double v;
-            if (hi == lo) v = dK[hi];
-            else if (hi < N) v = H[hi + (size_t)lo * N];
-            else if (lo < N) v = A[(hi - N) + (size_t)lo * M];
-            else v = 0.0;
-            col[a] = v;
+        double v[R];
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int a = lane + 32 * r;
+            double x = 0.0;
+            if (a >= b && a < n) {
+                const int rr = pa[r];
+                const int hi = rr > cc ? rr : cc, lo = rr > cc ? cc : rr;
+                if (hi == lo) x = dK[hi];
+                else if (hi < N) x = H[hi + (size_t)lo * N];
+                else if (lo < N) x = A[(hi - N) + (size_t)lo * M];
+            }
+            v[r] = x;
         }
+        PMB_UNROLL
+        for (int r = 0; r < R; ++r) { const int a = lane + 32 * r; if (a >= b && a < n) col[a] = v[r]; }
     }
     c.sync();
 }
@@ -506,7 +520,13 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
 
 /** the whole boxADMM solve of one instance by one CTA.  Lp: n(n+1)/2 doubles (shared or global), vec: qp_vec_bytes() of
  *  shared memory. */
-template <int R, int NC = 0, int MC = 0, int NW = 4>   // NC, MC: problem size when known at compile time (fused SQP kernel), 0 = a.N, a.M; NW: warps per CTA
+}  // namespace pmb
+#include "pmb_qp_fast.hpp"
+namespace pmb {
+
+/** FAST: the factor workspace Lp is laid out by fast::Ws (fast::workspace_doubles) and the linear algebra runs on the fp64
+ *  tensor cores (pmb_qp_fast.hpp); everything else — classification, rho, ADMM updates, residuals, termination — is shared */
+template <int R, int NC = 0, int MC = 0, int NW = 4, bool FAST = false>   // NC, MC: problem size when known at compile time (fused SQP kernel), 0 = a.N, a.M; NW: warps per CTA
 PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec)
 {
     const int N = NC > 0 ? NC : a.N, M = (NC > 0) ? MC : a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
@@ -526,6 +546,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     double* first = rvi + M;   // [12]
     int* perm = reinterpret_cast<int*>(first + 12);
     int* ctype = perm + n;     // [constr_type (M) ; box_constr_type (N)]
+    int* iperm = ctype + n;    // inverse pivot permutation (fast arithmetic: the right-hand side is kept in pivot order)
     const double *alb = a.Alb, *aub = a.Aub, *xlb = a.xlb, *xub = a.xub;   // bounds stay in global memory (read-only here)
 
     // ---- load, initial iterates (box_admm.hpp:97-100) -----------------------------------------------------------
@@ -568,12 +589,22 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     QpProf* const prof = a.prof;
     auto factorise = [&]() {
         const unsigned long long t0 = prof ? c.w.clock() : 0;
-        ldlt_pivot_order<R>(c, n, dK, perm);
+        ldlt_pivot_order<R>(c, n, dK, perm, reinterpret_cast<int*>(tmp));
         if (n_factor == 0 && a.perm) { for (int i = tid; i < n; i += nt) a.perm[i] = perm[i]; }
+        if (FAST) { for (int i = tid; i < n; i += nt) iperm[perm[i]] = i; }
         const unsigned long long t1 = prof ? c.w.clock() : 0;
-        kkt_gather_permuted(c, N, M, a.H, a.A, dK, perm, Lp);
+        if (FAST) fast::gather<R>(c, N, M, a.H, a.A, dK, perm, fast::Ws(Lp, n));
+        else kkt_gather_permuted<R>(c, N, M, a.H, a.A, dK, perm, Lp);
         const unsigned long long t2 = prof ? c.w.clock() : 0;
-        ldlt_factor_packed<R>(c, n, Lp);
+        if (FAST) {
+            const fast::Ws fw(Lp, n);
+            fast::FactorProf fp;
+            fast::factor(c, fw, prof ? &fp : nullptr);
+            const unsigned long long ti = prof ? c.w.clock() : 0;
+            fast::invert(c, fw);
+            if (prof) { prof->f_diag += fp.diag; prof->f_panel += fp.panel; prof->f_trail += fp.trail; prof->f_inv += c.w.clock() - ti; }
+        }
+        else ldlt_factor_packed<R>(c, n, Lp);
         if (prof) { const unsigned long long t3 = c.w.clock(); prof->pivot += t1 - t0; prof->gather += t2 - t1; prof->factor += t3 - t2; }
         ++n_factor;
     };
@@ -639,16 +670,31 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
     bool need_factor = true;
     int iter;
     for (iter = 1; ; ++iter) {
-        if (need_factor) { factorise(); need_factor = false; }
+        if (need_factor) {
+            factorise(); need_factor = false;
+            if (FAST) {   // compute_kkt_rhs (351-355) in pivot order, padded to whole tiles; later trips refresh it inside the update phase
+                const fast::Ws fw(Lp, n);
+                for (int e = tid; e < fw.T * 8; e += nt) {
+                    double v = 0.0;
+                    if (e < n) { const int i = perm[e]; v = i < N ? ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i] : z[i - N] - rvi[i - N] * ya[i - N]; }
+                    fw.tb[e] = v;
+                }
+                c.sync();
+            }
+        }
         if (iter > st.max_iter) break;
         const unsigned long long ta = prof ? c.w.clock() : 0;
-        // compute_kkt_rhs (351-355)
-        for (int i = tid; i < N; i += nt) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
-        for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
-        c.sync();
+        if (!FAST) {
+            // compute_kkt_rhs (351-355)
+            for (int i = tid; i < N; i += nt) sol[i] = ((sigma * x[i] - h[i]) + rb[i] * q[i]) - yb[i];
+            for (int i = tid; i < M; i += nt) sol[N + i] = z[i] - rvi[i] * ya[i];
+            c.sync();
+        }
         const unsigned long long tb = prof ? c.w.clock() : 0;
-        ldlt_solve_packed<R, NW>(c, n, Lp, perm, sol, tmp);
+        if (FAST) fast::solve_rows<(4 * R + NW - 1) / NW, NW>(c, fast::Ws(Lp, n), perm, sol);   // T <= 4 R tile rows, dealt round-robin
+        else ldlt_solve_packed<R, NW>(c, n, Lp, perm, sol, tmp);
         const unsigned long long tc = prof ? c.w.clock() : 0;
+        double* const tbn = FAST ? fast::Ws(Lp, n).tb : nullptr;      // fast arithmetic: the next trip's right-hand side, pivot order
         // z, y_A (126, 133-135, 142-144)
         for (int i = tid; i < M; i += nt) {
             const double zp = z[i];
@@ -656,8 +702,10 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
             double v = alpha * zt;
             v += ((1 - alpha) * zp) + (rvi[i] * ya[i]);
             const double zn = dm::min(dm::max(v, alb[i]), aub[i]);
-            ya[i] += rv[i] * (((alpha * zt) + ((1 - alpha) * zp)) - zn);
+            const double yn = ya[i] + rv[i] * (((alpha * zt) + ((1 - alpha) * zp)) - zn);
+            ya[i] = yn;
             z[i] = zn;
+            if (FAST) tbn[iperm[N + i]] = zn - rvi[i] * yn;
         }
         // x, q, y_box (129-130, 138-139, 146-147)
         for (int i = tid; i < N; i += nt) {
@@ -666,7 +714,9 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
             x[i] = xv;
             const double qv = dm::min(dm::max(xv + rbi[i] * yb[i], xlb[i]), xub[i]);
             q[i] = qv;
-            yb[i] += rb[i] * (xv - qv);
+            const double ybn = yb[i] + rb[i] * (xv - qv);
+            yb[i] = ybn;
+            if (FAST) tbn[iperm[i]] = ((sigma * xv - h[i]) + rb[i] * qv) - ybn;
         }
         c.sync();
         if (prof) { const unsigned long long td = c.w.clock(); prof->update += (tb - ta) + (td - tc); prof->solve += tc - tb; }

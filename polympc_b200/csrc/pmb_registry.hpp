@@ -29,6 +29,12 @@ struct IProblem {
     /** one persistent launch that solves `batch` instances (grid CTAs draw them from `queue`) */
     virtual bool launch_solve(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
+    /** the same kernel in fast arithmetic (pmb_qp_fast.hpp); only for problems whose tile workspace fits in shared memory */
+    virtual bool has_fast() const = 0;
+    virtual size_t fast_smem_bytes() const = 0;
+    virtual int fast_resident_ctas() const = 0;
+    virtual bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
+                                   int batch, int* queue, stream_t s) const = 0;
 };
 
 template <class O>
@@ -75,6 +81,25 @@ struct ProblemImpl : IProblem {
     {
         FactorStore fs{Solve::IN_SMEM ? nullptr : factor_scratch, Solve::FACTOR_DOUBLES, rt_sm_count()};
         return rt_launch<Solve>(grid, Solve::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
+    }
+    using SolveFast = SqpSolveBody<O, true>;
+    static constexpr bool HAS_FAST = SolveFast::IN_SMEM;
+    bool has_fast() const override { return HAS_FAST; }
+    size_t fast_smem_bytes() const override { return HAS_FAST ? SolveFast::smem_bytes() : 0; }
+    int fast_resident_ctas() const override
+    {
+        if constexpr (HAS_FAST)
+            return resident_ctas<SolveFast, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
+                SolveFast::smem_bytes(), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
+        else return 0;
+    }
+    bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, int batch, int* queue,
+                           stream_t s) const override
+    {
+        if constexpr (HAS_FAST) {
+            FactorStore fs{nullptr, SolveFast::FACTOR_DOUBLES, rt_sm_count()};
+            return rt_launch<SolveFast>(grid, SolveFast::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
+        } else { last_error_string() = "fast arithmetic: the tile workspace of this problem does not fit in shared memory"; return false; }
     }
 };
 

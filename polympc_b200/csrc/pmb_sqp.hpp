@@ -22,15 +22,19 @@ PMB_DEV double dot_tree32(Cta& c, const double* a, const double* b, int n)
  *  exact and order free; the first-coefficient rule is applied afterwards. */
 PMB_DEV double norm_inf_cta(Cta& c, const double* a, int n)
 {
-    double m = 0.0;
-    for (int i = c.tid(); i < n; i += c.nthreads()) { const double v = dm::fabs(a[i]); if (v > m) m = v; }
-    m = c.max_all1(m);
-    const double a0 = dm::fabs(a[0]);
-    return (a0 != a0) ? a0 : m;
+    double m[2] = {0.0, 0.0};                                   // [1]: flag "the first coefficient is NaN"
+    for (int i = c.tid(); i < n; i += c.nthreads()) {
+        const double v = dm::fabs(a[i]);
+        if (v > m[0]) m[0] = v;
+        if (i == 0 && v != v) m[1] = 1.0;
+    }
+    c.max_all<2>(m);
+    return m[1] > 0.0 ? dm::fabs(a[0]) : m[0];                  // (the load only happens on the NaN path)
 }
 
 /** bfgs.hpp:23-52.  B (n x n, column-major) is updated in place; Bs, r: scratch of n doubles each (shared memory).
  *  Returns 0 plain, 1 damped, 2 skipped (uniform over the block). */
+template <bool FAST = false>
 PMB_DEV int bfgs_update_cta(Cta& c, int n, double* B, const double* s, const double* y, double* Bs, double* r)
 {
     const int tid = c.tid(), nt = c.nthreads();
@@ -52,12 +56,18 @@ PMB_DEV int bfgs_update_cta(Cta& c, int n, double* B, const double* s, const dou
     }
     c.sync();
     if (sr < DBL_EPSILON) return 2;
-    for (int e = tid; e < n * n; e += nt) {
-        const int j = e / n, i = e - j * n;
-        double b = B[e];
-        b += ((-Bs[i]) * Bs[j]) / sBs;
-        b += (r[i] * r[j]) / sr;
-        B[e] = b;
+    // columns over the warps, rows over the lanes (no integer division per element).  Exact arithmetic divides per element like
+    // bfgs.hpp:48-49 (`-Bs Bs^T / sBs`, `r r^T / sr`); fast arithmetic multiplies by the two reciprocals instead.
+    const double isBs = FAST ? 1.0 / sBs : 0.0, isr = FAST ? 1.0 / sr : 0.0;
+    for (int j = c.warp_id(); j < n; j += c.nwarps()) {
+        const double bsj = Bs[j], rj = r[j];
+        double* col = B + (size_t)j * n;
+        for (int i = c.lane(); i < n; i += 32) {
+            double b = col[i];
+            if (FAST) { b += ((-Bs[i]) * bsj) * isBs; b += (r[i] * rj) * isr; }
+            else { b += ((-Bs[i]) * bsj) / sBs; b += (r[i] * rj) / sr; }
+            col[i] = b;
+        }
     }
     c.sync();
     return branch;
@@ -215,6 +225,7 @@ struct SqpDev {
 
     /** first (exact Hessian) or later (BFGS) linearisation + QP bounds (sqp_base.hpp:583-593, 649-657, 489-504) */
     /** returns the cost at x (the value every linearisation computes on the way) */
+    template <bool FAST = false>
     PMB_DEV static double linearise(Cta& c, const O& o, const SqpInst<O>& s, bool first, int trace_row, double* scratch)
     {
         const int tid = c.tid(), nt = c.nthreads();
@@ -245,7 +256,7 @@ struct SqpDev {
             for (int i = tid; i < N; i += nt) yv[i] = lg[i] - s.lag_grad()[i];
             c.sync();
             const int br = s.ws.opt_block_bfgs ? block_bfgs_update_cta<O>(c, s.H(), s.step_prev(), yv, Bs, r)
-                                               : bfgs_update_cta(c, N, s.H(), s.step_prev(), yv, Bs, r);
+                                               : bfgs_update_cta<FAST>(c, N, s.H(), s.step_prev(), yv, Bs, r);
             if (s.tr_bfgs() && tid == 0) s.tr_bfgs()[trace_row] = br;
             for (int i = tid; i < N; i += nt) s.lag_grad()[i] = lg[i];
         }
@@ -375,7 +386,7 @@ struct SqpDev {
 
     /** SQPBase::solve (sqp_base.hpp:568-696) of one instance: iterate linearise -> QP -> line search / step until the
      *  termination test holds or max_iter QPs were solved.  Lp / vec: QP workspaces (pmb_qp.hpp), scratch: SCRATCH_DOUBLES. */
-    template <int R, int NW>
+    template <int R, int NW, bool FAST = false>
     PMB_DEV static void solve(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* Lp, unsigned char* vec, double* scratch)
     {
@@ -391,9 +402,9 @@ struct SqpDev {
         for (int it = 1; ; ++it) {                   // the first iteration always runs (sqp_base.hpp:583-637 precede the loop)
             const int row = it - 1;
             const unsigned long long t0 = c.w.clock();
-            const double cost_x = linearise(c, o, s, it == 1 || s.ws.opt_exact_hessian != 0, row, scratch);
+            const double cost_x = linearise<FAST>(c, o, s, it == 1 || s.ws.opt_exact_hessian != 0, row, scratch);
             const unsigned long long t1 = c.w.clock();
-            qp_solve_cta<R, N, M, NW>(c, qst, qa, Lp, vec);
+            qp_solve_cta<R, N, M, NW, FAST>(c, qst, qa, Lp, vec);
             const unsigned long long t2 = c.w.clock();
             const bool done = step(c, o, s, st, row, scratch, cost_x);
             const unsigned long long t3 = c.w.clock();
@@ -407,6 +418,7 @@ struct SqpDev {
             atomic_add_u64(s.phase() + 4, qprof.pivot); atomic_add_u64(s.phase() + 5, qprof.gather); atomic_add_u64(s.phase() + 6, qprof.factor);
             atomic_add_u64(s.phase() + 7, qprof.solve); atomic_add_u64(s.phase() + 8, qprof.update); atomic_add_u64(s.phase() + 9, qprof.resid);
             atomic_add_u64(s.phase() + 10, (unsigned long long)s.info()->qp_solver_iter);
+            atomic_add_u64(s.phase() + 12, qprof.f_diag); atomic_add_u64(s.phase() + 13, qprof.f_panel); atomic_add_u64(s.phase() + 14, qprof.f_trail); atomic_add_u64(s.phase() + 15, qprof.f_inv);
         }
         c.sync();
     }

@@ -46,6 +46,12 @@ struct Warp {
     /** warp-wide integer reductions (REDUX.SYNC) */
     PMB_DEV unsigned reduce_max(unsigned v) const { return __reduce_max_sync(0xffffffffu, v); }
     PMB_DEV unsigned reduce_min(unsigned v) const { return __reduce_min_sync(0xffffffffu, v); }
+    /** fp64 tensor-core tile product D = A (8 x 4) B (4 x 8) + C (8 x 8): lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+     *  C[l >> 2][2 (l & 3) + {0, 1}]  (mma.sync.m8n8k4.f64, SASS DMMA) */
+    PMB_DEV void dmma(double& c0, double& c1, double a, double b) const
+    {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    }
 };
 
 PMB_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
@@ -114,7 +120,7 @@ struct EmuBlock {
     std::vector<ucontext_t> ctx;
     ucontext_t main_ctx;
     std::vector<char> done;
-    std::vector<uint64_t> slot;
+    std::vector<uint64_t> slot, slot2;
     std::vector<unsigned char> pred;
     struct Bar { int count = 0; int gen = 0; };
     Bar block_bar;
@@ -143,7 +149,7 @@ struct EmuBlock {
     void run(int n, size_t stack_bytes, std::function<void(int)> f)
     {
         nthreads = n; body = std::move(f);
-        ctx.assign(n, ucontext_t()); done.assign(n, 0); slot.assign(n, 0); pred.assign(n, 0);
+        ctx.assign(n, ucontext_t()); done.assign(n, 0); slot.assign(n, 0); slot2.assign(n, 0); pred.assign(n, 0);
         block_bar = Bar(); warp_bar.assign((n + 31) / 32, Bar());
         stacks = (char*)std::malloc(stack_bytes * (size_t)n);
         EmuBlock* prev = current();
@@ -215,6 +221,22 @@ struct Warp {
         return m;
     }
     unsigned reduce_min(unsigned v) const { return ~reduce_max(~v); }
+    /** emulated mma.m8n8k4.f64: c += sum_kk a[r][kk] b[kk][n] as an ascending fused chain (the hardware's internal order is not
+     *  specified; the fast-arithmetic path is tolerance-checked, not bit-checked) */
+    void dmma(double& c0, double& c1, double a, double bv) const
+    {
+        b->slot[t] = dm::to_bits(a); b->slot2[t] = dm::to_bits(bv);
+        sync();
+        const int base = t & ~31, l = t & 31, r = l >> 2, q = l & 3;
+        for (int i = 0; i < 2; ++i) {
+            const int n = 2 * q + i;
+            double acc = i ? c1 : c0;
+            for (int kk = 0; kk < 4; ++kk)
+                acc = dm::fma(dm::from_bits(b->slot[base + r * 4 + kk]), dm::from_bits(b->slot2[base + n * 4 + kk]), acc);
+            (i ? c1 : c0) = acc;
+        }
+        sync();
+    }
     bool any(bool p) const { return ballot(p) != 0; }
     bool all(bool p) const { const unsigned m = ballot(p); const int cnt = (b->nthreads - (t & ~31)) >= 32 ? 32 : (b->nthreads - (t & ~31)); return m == (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)); }
 };

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(NT, 4) phases(int n, const double* Kin, long l
     for (int i = threadIdx.x; i < n; i += NT) { dK[i] = Kin[packed_off(i, n)]; sol[i] = 1.0 + i; }
     __syncthreads();
     long long t0 = clock64();
-    ldlt_pivot_order<R>(c, n, dK, perm);
+    ldlt_pivot_order<R>(c, n, dK, perm, reinterpret_cast<int*>(dK + 4 * n));
     long long t1 = clock64();
     for (int i = threadIdx.x; i < n; i += NT) perm[i] = i;
     __syncthreads();

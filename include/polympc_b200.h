@@ -200,6 +200,13 @@ int pmb_set_default_arithmetic(int mode);
 int pmb_get_default_arithmetic(void);
 int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode);
 int pmb_sqp_get_arithmetic(const pmb_sqp_t* s);
+/* Order in which the persistent kernel's CTAs take instances off the work queue.  Results never depend on it.
+ *   PMB_SCHEDULE_FIFO         instance index order;
+ *   PMB_SCHEDULE_LPT_HISTORY  (default) from the second solve of a handle on: descending SQP iteration count of the PREVIOUS
+ *                             solve (longest processing time first) — a fleet that is re-solved every control period keeps its
+ *                             hard instances, so their long chains start at t = 0 instead of forming the tail of the batch. */
+typedef enum pmb_schedule { PMB_SCHEDULE_FIFO = 0, PMB_SCHEDULE_LPT_HISTORY = 1 } pmb_schedule_t;
+int pmb_sqp_set_schedule(pmb_sqp_t* s, int schedule);
 /* per-iteration decision traces (pmb_sqp_get_trace) are recorded only when switched on before the solve (default off:
  * they cost batch x max_iter rows of device memory and five memsets per solve) */
 int pmb_sqp_set_trace(pmb_sqp_t* s, int on);

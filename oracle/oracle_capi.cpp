@@ -425,6 +425,7 @@ int pmb_set_default_arithmetic(int mode) { return mode == PMB_ARITH_EXACT ? PMB_
 int pmb_get_default_arithmetic(void) { return PMB_ARITH_EXACT; }
 int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode) { return !s ? PMB_ERR_BAD_ARGUMENT : (mode == PMB_ARITH_EXACT ? PMB_OK : PMB_ERR_UNSUPPORTED); }
 int pmb_sqp_get_arithmetic(const pmb_sqp_t* s) { return s ? (int)PMB_ARITH_EXACT : (int)PMB_ERR_BAD_ARGUMENT; }
+int pmb_sqp_set_schedule(pmb_sqp_t* s, int) { return s ? PMB_OK : PMB_ERR_BAD_ARGUMENT; }   /* no queue in the oracle */
 int pmb_sqp_set_trace(pmb_sqp_t* s, int) { return s ? PMB_OK : PMB_ERR_BAD_ARGUMENT; }   /* the oracle always records its traces */
 /* the oracle has no kernels to register: problem classes are added to its own table (REG above) */
 int pmb_register_problem(const char*, void* (*)(void)) { g_err = "the oracle does not register external problems"; return PMB_ERR_BAD_ARGUMENT; }

@@ -58,7 +58,7 @@ ABI_FUNCTIONS = [
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
@@ -131,6 +131,7 @@ class CApi:
         g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
         g("sqp_set_hessian_update").argtypes = [C.c_void_p, C.c_int]
         g("sqp_set_trace").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_set_schedule").argtypes = [C.c_void_p, C.c_int]
         g("set_default_arithmetic").argtypes = [C.c_int]
         g("sqp_set_arithmetic").argtypes = [C.c_void_p, C.c_int]
         g("sqp_get_arithmetic").argtypes = [C.c_void_p]
@@ -446,6 +447,10 @@ class Sqp:
     def set_arithmetic(self, mode: int):
         """0 = PMB_ARITH_EXACT (bit-identical to the oracle), 1 = PMB_ARITH_FAST (fp64 tensor-core LDL^T, rounding-level differences)"""
         self.api._chk(self.api._fn("sqp_set_arithmetic")(self.h, int(mode)), "sqp_set_arithmetic")
+
+    def set_schedule(self, schedule: int):
+        """0 = FIFO, 1 = longest-processing-time-first from the previous solve's iteration counts (default)"""
+        self.api._chk(self.api._fn("sqp_set_schedule")(self.h, int(schedule)), "sqp_set_schedule")
 
     def set_trace(self, on: bool = True):
         """record the per-iteration decision traces read by trace() (off by default)"""

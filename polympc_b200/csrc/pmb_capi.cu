@@ -177,6 +177,9 @@ struct pmb_sqp {
     int opt_exact_hessian = 0, opt_gershgorin = 0;   // pmb_sqp_set_hessian_options
     int opt_block_bfgs = 0;                          // pmb_sqp_set_hessian_update
     int arithmetic = PMB_ARITH_EXACT;                // pmb_sqp_set_arithmetic
+    int schedule = PMB_SCHEDULE_LPT_HISTORY;         // pmb_sqp_set_schedule
+    bool have_history = false;                       // info holds the iteration counts of a completed solve of this handle
+    pmb::DevBuf<int> order;
     int grid_fast = 0;
     bool trace_on = false;                           // pmb_sqp_set_trace
     pmb::stream_t own_stream = nullptr, stream = nullptr;
@@ -544,6 +547,12 @@ int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode)
     s->arithmetic = mode;
     return PMB_OK;
 }
+int pmb_sqp_set_schedule(pmb_sqp_t* s, int schedule)
+{
+    if (!s || (schedule != PMB_SCHEDULE_FIFO && schedule != PMB_SCHEDULE_LPT_HISTORY)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_schedule: bad argument");
+    s->schedule = schedule;
+    return PMB_OK;
+}
 int pmb_sqp_get_arithmetic(const pmb_sqp_t* s) { return s ? s->arithmetic : (int)PMB_ERR_BAD_ARGUMENT; }
 int pmb_sqp_set_trace(pmb_sqp_t* s, int on) { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->trace_on = on != 0; return PMB_OK; }
 
@@ -668,6 +677,13 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     if (rows > 0) { ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p; }
     ws.trace_rows = rows;
     ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin; ws.opt_block_bfgs = s->opt_block_bfgs;
+    ws.order = nullptr;
+    if (s->schedule == PMB_SCHEDULE_LPT_HISTORY && s->have_history && B > s->grid) {
+        // longest-processing-time-first from the previous solve's iteration counts (still in s->info at this point of the stream)
+        ok = ok && s->order.resize(B) && rt_launch<LptOrderBody>(1, LptOrderBody::SMEM, st, B, (const pmb_sqp_info_t*)s->info.p, s->order.p);
+        ws.order = s->order.p;
+        ++launches;
+    }
     ws.phase = nullptr;
     if (s->profiling) {
         ok = ok && s->phase.resize(16) && rt_memset(s->phase.p, 0, 16 * sizeof(unsigned long long), st);
@@ -682,6 +698,7 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     ok = ok && rt_event_record(s->ev1, st);
     if (!ok) return PMB_ERR_CUDA;
     s->last_launches = launches;
+    s->have_history = true;                 // stream order: the next solve's lpt_order kernel runs after this solve
     return PMB_OK;
 }
 

@@ -165,6 +165,33 @@ struct BlockBfgsBody {
     }
 };
 
+// ---- work-queue order: longest processing time first, from the iteration counts of the previous solve -------------------
+/** The persistent sqp_solve kernel is a list scheduler: CTAs take instances off a queue.  With a few instances that need 10x
+ *  the iterations of the rest (0.4 % of the robot sweep run all 100), the makespan of a batch is bulk + the longest chain that
+ *  happened to start late.  Re-solving the same fleet (closed-loop MPC; every timed step of bench.py) the previous solve's
+ *  iteration counts are an excellent predictor, so the queue is served in descending order of them (LPT rule): the long chains
+ *  start at t = 0 and overlap with the bulk.  Counting sort by iteration count, one block.  Results do not depend on the order. */
+struct LptOrderBody {
+    static constexpr int THREADS = 1024;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int MAX_KEY = 1023;
+    static constexpr size_t SMEM = (MAX_KEY + 2) * sizeof(int);
+    static constexpr const char* NAME = "lpt_order";
+    static constexpr size_t EMU_STACK_BYTES = 64u << 10;
+    PMB_DEV static void run(const Warp& w, int, unsigned char* smem, int batch, const pmb_sqp_info_t* info, int* order)
+    {
+        int* bin = reinterpret_cast<int*>(smem);                   // bin[k]: instances with key k, later the write cursor
+        const int tid = w.tid(), nt = w.nthreads();
+        for (int k = tid; k <= MAX_KEY + 1; k += nt) bin[k] = 0;
+        w.block_sync();
+        for (int b = tid; b < batch; b += nt) { int k = info[b].iter; k = k < 0 ? 0 : (k > MAX_KEY ? MAX_KEY : k); atomic_add(bin + k, 1); }
+        w.block_sync();
+        if (tid == 0) { int run = 0; for (int k = MAX_KEY; k >= 0; --k) { const int cnt = bin[k]; bin[k] = run; run += cnt; } }   // descending keys first
+        w.block_sync();
+        for (int b = tid; b < batch; b += nt) { int k = info[b].iter; k = k < 0 ? 0 : (k > MAX_KEY ? MAX_KEY : k); order[atomic_add(bin + k, 1)] = b; }
+    }
+};
+
 // ---- SQP pipeline ---------------------------------------------------------------------------------------------------
 /** the whole SQPBase::solve of the batch in ONE persistent launch: each CTA draws an instance from the atomic queue and
  *  iterates linearise -> boxADMM -> line search / step on it until it converges (no host round trip per iteration, no
@@ -219,8 +246,9 @@ struct SqpSolveBody {
             vec = base + (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES);
         }
         for (;;) {
-            const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
-            if (b >= batch) break;
+            const int ticket = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
+            if (ticket >= batch) break;
+            const int b = ws.order ? ws.order[ticket] : ticket;
             const SqpInst<O> s{ws, b};
             SqpDev<O>::template solve<R, THREADS / 32, FAST>(c, o, s, st, qst, Lp, vec, scratch);
         }

@@ -202,46 +202,44 @@ PMB_DEV void factor(Cta& c, const Ws& w, FactorProf* prof = nullptr)
         const unsigned long long t2 = prof ? wp.clock() : 0;
         if (prof) prof->panel += t2 - t1;
         {   // trailing update with look-ahead
-            const int m = T - 1 - k;
-            const int cnt = ((m * (m + 1)) >> 1) - 1;                 // all tiles except (k+1, k+1)
             const int dw = (k + 1) % nw;                              // the warp that factors the next diagonal tile
-            auto update = [&](int I, int J, int I2, int J2, bool two) {
-                const double* la = w.tile(I, k);
-                const double* ub = w.upanel + J * 64;
-                const double* la2 = w.tile(I2, k);
-                const double* ub2 = w.upanel + J2 * 64;
-                d2* ct = reinterpret_cast<d2*>(w.tile(I, J) + cl);
-                d2* ct2 = reinterpret_cast<d2*>(w.tile(I2, J2) + cl);
-                const double a0 = la[lane], a1 = la[32 + lane], b0 = ub[lane], b1 = ub[32 + lane];
-                const double e0 = la2[lane], e1 = la2[32 + lane], f0 = ub2[lane], f1 = ub2[32 + lane];
-                d2 cv = *ct, cw = *ct2;
-                wp.dmma(cv.x, cv.y, a0, b0);
-                wp.dmma(cw.x, cw.y, e0, f0);
-                wp.dmma(cv.x, cv.y, a1, b1);
-                wp.dmma(cw.x, cw.y, e1, f1);
-                *ct = cv;
-                if (two) *ct2 = cw;
-            };
+            const int workers = nw > 1 ? nw - 1 : 1;
+            const int me = nw > 1 ? (wid + nw - dw - 1) % nw : 0;     // 0 .. nw-2 for the workers, nw-1 for the warp of the diagonal tile
             if (wid == dw) {
-                if (k >= 0) update(k + 1, k + 1, k + 1, k + 1, false);
-                wp.sync();
+                if (k >= 0) {                                         // tile (k+1, k+1) first ...
+                    const double* la = w.tile(k + 1, k);
+                    const double* ub = w.upanel + (k + 1) * 64;
+                    d2* ct = reinterpret_cast<d2*>(w.tile(k + 1, k + 1) + cl);
+                    d2 cv = *ct;
+                    wp.dmma(cv.x, cv.y, la[lane], ub[lane]);
+                    wp.dmma(cv.x, cv.y, la[32 + lane], ub[32 + lane]);
+                    *ct = cv;
+                }
+                wp.sync();                                            // ... then its factorisation, while the others stream the rest
                 factor_diag_tile(wp, w.tile(k + 1, k + 1), w.dinv + 8 * (k + 1), w.rfac + ((k + 1) & 1) * 16, w.wfrag + ((k + 1) & 1) * 64);
             }
-            // the remaining tiles, index t = i (i + 1) / 2 + j - 1 over i >= 1 (I = k + 1 + i, J = k + 1 + j): dealt to the other warps,
-            // or to everybody when the block has a single warp
-            const int workers = nw > 1 ? nw - 1 : 1;
-            const int me = nw > 1 ? (wid + nw - dw - 1) % nw : 0;     // 0 .. nw-2 for the workers, nw-1 for the diagonal warp
-            if (me < workers && k >= 0) {
-                int i = 1, j = me;
-                while (j > i) { j -= i + 1; ++i; }
-                for (int t = me; t < cnt; t += 2 * workers) {
-                    int i2 = i, j2 = j + workers;
-                    while (j2 > i2) { j2 -= i2 + 1; ++i2; }
-                    const bool two = t + workers < cnt;
-                    if (!two) { i2 = i; j2 = j; }
-                    update(k + 1 + i, k + 1 + j, k + 1 + i2, k + 1 + j2, two);
-                    i = i2; j = j2 + workers;
-                    while (j > i) { j -= i + 1; ++i; }
+            if (k >= 0 && (me < workers || nw == 1)) {
+                // tile columns J = k+1 .. T-1; within a column the rows I >= J (I > J for the first column) are dealt to the
+                // workers; the B fragments (-U_Jk) are loaded once per column, two tiles are in flight per step
+                for (int J = k + 1; J < T; ++J) {
+                    const double* ub = w.upanel + J * 64;
+                    const double b0 = ub[lane], b1 = ub[32 + lane];
+                    const int first = (J == k + 1 ? J + 1 : J) + me;
+                    for (int I = first; I < T; I += 2 * workers) {
+                        const int I2 = I + workers < T ? I + workers : I;
+                        const double* la = w.tile(I, k);
+                        const double* la2 = w.tile(I2, k);
+                        d2* ct = reinterpret_cast<d2*>(w.tile(I, J) + cl);
+                        d2* ct2 = reinterpret_cast<d2*>(w.tile(I2, J) + cl);
+                        const double a0 = la[lane], a1 = la[32 + lane], e0 = la2[lane], e1 = la2[32 + lane];
+                        d2 cv = *ct, cw = *ct2;
+                        wp.dmma(cv.x, cv.y, a0, b0);
+                        wp.dmma(cw.x, cw.y, e0, b0);
+                        wp.dmma(cv.x, cv.y, a1, b1);
+                        wp.dmma(cw.x, cw.y, e1, b1);
+                        *ct = cv;
+                        if (I2 != I) *ct2 = cw;
+                    }
                 }
             }
         }
@@ -277,31 +275,30 @@ PMB_DEV void invert(Cta& c, const Ws& w)
     };
     if (T > 1) m_row(1);
     c.sync();
-    constexpr int MAXC = 4;
     PMB_NOUNROLL
     for (int I = 1; I < T; ++I) {
         const double* mb = w.upanel + (I & 1) * T * 64;
-        for (int base = 0; base < I; base += MAXC * nw) {
-            double acc0[MAXC], acc1[MAXC];
-            PMB_UNROLL
-            for (int s = 0; s < MAXC; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
-            for (int K = base + wid; K < I; ++K) {
-                const double a0 = mb[K * 64 + lane], a1 = mb[K * 64 + 32 + lane];
-                PMB_UNROLL
-                for (int s = 0; s < MAXC; ++s) {
-                    const int J = base + wid + s * nw;
-                    if (J <= K) {                                     // warp-uniform (J <= K < I)
-                        const double* xt = w.tile(K, J);
-                        wp.dmma(acc0[s], acc1[s], a0, xt[bl0]);
-                        wp.dmma(acc0[s], acc1[s], a1, xt[bl1]);
-                    }
-                }
+        // the warp's columns J = wid, wid + nw, ...: X_IJ = -sum_{K = J}^{I-1} M_IK X_KJ as two independent accumulator chains
+        // (even / odd K); nobody reads tile row I in this phase, so the result is stored right away
+        for (int J = wid; J < I; J += nw) {
+            double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+            int K = J;
+            for (; K + 1 < I; K += 2) {
+                const double* xt = w.tile(K, J);
+                const double* xu = w.tile(K + 1, J);
+                const double* ma = mb + K * 64;
+                wp.dmma(e0, e1, ma[lane], xt[bl0]);
+                wp.dmma(o0, o1, ma[64 + lane], xu[bl0]);
+                wp.dmma(e0, e1, ma[32 + lane], xt[bl1]);
+                wp.dmma(o0, o1, ma[96 + lane], xu[bl1]);
             }
-            PMB_UNROLL
-            for (int s = 0; s < MAXC; ++s) {
-                const int J = base + wid + s * nw;
-                if (J < I) *reinterpret_cast<d2*>(w.tile(I, J) + cl) = d2{-acc0[s], -acc1[s]};
+            if (K < I) {
+                const double* xt = w.tile(K, J);
+                const double* ma = mb + K * 64;
+                wp.dmma(e0, e1, ma[lane], xt[bl0]);
+                wp.dmma(e0, e1, ma[32 + lane], xt[bl1]);
             }
+            *reinterpret_cast<d2*>(w.tile(I, J) + cl) = d2{-(e0 + o0), -(e1 + o1)};
         }
         if (I + 1 < T) m_row(I + 1);
         c.sync();
@@ -324,19 +321,30 @@ PMB_DEV void solve_rows(Cta& c, const Ws& w, const int* perm, double* sol)
     const int T = w.T, n = w.n, lane = c.lane(), wid = c.warp_id();
     const int h = lane >> 4, r8 = (lane >> 1) & 7, jj = lane & 1;
     const d2* tl = reinterpret_cast<const d2*>(w.tiles) + lane;          // pair `lane` of tile number t: tl[32 t]
+    // The warp's tile rows are I_s = wid + NW s.  Row I_s has tiles J = 0 .. I_s, so over the J loop the set of active rows only
+    // shrinks: segment `seg` covers the J for which exactly the rows s >= seg are active.  Inside a segment there is no
+    // predicate at all: the loads of a step are independent and pipeline (with a per-row `if` the compiler emitted branches
+    // and serialised the shared-memory latencies: 9.4 k instead of 4.7 k cycles per solve pair).  Rows beyond T (last warps)
+    // are clamped to row T - 1: they compute garbage that is never stored.
     {
         const d2* tv = reinterpret_cast<const d2*>(w.tb) + 2 * h + jj;
         double a0[RS], a1[RS];
         int base[RS];
         PMB_UNROLL
-        for (int s = 0; s < RS; ++s) { a0[s] = 0.0; a1[s] = 0.0; const int I = wid + NW * s; base[s] = 32 * ((I * (I + 1)) / 2); }
-        PMB_NOUNROLL
-        for (int J = 0; J < T; ++J) {
-            const d2 t = tv[4 * J];
-            PMB_UNROLL
-            for (int s = 0; s < RS; ++s) {
-                const int I = wid + NW * s;
-                if (I >= J && I < T) {
+        for (int s = 0; s < RS; ++s) {
+            a0[s] = 0.0; a1[s] = 0.0;
+            int I = wid + NW * s; I = I < T ? I : T - 1;
+            base[s] = 32 * ((I * (I + 1)) / 2);
+        }
+        PMB_UNROLL
+        for (int seg = 0; seg < RS; ++seg) {
+            const int jlo = seg == 0 ? 0 : wid + NW * (seg - 1) + 1;
+            int jhi = wid + NW * seg; jhi = jhi < T ? jhi : T - 1;
+            PMB_NOUNROLL
+            for (int J = jlo; J <= jhi; ++J) {
+                const d2 t = tv[4 * J];
+                PMB_UNROLL
+                for (int s = seg; s < RS; ++s) {
                     const d2 x = tl[base[s] + 32 * J];
                     a0[s] = dm::fma(x.x, t.x, a0[s]);
                     a1[s] = dm::fma(x.y, t.y, a1[s]);
@@ -353,19 +361,22 @@ PMB_DEV void solve_rows(Cta& c, const Ws& w, const int* perm, double* sol)
         }
     }
     c.sync();
+    // backward: the warp's tile columns J_s = wid + NW s; over the I loop the set of active columns only grows
     {
         double b0[RS], b1[RS];
         PMB_UNROLL
         for (int s = 0; s < RS; ++s) { b0[s] = 0.0; b1[s] = 0.0; }
-        PMB_NOUNROLL
-        for (int I = wid; I < T; ++I) {                                  // tile rows above the warp's first column hold nothing for it
-            const double yv = w.yb[8 * I + r8];
-            const int rowbase = 32 * ((I * (I + 1)) / 2);
-            PMB_UNROLL
-            for (int s = 0; s < RS; ++s) {
-                const int J = wid + NW * s;
-                if (J <= I) {
-                    const d2 t = tl[rowbase + 32 * J];
+        PMB_UNROLL
+        for (int seg = 0; seg < RS; ++seg) {
+            const int ilo = wid + NW * seg;
+            int ihi = ilo + NW - 1; ihi = (seg == RS - 1 || ihi >= T) ? T - 1 : ihi;
+            PMB_NOUNROLL
+            for (int I = ilo; I <= ihi; ++I) {
+                const double yv = w.yb[8 * I + r8];
+                const d2* row = tl + 32 * ((I * (I + 1)) / 2 + wid);
+                PMB_UNROLL
+                for (int s = 0; s <= seg; ++s) {
+                    const d2 t = row[32 * NW * s];
                     b0[s] = dm::fma(t.x, yv, b0[s]);
                     b1[s] = dm::fma(t.y, yv, b1[s]);
                 }

@@ -147,6 +147,7 @@ struct SqpWs {
     int opt_exact_hessian;       // pmb_sqp_set_hessian_options: exact Lagrangian Hessian at every iteration (no BFGS)
     int opt_gershgorin;          //                              Gershgorin shift after every exact Hessian
     int opt_block_bfgs;          // pmb_sqp_set_hessian_update: the OCP's block BFGS instead of the dense damped BFGS
+    const int* order;            // work-queue order (pmb_sqp_set_schedule): ticket q solves instance order[q]; nullptr = identity
     unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
                                  // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
 };

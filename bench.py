@@ -18,7 +18,14 @@ the same initial guess.  metric = sum over instances of sqp_info.iter / time.
   kkt_kernel   : the materialising KKT kernel of the metric's second half (pmb_kkt_assemble_dev, box_admm.hpp:207-223),
                  B_KKT = 8 (N^2 + M N + (N+M)^2) bytes per instance, device-resident inputs larger than L2.
   cpu_baseline : the CPU restatement of the reference algorithm (oracle/, Eigen is not available so the reference itself
-                 cannot be built) on a bounded sample of the same workload, all host cores.
+                 cannot be built) on a bounded sample of the same workload, all host cores — in two builds: "native" (-O3, AVX2 +
+                 FMA contraction, libm: how a user would build the reference; the figure quoted) and "strict" (the bit-reproducible
+                 parity oracle).
+  arithmetic   : --arithmetic fast (default; KKT linear algebra on the fp64 tensor cores, csrc/pmb_qp_fast.hpp) or exact (every
+                 fp64 operation in the oracle's order: bit-identical results).  The line always carries BOTH: the other mode's
+                 throughput is under `other_arithmetic`, and `parity` holds the comparison of both with the oracle, next to the
+                 control (the oracle against its own native build: what a change of rounding alone does to whole solves).
+  configs      : the other BASELINE.json configurations (CSTR 4096, kite 1024 sharded over the ranks, robot batch sweep), short runs.
 """
 from __future__ import annotations
 
@@ -121,11 +128,11 @@ def build_workload(args, n_inst: int, offset_seed: int = 0):
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the CPU restatement of the reference algorithm (oracle/), timed on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int, keep=None):
+def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int, keep=None, flavour="strict", trace=False):
     from oracle import pyoracle   # the one place bench.py executes oracle/: as the timed CPU arm
-    orc = pyoracle.load()
+    orc = pyoracle.load_native() if flavour == "native" else pyoracle.load()
     cores = os.cpu_count() or 1
-    pyoracle.set_num_threads(cores)
+    pyoracle.load(); pyoracle.set_num_threads(cores)
     w = build_workload(args, max(args.batch, n_inst))        # the GPU arm's workload ...
     w.x0 = np.ascontiguousarray(w.x0[:n_inst])               # ... of which the CPU arm solves the first n_inst instances
     s = orc.sqp(w.name, n_inst)
@@ -140,8 +147,36 @@ def cpu_solve_rate(args, n_inst: int, steps: int, warmup: int, keep=None):
             total_it += int(s.info()["iter"].sum()); total_t += dt
     if keep is not None:
         keep["x"] = s.primal(); keep["lam"] = s.dual(); keep["info"] = s.info()
+        if trace:
+            keep["trace"] = s.trace(w.sqp_max_iter)
     s.close()
     return total_it / total_t, total_t / max(steps, 1), cores, total_it
+
+
+def rel_inf_rows(a, b):
+    return np.max(np.abs(a - b), axis=1) / np.maximum(1.0, np.max(np.abs(b), axis=1))
+
+
+def compare_solves(a, b):
+    """whole-solve comparison of two result sets (dicts with x, lam, info, trace) of the same instances — SURVEY.md §8d parity
+    definitions: decision traces (ADMM trips, factorisations, BFGS branch, line-search trials, alpha per SQP iteration; iteration
+    count; status), iterate parity on the instances whose traces are identical"""
+    ia, ib = a["info"], b["info"]
+    same = (ia["iter"] == ib["iter"]) & (ia["status"] == ib["status"])
+    for k in ("qp_iter", "bfgs", "ls_trials", "qp_factor"):
+        same &= (a["trace"][k] == b["trace"][k]).all(axis=1)
+    same &= np.array([np.array_equal(u, v, equal_nan=True) for u, v in zip(a["trace"]["alpha"], b["trace"]["alpha"])])
+    fin = np.isfinite(a["x"]).all(axis=1) & np.isfinite(b["x"]).all(axis=1)
+    e = np.maximum(rel_inf_rows(a["x"], b["x"]), rel_inf_rows(a["lam"], b["lam"]))
+    m = same & fin
+    bit = ((a["x"] == b["x"]) | (np.isnan(a["x"]) & np.isnan(b["x"]))).all(axis=1) & ((a["lam"] == b["lam"]) | (np.isnan(a["lam"]) & np.isnan(b["lam"]))).all(axis=1)
+    return {"instances": int(len(same)), "identical_status_pct": 100.0 * float((ia["status"] == ib["status"]).mean()),
+            "identical_iteration_counts_pct": 100.0 * float((ia["iter"] == ib["iter"]).mean()),
+            "identical_decision_traces_pct": 100.0 * float(same.mean()), "bit_identical_iterates_pct": 100.0 * float(bit.mean()),
+            "max_rel_inf_on_identical_traces": float(e[m].max()) if m.any() else None,
+            "median_rel_inf_on_identical_traces": float(np.median(e[m])) if m.any() else None,
+            "within_1e-10_pct_of_identical_traces": 100.0 * float((e[m] <= 1e-10).mean()) if m.any() else None,
+            "max_rel_inf_all_finite": float(e[fin].max()) if fin.any() else None}
 
 
 def run_reference(args):
@@ -149,14 +184,15 @@ def run_reference(args):
     if rank != 0:
         return 0
     n_inst = args.cpu_sample
-    rate, t_step, cores, _ = cpu_solve_rate(args, n_inst, args.steps, min(args.warmup, 1))
+    rate, t_step, cores, _ = cpu_solve_rate(args, n_inst, args.steps, min(args.warmup, 1), flavour="native")
     sample = f"{n_inst} instances of the {args.workload} workload per step (same seeds/inputs as the GPU arm's first rows), solved to convergence"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, args.batch, max(1, args.gpus)),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "CPU restatement of PolyMPC's algorithm (oracle/): Eigen is absent, the reference itself cannot be built"},
+                         "note": "CPU restatement of PolyMPC's algorithm (oracle/, native build: -O3, AVX2 + FMA contraction, libm): Eigen is absent, "
+                                 "the reference itself cannot be built"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,6 +206,7 @@ def config_dict(args, batch_per_gpu, n_gpus, cpu=False):
              "kite": "NX=13,NU=3, order 12 x 1 (13 nodes), N=208, M=169"}[args.workload]
     return {"workload": f"{args.workload} OCP batch={batch_per_gpu}{'' if cpu else ' per GPU'} random x0 sweep, fp64, SQP to convergence "
                         f"(max_iter {args.sqp_max_iter}, line search {args.ls_max_iter}), boxADMM + dense pivoted LDLT",
+            "arithmetic": "reference order (CPU)" if cpu else args.arithmetic,
             "problem": sizes, "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus,
             "parallelism": "cpu-threads" if cpu else f"instances sharded over {n_gpus} GPU(s), no data-path collective",
             "l2": "inputs larger than L2 (H + A + state of one batch = %.0f MB)" % (batch_per_gpu * 8 * (65 * 65 + 39 * 65 + 6 * 65) / 1e6)
@@ -197,6 +234,9 @@ def run_gpu(args):
     if api.device_count() < 1:
         raise SystemExit("bench.py: libpolympc_b200 sees no device")
 
+    ARITH = {"exact": 0, "fast": 1}
+    arith = ARITH[args.arithmetic]
+    other = "exact" if args.arithmetic == "fast" else "fast"
     B = args.batch                                   # per GPU (weak scaling)
     w_all = build_workload(args, B * world)
     lo, hi = W.shard_bounds(B * world, world, rank)
@@ -211,6 +251,7 @@ def run_gpu(args):
     s = api.sqp(w_all.name, hi - lo, device=local_rank)
     s.set_stream(stream.cuda_stream)
     W.configure(s, w_all, lo, hi)
+    s.set_arithmetic(arith)
     x0 = np.ascontiguousarray(w_all.x0[lo:hi])
     guess_x = np.zeros(dims["N"]); guess_l = np.zeros(dims["DUAL"])
     if w_all.x_guess is not None:
@@ -288,6 +329,31 @@ def run_gpu(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = sum_over_ranks(float(e2e_iters)) / (ms_e2e * 1e-3)
 
+    # ---- the same device-resident measurement in the other arithmetic (always reported next to the headline) -----------------
+    def device_rate(solver, steps, warm=2):
+        for _ in range(warm):
+            solver.reset_guess(); solver.solve()
+        its = int(solver.info()["iter"].sum())
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(steps):
+            solver.reset_guess(); solver.solve()
+        a1.record(stream)
+        barrier()
+        ms = max_over_ranks(a0.elapsed_time(a1))
+        return sum_over_ranks(float(its)) * steps / (ms * 1e-3), ms / steps
+
+    other_arith = None
+    try:
+        s.set_arithmetic(ARITH[other])
+        v_o, ms_o = device_rate(s, max(2, min(args.steps, 3)))
+        other_arith = {"arithmetic": other, "value": v_o, "unit": UNIT, "ms_per_step": ms_o,
+                       "note": "same workload, same handle, device-resident inputs, the other arithmetic of the KKT linear algebra"}
+    except Exception as e:                                      # noqa: BLE001
+        other_arith = {"arithmetic": other, "error": str(e)}
+    s.set_arithmetic(arith)
+
     # ---- roofline of the dominant (only) kernel of the step: the fused persistent sqp_solve ---------------------------------------
     # CUDA-event time of the kernel alone (pmb_sqp_set_profiling brackets the launch) and its phase split (SM cycle counters)
     s.set_profiling(True)
@@ -312,24 +378,26 @@ def run_gpu(args):
     flops_iter = K ** 3 / 3 + trips * (2 * K * K + 2 * K) + (trips / 10) * 2 * (2 * M * N + N * N) + 6 * N * N + 2 * M * N
     achieved = iters_per_solve * b_iter / (kernel_ms * 1e-3) / 1e9
     cyc_tot = sum(phases.get(k, 0) for k in ("linearise", "qp", "step")) or 1
-    roofline = {"kernel": "sqp_solve (fused persistent kernel: linearise + boxADMM/LDLT + line search, one CTA per instance)",
+    traffic_csv = "r2_sqp_solve_%s_ncu_raw.csv" % args.arithmetic
+    roofline = {"kernel": ("sqp_solve_fast" if arith else "sqp_solve") + " (fused persistent kernel: linearise + boxADMM/LDLT + line search, one CTA per instance)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("r1b_sqp_solve_ncu_raw.csv") if (args.workload == "mobile_robot" and B == 8192) else None,
-                "traffic_source": "profiles/r1b_sqp_solve_ncu_raw.csv (one ncu --set full capture of the same launch, batch 8192)",
+                "traffic": ncu_traffic(traffic_csv) if (args.workload == "mobile_robot" and B == 8192) else None,
+                "traffic_source": "profiles/" + traffic_csv + " (one ncu --set full capture of this launch at batch 8192, taken at the commit "
+                                  "named in profiles/README.md; null when the file is absent)",
                 "peak_source": peak_src, "avg_launch_ms": kernel_ms, "bytes_per_sqp_iteration": b_iter,
                 "sqp_iterations_per_launch": iters_per_solve,
                 "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
                 "phase_share": {k: phases.get(k, 0) / cyc_tot for k in ("linearise", "qp", "step")},
                 "qp_phase_share": {k: phases.get(k, 0) / max(1, phases.get("qp", 1)) for k in
                                    ("qp_pivot", "qp_gather", "qp_factor", "qp_solve", "qp_update", "qp_resid")},
+                "cycles_per_sqp_iteration": {k: int(v / it_n) for k, v in phases.items() if k not in ("sqp_iterations", "admm_trips")},
                 "admm_trips_per_iteration": trips,
                 "fp64": {"achieved_tflops": iters_per_solve * flops_iter / (kernel_ms * 1e-3) / 1e12, "peak_tflops": 37.07,
                          "peak_source": "measured on this pool's B200 with tools/ubench/lat.cu (fp64 FMA, all SMs)",
                          "flops_per_sqp_iteration": flops_iter},
                 "note": "fused design: K is built, factored and used in shared memory and never written to HBM; per-iteration state "
-                        "stays in L2.  The kernel is bound by the latency of dependent fp64 operations (triangular solves, "
-                        "division chain of the LDLT), not by HBM or fp64 throughput; the HBM-bound materialising KKT kernel is "
-                        "reported under kkt_kernel"}
+                        "stays in L2.  The kernel is bound by instruction issue / latency (barriers, instruction fetch, dependent fp64 "
+                        "chains), not by HBM or fp64 throughput; the HBM-bound materialising KKT kernel is reported under kkt_kernel"}
 
     # ---- the materialising KKT kernel (a17), device-resident, B_KKT bytes per instance ----------------------------------------------
     kkt = None
@@ -358,36 +426,58 @@ def run_gpu(args):
         gbs = nb * bk / (kms * 1e-3) / 1e9
         kkt = {"kernel": "kkt_assemble_dense", "bytes_per_instance": bk, "batch": nb, "avg_launch_ms": kms, "achieved": gbs, "peak": peak,
                "unit": "GB/s", "frac": gbs / peak, "working_set_mb": nb * bk / 1e6,
-               "traffic": ncu_traffic("r1_kkt_assemble_ncu_raw.csv") if (args.workload == "mobile_robot" and nb == 8192) else None}
+               "traffic": ncu_traffic("r2_kkt_assemble_ncu_raw.csv") if (args.workload == "mobile_robot" and nb == 8192) else None}
         launches_kkt = reps
         del H_d, A_d, K_d
     except Exception as e:   # never let the auxiliary measurement kill the bench line
         kkt = {"error": str(e)}
 
-    # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------------------------------------------------
+    # ---- CPU baseline + parity (rank 0, N == 1 only) -----------------------------------------------------------------------------
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        kept = {}
-        rate, t_step, cores, _ = cpu_solve_rate(args, args.cpu_sample, 1, 0, keep=kept)
-        # the CPU leg solved the first cpu_sample instances of the same workload: compare the GPU's results for them
-        s.reset_guess(); s.solve()
         ns = min(args.cpu_sample, hi - lo)
-        xg, lg, ig = s.primal()[:ns], s.dual()[:ns], s.info()[:ns]
-        xc, lc, ic = kept["x"][:ns], kept["lam"][:ns], kept["info"][:ns]
-        fin = np.isfinite(xc).all(axis=1) & np.isfinite(xg).all(axis=1)
-        same_x = ((xg == xc) | (np.isnan(xg) & np.isnan(xc))).all(axis=1)
-        same_l = ((lg == lc) | (np.isnan(lg) & np.isnan(lc))).all(axis=1)
-        denom = np.maximum(1.0, np.abs(xc[fin]).max(axis=1)) if fin.any() else np.ones(1)
-        rel = (np.abs(xg[fin] - xc[fin]).max(axis=1) / denom) if fin.any() else np.zeros(1)
-        parity = {"instances": int(ns), "max_rel_inf_x": float(rel.max()), "tolerance": 1e-10,
-                  "bit_identical_x_pct": 100.0 * float(same_x.mean()), "bit_identical_lam_pct": 100.0 * float(same_l.mean()),
-                  "identical_iteration_counts_pct": 100.0 * float((ig["iter"] == ic["iter"]).mean()),
-                  "identical_status_pct": 100.0 * float((ig["status"] == ic["status"]).mean()),
-                  "against": "CPU restatement (oracle/) on the same inputs"}
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {args.cpu_sample} instances of the same workload, one solve to convergence ({t_step:.1f} s), all host cores",
+        strict, native = {}, {}
+        rate_s, t_s, cores, _ = cpu_solve_rate(args, ns, 1, 0, keep=strict, flavour="strict", trace=True)
+        rate_n, t_n, _, _ = cpu_solve_rate(args, ns, 1, 0, keep=native, flavour="native", trace=True)
+        cpu = {"value": rate_n, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ns} instances of the same workload, one solve to convergence ({t_n:.1f} s), all host cores",
+               "build": "native: -O3 -march=x86-64-v3 -ffp-contract=fast, libm (oracle/Makefile)",
+               "strict_build": {"value": rate_s, "seconds": t_s, "build": "-O3 -march=x86-64-v3 -ffp-contract=off, deterministic elementary "
+                                "functions: the bit-reproducible parity oracle"},
                "note": "CPU restatement of PolyMPC's algorithm (oracle/); Eigen is absent so the reference itself cannot be built"}
+        # the CPU legs solved the first `ns` instances of the same workload: the GPU's results for them, in both arithmetics
+        gpu = {}
+        sp = api.sqp(w_all.name, ns, device=local_rank); sp.set_stream(stream.cuda_stream); W.configure(sp, w_all, lo, lo + ns); sp.set_trace(True)
+        for name in ("exact", "fast"):
+            try:
+                sp.set_arithmetic(ARITH[name]); sp.reset_guess(); sp.solve()
+                gpu[name] = {"x": sp.primal(), "lam": sp.dual(), "info": sp.info(), "trace": sp.trace(w_all.sqp_max_iter)}
+            except Exception as e:                              # noqa: BLE001
+                gpu[name] = None
+        sp.close()
+        # stage-wise: ONE SQP iteration from the same state (exact Hessian, QP, line search, step), fast vs exact on the GPU
+        one = None
+        try:
+            w1 = build_workload(args, ns); w1.sqp_max_iter = 1
+            r1 = {}
+            for name in ("exact", "fast"):
+                s1 = api.sqp(w1.name, ns, device=local_rank); s1.set_stream(stream.cuda_stream); W.configure(s1, w1); s1.set_arithmetic(ARITH[name]); s1.solve()
+                r1[name] = (s1.primal(), s1.dual(), s1.info()); s1.close()
+            e1 = np.maximum(rel_inf_rows(r1["fast"][0], r1["exact"][0]), rel_inf_rows(r1["fast"][1], r1["exact"][1]))
+            one = {"instances": int(ns), "max_rel_inf": float(e1.max()), "tolerance": 1e-10,
+                   "identical_admm_trip_counts_pct": 100.0 * float((r1["fast"][2]["qp_solver_iter"] == r1["exact"][2]["qp_solver_iter"]).mean())}
+        except Exception as e:                                  # noqa: BLE001
+            one = {"error": str(e)}
+        parity = {"tolerance": 1e-10, "against": "CPU restatement (oracle/, strict build) on the same inputs: the first %d instances" % ns,
+                  "exact_vs_oracle": compare_solves(gpu["exact"], strict) if gpu.get("exact") else None,
+                  "fast_vs_oracle": compare_solves(gpu["fast"], strict) if gpu.get("fast") else None,
+                  "fast_one_sqp_iteration_vs_exact": one,
+                  "control_native_oracle_vs_oracle": compare_solves(native, strict),
+                  "note": "exact arithmetic is bit-identical to the oracle.  Fast arithmetic rounds differently: one SQP iteration from the "
+                          "same state agrees to 1e-12; over whole solves rounding is amplified by the iteration itself (Armijo and "
+                          "termination tests at round-off level) — the control line shows the oracle against its own native build, "
+                          "i.e. what a change of rounding ALONE does; fast-vs-oracle should be read against it"}
 
     # ---- two batches in flight (secondary figure, never the headline) ---------------------------------------------------------
     # A persistent kernel ends with a tail: the 0.4 % of instances that run all 100 SQP iterations keep a few CTAs busy for
@@ -402,7 +492,8 @@ def run_gpu(args):
             s2 = api.sqp(w_all.name, hi - lo, device=local_rank)
             s2.set_stream(stream2.cuda_stream)
             W.configure(s2, w_all, lo, hi)
-            s2.solve()
+            s2.set_arithmetic(arith)
+            s2.solve(); s2.reset_guess(); s2.solve()
             steps2 = max(2, args.steps + (args.steps % 2))
             barrier()
             p0, p1, pj = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
@@ -422,6 +513,36 @@ def run_gpu(args):
         except Exception as e:                                  # noqa: BLE001 — a secondary figure must not break the line
             pipelined = {"error": str(e)}
 
+    # ---- the other BASELINE.json configurations, short runs (every rank takes part: max-over-ranks timing) ---------------------
+    configs = None
+    if not args.no_configs:
+        configs = {}
+
+        def quick(workload, batch_per_rank, arithmetic, steps=2, **kw):
+            """it/s of `workload` with batch_per_rank instances on every rank (rank r solves block r of the sweep)"""
+            try:
+                wq = W.WORKLOADS[workload](batch_per_rank * world, **kw)
+                sq = api.sqp(wq.name, batch_per_rank, device=local_rank)
+                sq.set_stream(stream.cuda_stream)
+                W.configure(sq, wq, rank * batch_per_rank, (rank + 1) * batch_per_rank)
+                sq.set_arithmetic(ARITH[arithmetic])
+                v, ms = device_rate(sq, steps, warm=2)
+                solved = sum_over_ranks(float((sq.info()["status"] == 0).sum())) / (batch_per_rank * world)
+                sq.close()
+                return {"value": v, "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": batch_per_rank, "arithmetic": arithmetic, "solved_fraction": solved}
+            except Exception as e:                              # noqa: BLE001
+                return {"error": str(e)}
+
+        configs["cstr_batch4096"] = {a: quick("cstr", 4096, a) for a in ("fast", "exact")}                      # BASELINE config 3
+        kb = max(1, 1024 // world)
+        configs["kite_12x1_batch1024_sharded"] = {"exact": quick("kite", kb, "exact", steps=1),                   # config 4: 1024 / N per GPU
+                                                  "fast": quick("kite", kb, "fast", steps=1),
+                                                  "note": "kite is quoted in exact arithmetic: fast arithmetic loses 2e-7 per SQP iteration on its "
+                                                          "377 x 377 KKT systems (tests/test_gpu_fast.py)"}
+        configs["mobile_robot_batch_sweep"] = {str(b): quick("mobile_robot", b, args.arithmetic) for b in (256, 1024, 4096, 16384, 65536)}   # config 5
+        configs["mobile_robot_reference_test_settings"] = quick("mobile_robot", B, args.arithmetic, sqp_max_iter=10, ls_max_iter=10)
+        configs["note"] = "per-GPU batch; under --gpus N every rank solves its own block of the sweep (weak scaling) except the kite, which is sharded"
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -431,7 +552,10 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "kkt_kernel": kkt, "cpu_baseline": cpu, "parity": parity, "pipelined": pipelined,
+            "arithmetic": args.arithmetic, "other_arithmetic": other_arith,
+            "roofline": roofline, "kkt_kernel": kkt, "cpu_baseline": cpu, "parity": parity, "pipelined": pipelined, "configs": configs,
+            "schedule": "work queue in longest-processing-time-first order from the previous solve's iteration counts (pmb_sqp_set_schedule; "
+                        "the warm-up solves provide the history, results do not depend on the order)",
             "sqp_iterations_per_step": total_iters / args.steps, "solved_fraction": solved_frac,
             "mean_sqp_iter_per_instance": iters_per_solve / (hi - lo),
         }
@@ -466,6 +590,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None, help="instances solved by the CPU arm per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-batches-in-flight secondary measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE.json configurations")
+    ap.add_argument("--arithmetic", default="fast", choices=["fast", "exact"], help="arithmetic of the KKT linear algebra (pmb_sqp_set_arithmetic)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]

@@ -36,5 +36,24 @@ def load() -> CApi:
     return _api
 
 
+NATIVE_LIB_PATH = os.path.join(_HERE, "_build", "liboracle_native.so")
+_native = None
+
+
+def load_native() -> CApi:
+    """the same oracle sources built `-O3 -march=native -ffp-contract=fast` against libm: a faster CPU baseline and the
+    rounding-sensitivity control.  NOT bit-reproducible (it is tied to the host CPU); never the parity reference."""
+    global _native
+    if _native is None:
+        if not os.path.exists(NATIVE_LIB_PATH):
+            build(force=True)
+        lib = ctypes.CDLL(NATIVE_LIB_PATH)
+        _native = CApi(lib, "orc_")
+        lib.orc_set_num_threads.argtypes = [ctypes.c_int]
+    return _native
+
+
 def set_num_threads(n: int) -> None:
     load().lib.orc_set_num_threads(int(n))
+    if _native is not None:
+        _native.lib.orc_set_num_threads(int(n))

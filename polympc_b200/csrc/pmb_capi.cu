@@ -189,7 +189,7 @@ struct pmb_sqp {
     pmb::DevBuf<pmb_sqp_info_t> info;
     pmb::DevBuf<pmb_qp_info_t> qp_info;
     pmb::DevBuf<int> qp_nfac, tr_qp_iter, tr_bfgs, tr_ls, tr_qp_factor, queue;
-    pmb::DevBuf<double> factor_scratch;
+    pmb::DevBuf<double> factor_scratch, factor_scratch_fast;
     int grid = 0;
     bool factor_in_smem = true;
     int trace_rows = 0;
@@ -501,7 +501,7 @@ pmb_sqp_t* pmb_sqp_create(const char* name, int batch, int device)
     if (NI > 0) ok = ok && rt_h2d(s->lbg.p, lo.data(), B * NI * sizeof(double), s->stream) && rt_h2d(s->ubg.p, hi.data(), B * NI * sizeof(double), s->stream);
     ok = ok && rt_sync(s->stream);
     if (!ok) return nullptr;
-    if (g_default_arithmetic.load() == PMB_ARITH_FAST && s->ocp.impl->has_fast()) pmb_sqp_set_arithmetic(s.get(), PMB_ARITH_FAST);
+    if (g_default_arithmetic.load() == PMB_ARITH_FAST) pmb_sqp_set_arithmetic(s.get(), PMB_ARITH_FAST);
     return s.release();
 }
 void pmb_sqp_destroy(pmb_sqp_t* s) { delete s; }
@@ -536,12 +536,15 @@ int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode)
     if (!s || (mode != PMB_ARITH_EXACT && mode != PMB_ARITH_FAST)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_arithmetic: bad argument");
     if (mode == PMB_ARITH_FAST) {
         const IProblem& P = *s->ocp.impl;
-        if (!P.has_fast() || P.fast_smem_bytes() > SMEM_CTA_MAX) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_arithmetic: the tile workspace of this problem does not fit in shared memory");
+        if (P.fast_smem_bytes() > SMEM_CTA_MAX) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_arithmetic: problem too large for shared memory");
         if (s->grid_fast == 0) {
             if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
             int grid = P.fast_resident_ctas();
             if (grid <= 0) PMB_FAIL(PMB_ERR_CUDA, "set_arithmetic: the fast sqp_solve kernel does not fit on the device");
-            s->grid_fast = grid > s->batch ? s->batch : grid;
+            if (!P.fast_in_smem()) grid = grid > 2 * 148 ? 2 * 148 : grid;       // keep the global tile workspaces L2 resident
+            grid = grid > s->batch ? s->batch : grid;
+            if (!P.fast_in_smem() && !s->factor_scratch_fast.resize((size_t)grid * P.fast_factor_doubles())) return PMB_ERR_CUDA;
+            s->grid_fast = grid;
         }
     }
     s->arithmetic = mode;
@@ -691,7 +694,7 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     }
     // one persistent launch: CTAs draw instances from the queue and run their whole SQP loop on the device
     ok = ok && rt_event_record(s->kev0, st);
-    if (s->arithmetic == PMB_ARITH_FAST) ok = ok && s->ocp.impl->launch_solve_fast(s->grid_fast, ws, s->settings, s->qp_settings, B, s->queue.p, st);
+    if (s->arithmetic == PMB_ARITH_FAST) ok = ok && s->ocp.impl->launch_solve_fast(s->grid_fast, ws, s->settings, s->qp_settings, s->factor_scratch_fast.p, B, s->queue.p, st);
     else ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
     ok = ok && rt_event_record(s->kev1, st);
     ++launches;

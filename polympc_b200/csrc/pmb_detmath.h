@@ -225,8 +225,13 @@ PMB_DM_NOINLINE double cos_rare(double x)
 }
 } // namespace detail
 
+#ifdef PMB_DM_LIBM   /* oracle 'native' flavour only (oracle/Makefile): the C library instead of the deterministic algorithms */
+PMB_HD double sin(double x) { return std::sin(x); }
+PMB_HD double cos(double x) { return std::cos(x); }
+#else
 PMB_HD double sin(double x) { return (fabs(x) < detail::TRIG_FOLD) ? detail::sin_core(x) : detail::sin_rare(x); }
 PMB_HD double cos(double x) { return (fabs(x) < detail::TRIG_FOLD) ? detail::cos_core(x) : detail::cos_rare(x); }
+#endif
 
 PMB_HD double tan(double x) { return sin(x) / cos(x); }
 
@@ -235,6 +240,9 @@ PMB_HD double tan(double x) { return sin(x) / cos(x); }
 // ---------------------------------------------------------------------------------------------------------
 PMB_HD double exp(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::exp(x);
+#endif
     const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
                  invln2 = 1.44269504088896338700e+00;
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
@@ -265,6 +273,9 @@ PMB_HD double exp(double x)
 
 PMB_HD double log(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::log(x);
+#endif
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
                  Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
@@ -342,6 +353,9 @@ PMB_HD double atan(double x)
 
 PMB_HD double atan2(double y, double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::atan2(y, x);
+#endif
     const double pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
     if (isnan(x) || isnan(y)) return nan();
     const bool yneg = (to_bits(y) >> 63) != 0;
@@ -368,11 +382,17 @@ PMB_HD double atan2(double y, double x)
 
 PMB_HD double asin(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::asin(x);
+#endif
     if (fabs(x) > 1.0) return nan();
     return atan2(x, sqrt((1.0 - x) * (1.0 + x)));
 }
 PMB_HD double acos(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::acos(x);
+#endif
     if (fabs(x) > 1.0) return nan();
     return atan2(sqrt((1.0 - x) * (1.0 + x)), x);
 }
@@ -382,6 +402,9 @@ PMB_HD double acos(double x)
 // ---------------------------------------------------------------------------------------------------------
 PMB_HD double sinh(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::sinh(x);
+#endif
     const double ax = fabs(x);
     if (ax < 0.5) {
         const double z = x * x;
@@ -401,6 +424,9 @@ PMB_HD double sinh(double x)
 }
 PMB_HD double cosh(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::cosh(x);
+#endif
     const double ax = fabs(x);
     if (ax > 709.0) {
         const double e = exp(0.5 * ax);
@@ -411,6 +437,9 @@ PMB_HD double cosh(double x)
 }
 PMB_HD double tanh(double x)
 {
+#ifdef PMB_DM_LIBM
+    return std::tanh(x);
+#endif
     const double ax = fabs(x);
     if (ax < 0.5) return sinh(x) / cosh(x);
     if (ax > 22.0) return x < 0.0 ? -1.0 : 1.0;
@@ -420,6 +449,9 @@ PMB_HD double tanh(double x)
 
 PMB_HD double pow(double x, double y)
 {
+#ifdef PMB_DM_LIBM
+    return std::pow(x, y);
+#endif
     if (y == 0.0) return 1.0;
     if (isnan(x) || isnan(y)) return nan();
     const double fy = floor(y);

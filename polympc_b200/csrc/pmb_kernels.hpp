@@ -105,27 +105,87 @@ struct QpBody {
 };
 
 // ---- a17: KKT assembly, reference layout (dense (N+M)^2, lower part + diagonal blocks written, rest zero) ------------
+/** The metric's "KKT kernel": K = [[H + sigma I + diag(rho_box), 0], [A, -diag(1 / rho_A)]] materialised in HBM, one CTA per
+ *  instance.  Pure data movement (read H and A once, write K once): columns are dealt to the warps two at a time, a lane owns
+ *  rows lane, lane + 32, ... of both columns and issues all its loads before the first store (eight independent 8-byte loads in
+ *  flight per lane for n <= 128), every warp-level access is a contiguous run of a column, loads are read-only streaming
+ *  (ld.global.cs) and stores are streaming (st.global.cs: K is not re-read here), no integer division anywhere. */
 struct KktDenseBody {
     static constexpr int THREADS = 256;
-    static constexpr int MIN_BLOCKS = 1;
+#ifdef PMB_KKT_MINB
+    static constexpr int MIN_BLOCKS = PMB_KKT_MINB;
+#else
+    static constexpr int MIN_BLOCKS = 6;     // 42 registers per thread: measured 5.11 / 5.32 / 5.78 TB/s at 4 / 5 / 6 CTAs per SM (8: spills, 4.35)
+#endif
     static constexpr const char* NAME = "kkt_assemble_dense";
     static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static double ld(const double* p)
+    {
+#if defined(__CUDACC__) && !defined(PMB_EMU)
+        return __ldcs(p);
+#else
+        return *p;
+#endif
+    }
+    PMB_DEV static void st(double* p, double v)
+    {
+#if defined(__CUDACC__) && !defined(PMB_EMU)
+        __stcs(p, v);
+#else
+        *p = v;
+#endif
+    }
     PMB_DEV static void run(const Warp& w, int b, unsigned char*, int N, int M, const double* H, const double* A, const double* rho_box,
                             const double* rho_inv, double sigma, double* K)
     {
-        const int n = N + M;
+        const int n = N + M, lane = w.lane(), wid = w.warp_id(), nw = w.nthreads() >> 5;
         const double* Hb = H + (size_t)b * N * N;
         const double* Ab = A + (size_t)b * M * N;
+        const double* rb = rho_box + (size_t)b * N;
+        const double* ri = rho_inv + (size_t)b * M;
         double* Kb = K + (size_t)b * n * n;
-        const int total = n * n;
-        for (int e = w.tid(); e < total; e += w.nthreads()) {
-            const int j = e / n, i = e - j * n;
-            double v = 0.0;
-            if (j < N) {
-                if (i < N) { v = Hb[i + (size_t)j * N]; if (i == j) { v += sigma; v += rho_box[(size_t)b * N + i]; } }
-                else v = Ab[(i - N) + (size_t)j * M];
-            } else if (i == j) v = -rho_inv[(size_t)b * M + (i - N)];
-            Kb[e] = v;
+        auto entry = [&](int i, int j) -> double {
+            if (j < N) {                                            // warp-uniform
+                if (i < N) { double v = ld(Hb + i + (size_t)j * N); if (i == j) { v += sigma; v += rb[i]; } return v; }
+                return ld(Ab + (i - N) + (size_t)j * M);
+            }
+            return i == j ? -ri[i - N] : 0.0;
+        };
+#if defined(__CUDACC__) && !defined(PMB_EMU)
+        if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(Kb) & 15) == 0 && n <= 128) {
+            // a lane owns the row pairs (2 lane, 2 lane + 1) and (64 + 2 lane, 65 + 2 lane) of two columns: eight loads in flight,
+            // then four 16-byte streaming stores (columns of K start 16-byte aligned when n is even)
+            for (int j = 2 * wid; j < n; j += 2 * nw) {
+                const int j2 = j + 1 < n ? j + 1 : j;
+                const int i0 = 2 * lane, i1 = 64 + 2 * lane;
+                const bool hi = i1 < n;
+                const double a0 = entry(i0, j), a1 = entry(i0 + 1, j), b0 = entry(i0, j2), b1 = entry(i0 + 1, j2);
+                const double c0 = hi ? entry(i1, j) : 0.0, c1 = hi ? entry(i1 + 1, j) : 0.0, d0 = hi ? entry(i1, j2) : 0.0, d1 = hi ? entry(i1 + 1, j2) : 0.0;
+                if (i0 < n) {
+                    __stcs(reinterpret_cast<double2*>(Kb + i0 + (size_t)j * n), make_double2(a0, a1));
+                    if (j2 != j) __stcs(reinterpret_cast<double2*>(Kb + i0 + (size_t)j2 * n), make_double2(b0, b1));
+                }
+                if (hi) {
+                    __stcs(reinterpret_cast<double2*>(Kb + i1 + (size_t)j * n), make_double2(c0, c1));
+                    if (j2 != j) __stcs(reinterpret_cast<double2*>(Kb + i1 + (size_t)j2 * n), make_double2(d0, d1));
+                }
+            }
+            return;
+        }
+#endif
+        constexpr int U = 4;                                        // rows per lane and column held in registers
+        for (int j = 2 * wid; j < n; j += 2 * nw) {
+            const int j2 = j + 1 < n ? j + 1 : j;
+            for (int i0 = 0; i0 < n; i0 += 32 * U) {
+                double v[U], u[U];
+                PMB_UNROLL
+                for (int k = 0; k < U; ++k) { const int i = i0 + lane + 32 * k; v[k] = i < n ? entry(i, j) : 0.0; u[k] = i < n ? entry(i, j2) : 0.0; }
+                PMB_UNROLL
+                for (int k = 0; k < U; ++k) {
+                    const int i = i0 + lane + 32 * k;
+                    if (i < n) { st(Kb + i + (size_t)j * n, v[k]); if (j2 != j) st(Kb + i + (size_t)j2 * n, u[k]); }
+                }
+            }
         }
     }
 };

@@ -29,12 +29,14 @@ struct IProblem {
     /** one persistent launch that solves `batch` instances (grid CTAs draw them from `queue`) */
     virtual bool launch_solve(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
-    /** the same kernel in fast arithmetic (pmb_qp_fast.hpp); only for problems whose tile workspace fits in shared memory */
-    virtual bool has_fast() const = 0;
+    /** the same kernel in fast arithmetic (pmb_qp_fast.hpp); the tile workspace lives in shared memory when it fits, else in a
+     *  per-CTA global slot of fast_factor_doubles() that stays L2 resident */
+    virtual bool fast_in_smem() const = 0;
     virtual size_t fast_smem_bytes() const = 0;
+    virtual size_t fast_factor_doubles() const = 0;
     virtual int fast_resident_ctas() const = 0;
     virtual bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
-                                   int batch, int* queue, stream_t s) const = 0;
+                                   double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
 };
 
 template <class O>
@@ -83,23 +85,19 @@ struct ProblemImpl : IProblem {
         return rt_launch<Solve>(grid, Solve::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
     }
     using SolveFast = SqpSolveBody<O, true>;
-    static constexpr bool HAS_FAST = SolveFast::IN_SMEM;
-    bool has_fast() const override { return HAS_FAST; }
-    size_t fast_smem_bytes() const override { return HAS_FAST ? SolveFast::smem_bytes() : 0; }
+    bool fast_in_smem() const override { return SolveFast::IN_SMEM; }
+    size_t fast_smem_bytes() const override { return SolveFast::smem_bytes(); }
+    size_t fast_factor_doubles() const override { return SolveFast::FACTOR_DOUBLES; }
     int fast_resident_ctas() const override
     {
-        if constexpr (HAS_FAST)
-            return resident_ctas<SolveFast, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
-                SolveFast::smem_bytes(), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
-        else return 0;
+        return resident_ctas<SolveFast, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
+            SolveFast::smem_bytes(), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
     }
-    bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, int batch, int* queue,
-                           stream_t s) const override
+    bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
+                           int batch, int* queue, stream_t s) const override
     {
-        if constexpr (HAS_FAST) {
-            FactorStore fs{nullptr, SolveFast::FACTOR_DOUBLES, rt_sm_count()};
-            return rt_launch<SolveFast>(grid, SolveFast::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
-        } else { last_error_string() = "fast arithmetic: the tile workspace of this problem does not fit in shared memory"; return false; }
+        FactorStore fs{SolveFast::IN_SMEM ? nullptr : factor_scratch, SolveFast::FACTOR_DOUBLES, rt_sm_count()};
+        return rt_launch<SolveFast>(grid, SolveFast::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
     }
 };
 

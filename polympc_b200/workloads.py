@@ -41,9 +41,21 @@ class Workload:
         return self.x0.shape[0]
 
 
+def _blocks(batch: int, block: int, seed: int, draw) -> np.ndarray:
+    """`batch` rows drawn in blocks of `block` rows, block k from its own stream (seed + 1000 k): the first rows of a sweep are the
+    same whatever the total size, so that N GPUs x `block` instances each is N times the single-GPU workload plus new instances
+    (rank r of a weak-scaling run owns block r) and a 1 -> 8 curve measures scaling, not a different draw of stragglers."""
+    rows = []
+    k = 0
+    while sum(len(r) for r in rows) < batch:
+        rows.append(draw(np.random.default_rng(seed + 1000 * k), block))
+        k += 1
+    return np.ascontiguousarray(np.concatenate(rows, axis=0)[:batch])
+
+
 def mobile_robot(batch: int, seed: int = 20260117 + 2, grid: str = "6x2", sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
-    rng = np.random.default_rng(seed)
-    x0 = np.column_stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch), rng.uniform(-np.pi / 4, np.pi / 4, batch)])
+    x0 = _blocks(batch, 8192, seed, lambda rng, n: np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n),
+                                                                   rng.uniform(-np.pi / 4, np.pi / 4, n)]))
     return Workload(f"mobile_robot_{grid}", 0.0, 2.0, np.array([2.0]), np.array([-1.5, -0.75]), np.array([1.5, 0.75]), x0,
                     sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
                     meta={"x0": "U([-1,1]^2 x [-pi/4,pi/4])", "seed": seed})
@@ -61,10 +73,9 @@ def robot_obstacle(batch: int, seed: int = 20260117 + 6, sqp_max_iter: int = 100
 
 
 def cstr(batch: int, seed: int = 20260117 + 3, sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
-    rng = np.random.default_rng(seed)
     nominal = np.array([1.0, 0.5, 100.0, 100.0])
     spread = np.array([0.1, 0.05, 1.0, 1.0])
-    x0 = nominal + rng.uniform(-1, 1, (batch, 4)) * spread
+    x0 = _blocks(batch, 4096, seed, lambda rng, n: nominal + rng.uniform(-1, 1, (n, 4)) * spread)
     return Workload("cstr_5x2", 0.0, 100.0, None, np.array([3.0, -9000.0]), np.array([35.0, 0.0]), x0,
                     sqp_max_iter=sqp_max_iter, ls_max_iter=ls_max_iter,
                     meta={"x0": "(1,0.5,100,100) + U(+-(0.1,0.05,1,1))", "seed": seed})
@@ -74,9 +85,11 @@ KITE_NOMINAL = np.array([12.0, 0.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, -50.0, 1.0, 0.
 
 
 def kite(batch: int, seed: int = 20260117 + 4, grid: str = "12x1", sqp_max_iter: int = 100, ls_max_iter: int = 100) -> Workload:
-    rng = np.random.default_rng(seed)
-    x0 = KITE_NOMINAL * (1.0 + 0.05 * rng.uniform(-1, 1, (batch, 13)))
-    x0[:, [1, 3, 4, 5, 6, 7, 10, 11, 12]] += 0.05 * rng.uniform(-1, 1, (batch, 9))   # entries whose nominal value is 0
+    def draw(rng, n):
+        x = KITE_NOMINAL * (1.0 + 0.05 * rng.uniform(-1, 1, (n, 13)))
+        x[:, [1, 3, 4, 5, 6, 7, 10, 11, 12]] += 0.05 * rng.uniform(-1, 1, (n, 9))   # entries whose nominal value is 0
+        return x
+    x0 = _blocks(batch, 1024, seed, draw)
     # horizon 0.5 s: with the default SQP/QP settings every instance of the sweep converges (4-13 SQP iterations)
     return Workload(f"kite_{grid}", 0.0, 0.5, np.array([4.0]), np.array([0.0, -0.3, -0.3]), np.array([5.0, 0.3, 0.3]), x0,
                     x_guess=KITE_NOMINAL, u_guess=np.array([1.5, 0.0, 0.0]),

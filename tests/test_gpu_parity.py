@@ -21,7 +21,7 @@ def test_device_present(pmb):
 
 
 @pytest.mark.parametrize("name", ["mobile_robot_6x2", "mobile_robot_5x2", "mobile_robot_5x3", "cstr_5x2", "kite_4x2", "kite_12x1", "robot_obstacle_5x2",
-                                  "dropin_robot_5x3", "dropin_cstr_5x2"])
+                                  "parking_5x2", "dropin_robot_5x3", "dropin_cstr_5x2"])
 def test_ocp_operators(pmb, orc, name):
     pc.ocp_case(pmb, orc, name, B=37, seed=1)
 
@@ -286,3 +286,41 @@ def test_closed_loop_mpc(pmb, orc):
     fin = np.isfinite(la[-1][3]).all(axis=1)
     assert fin.mean() > 0.95
     assert np.median(np.linalg.norm(la[-1][3][fin, :2], axis=1)) < np.median(np.linalg.norm(w.x0[fin, :2], axis=1))
+
+
+@pytest.mark.parametrize("name", ["mobile_robot_6x2", "cstr_5x2", "parking_5x2", "kite_4x2"])
+def test_block_bfgs_operator(pmb, orc, name):
+    """ContinuousOCP<..., SPARSE>::hessian_update_impl (continuous_ocp.hpp:2303-2431) as an operator, plain and damped branch"""
+    br = pc.block_bfgs_case(pmb, orc, name, B=33, seed=2)
+    assert br[0] == 0 and br[1] == 1
+
+
+@pytest.mark.parametrize("kind,batch", [("mobile_robot", 1024), ("cstr", 512)])
+def test_sqp_block_bfgs_vs_oracle(pmb, orc, kind, batch):
+    """PMB_HESSIAN_BFGS_BLOCK — the SPARSE semantics every reference control test asks for — bit-exact against the oracle"""
+    w = W.WORKLOADS[kind](batch, sqp_max_iter=20, ls_max_iter=20)
+    ra, rb = pc.sqp_case(pmb, orc, w, hessian_update=1)
+    assert np.isfinite(rb["x"]).all() and (rb["info"]["status"] == 0).mean() > 0.9
+
+
+def test_sqp_minimal_time_parking_vs_oracle(pmb, orc):
+    """NP = 1, exact Hessian at every iteration, Gershgorin regularisation, final-state box: the setup of the reference's
+    tests/control/minimal_time_test.cpp:146-188 on 256 initial states; instance 0 is the reference's own (SOLVED, iter < 20)"""
+    w = W.parking(256)
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    assert rb["info"]["status"][0] == 0 and rb["info"]["iter"][0] < w.sqp_max_iter
+    assert (rb["info"]["status"] == 0).mean() > 0.85
+
+
+def test_sqp_codegen_test_setup(pmb, orc):
+    """tests/solvers/sqp/codegen_test.cpp:402-437: robot 5 x 2 on [0, 1], d = 1, exact Hessian at every iteration, SQP 10 / 10, QP
+    max_iter 1000, x0 = (0.5, 0.5, 0.5): the reference asserts SOLVED and iter < 10"""
+    w = W.mobile_robot(1, grid="5x2", sqp_max_iter=10, ls_max_iter=10)
+    w.t0, w.tf, w.d = 0.0, 1.0, np.array([1.0]); w.x0[:] = [0.5, 0.5, 0.5]; w.exact_hessian = True
+    outs = []
+    for api in (pmb, orc):
+        s = api.sqp(w.name, 1); W.configure(s, w)
+        q = s.qp_settings(); q.max_iter = 1000; s.set_qp_settings(q)
+        s.solve(); outs.append((s.primal(), s.dual(), s.info())); s.close()
+    pc.assert_same(outs[0][0], outs[1][0], "x"); pc.assert_same(outs[0][1], outs[1][1], "lam")
+    assert outs[1][2]["status"][0] == 0 and outs[1][2]["iter"][0] < 10

@@ -40,3 +40,26 @@ def test_info_iter_counts_qps(orc):
     n_qp = (r["trace"]["qp_iter"] > 0).sum(axis=1)
     assert np.array_equal(n_qp, r["info"]["iter"])
     assert np.array_equal(r["info"]["qp_solver_iter"], np.where(r["trace"]["qp_iter"] > 0, r["trace"]["qp_iter"], 0).sum(axis=1))
+
+
+def test_codegen_test_setup(orc):
+    """tests/solvers/sqp/codegen_test.cpp:402-437 (the reference's own SQP pin on the CasADi-fixture problem): robot 5 x 2 on
+    [0, 1], d = 1, exact Hessian at every iteration, SQP 10 / 10, QP max_iter 1000, x0 = (0.5, 0.5, 0.5) -> SOLVED, iter < 10"""
+    import numpy as np
+    from polympc_b200 import workloads as W
+    w = W.mobile_robot(1, grid="5x2", sqp_max_iter=10, ls_max_iter=10)
+    w.t0, w.tf, w.d = 0.0, 1.0, np.array([1.0]); w.x0[:] = [0.5, 0.5, 0.5]; w.exact_hessian = True
+    s = orc.sqp(w.name, 1); W.configure(s, w)
+    q = s.qp_settings(); q.max_iter = 1000; s.set_qp_settings(q)
+    s.solve()
+    info = s.info(); s.close()
+    assert info["status"][0] == 0 and info["iter"][0] < 10
+
+
+def test_minimal_time_setup(orc):
+    """tests/control/minimal_time_test.cpp:146-188: SOLVED, iter < max_iter (20), final time inside its box"""
+    from polympc_b200 import workloads as W
+    w = W.parking(1)
+    s = orc.sqp(w.name, 1); W.configure(s, w); s.solve()
+    info, x = s.info(), s.primal(); s.close()
+    assert info["status"][0] == 0 and info["iter"][0] < 20 and 0.0 < x[0, -1] < 10.0

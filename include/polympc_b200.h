@@ -164,7 +164,7 @@ int pmb_bfgs_update(int N, int batch, double* B, const double* s, const double* 
 typedef struct pmb_sqp pmb_sqp_t;
 pmb_sqp_t* pmb_sqp_create(const char* problem_name, int batch, int device);
 void pmb_sqp_destroy(pmb_sqp_t* s);
-pmb_ocp_t* pmb_sqp_problem(pmb_sqp_t* s);                                   /* SQPBase::get_problem() */
+pmb_ocp_t* pmb_sqp_problem(pmb_sqp_t* s);                                   /* SQPBase::get_problem(); BORROWED: owned by s, pmb_ocp_destroy ignores it */
 int pmb_sqp_batch(const pmb_sqp_t* s);
 int pmb_sqp_set_settings(pmb_sqp_t* s, const pmb_sqp_settings_t* st);       /* SQPBase::settings()    */
 int pmb_sqp_get_settings(const pmb_sqp_t* s, pmb_sqp_settings_t* st);

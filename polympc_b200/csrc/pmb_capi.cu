@@ -300,7 +300,7 @@ pmb_ocp_t* pmb_ocp_create(const char* name, int device)
     h->impl->device = device;
     return h;
 }
-void pmb_ocp_destroy(pmb_ocp_t* h) { if (h) { if (h->owned) delete h->impl; delete h; } }
+void pmb_ocp_destroy(pmb_ocp_t* h) { if (h && h->owned) { delete h->impl; delete h; } }   // a handle borrowed from pmb_sqp_problem() is left alone
 int pmb_ocp_dims(const pmb_ocp_t* h, pmb_dims_t* out) { if (!h || !out) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); *out = h->impl->dims; return PMB_OK; }
 int pmb_ocp_set_params(pmb_ocp_t* h, const double* v, int n)
 { if (!h || !v || n != h->impl->dims.NPARAM) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_params: bad argument"); h->impl->set_params(v); return PMB_OK; }
@@ -315,6 +315,17 @@ static int ocp_eval_host(pmb_ocp_t* h, int mode, int batch, const double* var, c
     if (!h || batch < 0 || !var) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ocp: bad argument");
     const pmb_dims_t& D = h->impl->dims;
     if (D.ND > 0 && !d) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ocp: static parameters required");
+    // outputs every kernel of this mode writes unconditionally (only `cost` is optional)
+    {
+        const bool need_c = mode == OCP_EQ || mode == OCP_EQ_LIN || mode == OCP_LAG_GRAD || mode == OCP_LAG_GRAD_HESS;
+        const bool need_jac = mode == OCP_EQ_LIN || mode == OCP_LAG_GRAD || mode == OCP_LAG_GRAD_HESS;
+        const bool need_grad = mode == OCP_COST_GRAD || mode == OCP_COST_GRAD_HESS || mode == OCP_LAG_GRAD || mode == OCP_LAG_GRAD_HESS;
+        const bool need_hess = mode == OCP_COST_GRAD_HESS || mode == OCP_LAG_GRAD_HESS;
+        const bool need_lg = mode == OCP_LAG_GRAD || mode == OCP_LAG_GRAD_HESS;
+        if ((need_c && !c) || (need_jac && !jac) || (need_grad && !grad) || (need_hess && !hess) || (need_lg && !lag_grad) ||
+            (mode == OCP_INEQ && D.NG > 0 && !g) || (mode == OCP_COST && !cost))
+            PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ocp: a required output pointer is NULL");
+    }
     if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
     if (batch == 0) return PMB_OK;
     if (!rt_set_device(h->impl->device)) return PMB_ERR_CUDA;
@@ -397,7 +408,7 @@ int pmb_qp_solve(int N, int M, int batch, const double* H, const double* h, cons
 int pmb_kkt_assemble(int N, int M, int batch, const double* H, const double* A, const double* rho_box, const double* rho_inv, double sigma,
                      double* K)
 {
-    if (N <= 0 || M < 0 || batch < 0 || !H || !A || !rho_box || !rho_inv || !K) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "kkt_assemble: bad argument");
+    if (N <= 0 || M < 0 || batch < 0 || !H || (M > 0 && (!A || !rho_inv)) || !rho_box || !K) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "kkt_assemble: bad argument");
     if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
     if (batch == 0) return PMB_OK;
     const size_t B = batch, n = (size_t)N + M;

@@ -258,28 +258,32 @@ struct LptOrderBody {
  *  wave quantisation: a slow instance only occupies its own CTA). */
 template <class O, bool FAST = false>
 struct SqpSolveBody {
-#ifdef PMB_SQP_THREADS
-    static constexpr int THREADS = PMB_SQP_THREADS;
-#else
-    static constexpr int THREADS = 128;
-#endif
     static constexpr const char* NAME = FAST ? "sqp_solve_fast" : "sqp_solve";
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
     static constexpr int R = (O::N + O::M + 31) / 32;
     /** doubles of the LDL^T workspace: packed lower triangle (exact arithmetic) or the tile workspace of pmb_qp_fast.hpp */
     static constexpr size_t FACTOR_DOUBLES = FAST ? fast::workspace_doubles(O::N + O::M) : (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
     static constexpr size_t SCRATCH_BYTES = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
-    /** resident CTAs per SM the register allocation is asked to allow: at most 3 when the factor lives in shared memory
-     *  (168 registers per thread; measured on the mobile robot: 4 CTAs x 128 registers spill inside the QP loops and are
-     *  slower end to end — 127 ms vs 109 ms per batch of 8192 — although shared memory would admit 4), 2 when the factor is
-     *  in global scratch (large problems, heavy AD code) */
     static constexpr size_t SMEM_IN = Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
                                       (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
     static constexpr bool IN_SMEM = SMEM_IN <= 227 * 1024;    // placement of the factor, fixed per problem at compile time
+    /** Threads per CTA and resident CTAs per SM the register allocation is asked to allow.
+     *  Factor in shared memory: 128 threads, at most 3 CTAs per SM (168 registers per thread; measured on the mobile robot:
+     *  4 CTAs x 128 registers spill inside the QP loops and are slower end to end — 127 ms vs 109 ms per batch of 8192 — although
+     *  shared memory would admit 4).
+     *  Factor in a global (L2) slot — large problems with heavy AD code (kite 12 x 1): ONE CTA of 256 threads per SM.  Per-instance
+     *  latency is what counts there (one SQP iteration is 10-25 M cycles) and the 255-register budget halves the spills:
+     *  measured on kite 12 x 1, batch 1024: 128 threads x 2 CTAs 4.1 k / 8.4 k it/s (exact / fast), 256 x 2 4.8 k / 10.9 k,
+     *  256 x 1 6.5 k / 16.1 k. */
+#ifdef PMB_SQP_THREADS
+    static constexpr int THREADS = PMB_SQP_THREADS;
+#else
+    static constexpr int THREADS = IN_SMEM ? 128 : 256;
+#endif
 #ifdef PMB_MINB
     static constexpr int MIN_BLOCKS = PMB_MINB;
 #else
-    static constexpr int MIN_BLOCKS = !IN_SMEM ? 2 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
+    static constexpr int MIN_BLOCKS = !IN_SMEM ? 1 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
 #endif
     /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors      (factor in shared memory)
      *                 Cta scratch | SQP scratch | QP vectors                              (factor in global scratch) */

@@ -70,11 +70,9 @@ template <class Body, class... Args>
 inline cudaError_t launch(int grid, size_t smem, cudaStream_t stream, Args... args)
 {
     if (grid <= 0) return cudaSuccess;
-    static size_t configured = 0;   // per instantiation
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {   // per device and cheap: set unconditionally (a cached flag would be wrong on a second device)
         cudaError_t e = cudaFuncSetAttribute(pmb_kernel<Body, Args...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     pmb_kernel<Body, Args...><<<grid, Body::THREADS, smem, stream>>>(args...);
     return cudaGetLastError();

@@ -28,7 +28,7 @@ def _load_dropin_plugin(kind):
     lib = os.path.join(d, "_build", f"libdropin_{kind}.so")
     if kind == "emu" or not os.path.exists(lib):
         subprocess.run(["make", "-C", d, kind], check=True, stdout=subprocess.DEVNULL)
-    _plugins[kind] = ctypes.CDLL(lib, mode=ctypes.RTLD_GLOBAL)
+    _plugins[kind] = ctypes.CDLL(lib)      # resolves the engine through its own DT_NEEDED entry: the already loaded library
 
 
 @pytest.fixture(scope="session")
@@ -46,7 +46,7 @@ def emu():
     lib = os.path.join(d, "_build", "libpmb_emu.so")
     if not os.path.exists(lib):
         subprocess.run(["make", "-C", d, f"-j{os.cpu_count() or 4}"], check=True, stdout=subprocess.DEVNULL)
-    api = CApi(ctypes.CDLL(lib, mode=ctypes.RTLD_GLOBAL), "emu_")
+    api = CApi(ctypes.CDLL(lib), "emu_")
     _load_dropin_plugin("emu")
     return api
 

@@ -50,3 +50,34 @@ def test_zero_max_iter_and_empty_work(emu, orc):
         out.append(s.primal())
         s.close()
     assert np.array_equal(out[0], out[1])
+
+
+def test_required_outputs_and_borrowed_handles(emu):
+    """a NULL output that the kernel of that operator writes unconditionally is refused with PMB_ERR_BAD_ARGUMENT (it used to be
+    a device null write); the problem handle borrowed from an SQP handle survives pmb_ocp_destroy; the new switches check their
+    arguments"""
+    f = emu._fn
+    o = emu.ocp("mobile_robot_6x2")
+    v = np.zeros(65 * 104)
+    p = v.ctypes.data_as(C.POINTER(C.c_double))
+    assert f("ocp_cost_gradient")(o.h, 1, p, p, p, None) == -2
+    assert f("ocp_equalities")(o.h, 1, p, p, None) == -2
+    assert f("ocp_equalities_linearised")(o.h, 1, p, p, p, None) == -2
+    assert f("ocp_lagrangian_gradient")(o.h, 1, p, p, p, p, None, p, p, p) == -2
+    assert f("ocp_lagrangian_gradient_hessian")(o.h, 1, p, p, p, p, p, None, p, p, p) == -2
+    assert f("ocp_block_bfgs_update")(o.h, 1, None, p, p, None) == -2
+    s = emu.sqp("mobile_robot_6x2", 2)
+    f("sqp_problem").restype = C.c_void_p
+    f("ocp_destroy").argtypes = [C.c_void_p]
+    borrowed = f("sqp_problem")(s.h)
+    f("ocp_destroy")(borrowed)                                            # ignored: the handle belongs to s
+    assert s.d["N"] == 65
+    st = s.settings(); st.max_iter = 1; st.line_search_max_iter = 2; s.set_settings(st)
+    s.solve()
+    assert f("sqp_set_hessian_update")(s.h, 7) == -2
+    assert f("sqp_set_arithmetic")(s.h, 7) == -2
+    assert f("sqp_set_schedule")(s.h, 7) == -2
+    assert f("set_default_arithmetic")(7) == -2
+    with pytest.raises(PmbError):
+        s.trace(4)                                                        # traces were off during the solve
+    s.close()

@@ -17,6 +17,9 @@ import os as _os
 max_iter = int(_os.environ.get("PMB_MAX_ITER", "100"))
 if max_iter != 100:
     st = s.settings(); st.max_iter = max_iter; s.set_settings(st)
+s.set_arithmetic(int(_os.environ.get("PMB_ARITH", "0")))          # 0 exact, 1 fast
+if int(_os.environ.get("PMB_BLOCK_BFGS", "0")):
+    s.set_hessian_update(1)
 s.set_profiling(bool(int(_os.environ.get("PMB_PROFILE", "1"))))
 for _ in range(solves):
     s.reset_guess()

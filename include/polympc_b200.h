@@ -239,6 +239,8 @@ int pmb_sqp_get_stats(const pmb_sqp_t* s, double* stats);
 int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qp_iter, double* alpha, int* bfgs, int* ls_trials, int* qp_factor);
 /* device time of the last pmb_sqp_solve in milliseconds (CUDA events on the engine's stream) and launches it issued */
 double pmb_sqp_last_solve_ms(const pmb_sqp_t* s);
+/* CUDA-event time of the fused sqp_solve launch alone inside the last completed solve (no queue reset, ordering kernel or copies). */
+double pmb_sqp_last_kernel_ms(const pmb_sqp_t* s);
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s);
 /* phase breakdown of the fused sqp_solve kernel: with profiling on, every CTA accumulates the SM cycles it spends in the
  * three phases of an SQP iteration; ms[3] = device time of the kernel (CUDA events on the engine's stream) attributed to

@@ -529,6 +529,7 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf
     return PMB_OK;
 }
 double pmb_sqp_last_solve_ms(const pmb_sqp_t*) { return 0.0; }
+double pmb_sqp_last_kernel_ms(const pmb_sqp_t*) { return 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t*) { return 0; }
 int pmb_sqp_set_stream(pmb_sqp_t*, void*) { return PMB_OK; }
 int pmb_dm_eval(int fn, int n, const double* x, const double* y, double* out)

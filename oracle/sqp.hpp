@@ -203,11 +203,38 @@ struct Sqp {
         return alpha;
     }
 
+    /** tests/control/valet_parking_mpc_test.cpp:110-155: step_size_selection_impl with LSFilter (line_search.hpp:30-98) */
+    double step_size_selection_filter(const double* p, int& trials)
+    {
+        const double tau = settings.tau;
+        const double constr_l1 = constraints_violation(x.data());
+        double cost_1;
+        problem.cost(x.data(), p_static.data(), cost_1);
+        if (filter.is_acceptable(cost_1, constr_l1)) filter.add(cost_1, constr_l1);
+        double alpha = 1.0, cost_step;
+        std::vector<double> x_step(N);
+        trials = 0;
+        for (int i = 1; i < settings.line_search_max_iter; i++) {
+            for (int j = 0; j < N; ++j) { x_step[j] = alpha * p[j]; x_step[j] += x[j]; }
+            problem.cost(x_step.data(), p_static.data(), cost_step);
+            const double constr_step = constraints_violation(x_step.data());
+            cost_val = cost_step;
+            ++trials;
+            if (filter.is_acceptable(cost_step, constr_step)) { filter.add(cost_step, constr_step); return alpha; }
+            else alpha *= tau;
+        }
+        return alpha;
+    }
+
     // The fixed menu of SQPBase CRTP overrides the engine can honour (pmb_sqp_set_hessian_options): both are what the
     // reference's own solvers install, tests/control/minimal_time_test.cpp:90-135
     int opt_exact_hessian = 0;   // update_linearisation_dense_impl := linearisation_dense_impl (exact Hessian at every iteration)
     int opt_gershgorin = 0;      // hessian_regularisation_dense_impl := Gershgorin shift of the diagonal
     int opt_block_bfgs = 0;      // hessian_update_impl := the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)
+    int opt_precond = PRECOND_IDENTITY;   // Preconditioner template argument: RuizEquilibration<..., DENSE | SPARSE> (sqp_base.hpp:605-611, 662-667)
+    int opt_line_search = 0;     // 0: l1 merit (default), 1: the filter line search of tests/control/valet_parking_mpc_test.cpp:110-155
+    LsFilter filter;             // the solver member `filter` of that test: it lives as long as the solver object
+    Ruiz ruiz{N, M, PRECOND_RUIZ_DENSE};
 
     /** minimal_time_test.cpp:90-104; called from linearisation_dense_impl (sqp_base.hpp:316-317).  cwiseAbs().sum() of a
      *  column is taken in sequential ascending order ("parity unpinned": Eigen's order depends on the vector ISA). */
@@ -232,15 +259,23 @@ struct Sqp {
 
     bool iterate_tail(std::vector<double>& p, std::vector<double>& p_lambda)
     {
-        // solve_qp (532-565): status ignored
+        // m_preconditioner.compute (605 / 662), solve_qp (532-565, status ignored), unscale of the solution and of the data (609-611)
+        if (opt_precond != PRECOND_IDENTITY) {
+            ruiz.variant = opt_precond;
+            ruiz.compute(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data());
+        }
         qp.solve(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data(), nullptr, nullptr);
         info.qp_solver_iter += qp.info.iter;
         p = qp.x; p_lambda = qp.y;
+        if (opt_precond != PRECOND_IDENTITY) {
+            ruiz.unscale_solution(p.data(), p_lambda.data());
+            ruiz.unscale_data(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data());
+        }
         tr_qp_iter.push_back(qp.info.iter); tr_qp_factor.push_back(qp.n_factor);
         lam_k = p_lambda;
         for (int i = 0; i < DUAL; ++i) p_lambda[i] -= lam[i];
         int trials = 0;
-        const double alpha = step_size_selection(p.data(), trials);
+        const double alpha = opt_line_search == 1 ? step_size_selection_filter(p.data(), trials) : step_size_selection(p.data(), trials);
         tr_alpha.push_back(alpha); tr_ls_trials.push_back(trials);
         for (int i = 0; i < N; ++i) x[i] += alpha * p[i];
         for (int i = 0; i < DUAL; ++i) lam[i] += alpha * p_lambda[i];

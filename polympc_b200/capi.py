@@ -60,7 +60,7 @@ ABI_FUNCTIONS = [
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
-    "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_solve_launches", "sqp_set_profiling",
+    "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_kernel_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
 ]
 
@@ -150,6 +150,8 @@ class CApi:
         g("sqp_get_trace").argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_int_p, c_int_p, c_int_p]
         g("sqp_last_solve_ms").restype = C.c_double
         g("sqp_last_solve_ms").argtypes = [C.c_void_p]
+        g("sqp_last_kernel_ms").restype = C.c_double
+        g("sqp_last_kernel_ms").argtypes = [C.c_void_p]
         g("sqp_last_solve_launches").restype = C.c_longlong
         g("sqp_last_solve_launches").argtypes = [C.c_void_p]
         g("sqp_set_stream").argtypes = [C.c_void_p, C.c_void_p]
@@ -553,6 +555,9 @@ class Sqp:
 
     def last_solve_ms(self):
         return float(self.api._fn("sqp_last_solve_ms")(self.h))
+
+    def last_kernel_ms(self):
+        return float(self.api._fn("sqp_last_kernel_ms")(self.h))
 
     def last_solve_launches(self):
         return int(self.api._fn("sqp_last_solve_launches")(self.h))

@@ -766,6 +766,7 @@ int pmb_sqp_get_trace(const pmb_sqp_t* s, int rows, int* qi, double* al, int* bf
     return ok ? PMB_OK : PMB_ERR_CUDA;
 }
 double pmb_sqp_last_solve_ms(const pmb_sqp_t* s) { return s ? s->last_ms : 0.0; }
+double pmb_sqp_last_kernel_ms(const pmb_sqp_t* s) { return s ? s->last_kernel_ms : 0.0; }
 long long pmb_sqp_last_solve_launches(const pmb_sqp_t* s) { return s ? s->last_launches : 0; }
 int pmb_sqp_set_profiling(pmb_sqp_t* s, int on) { if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null"); s->profiling = on != 0; return PMB_OK; }
 int pmb_sqp_get_kernel_times(const pmb_sqp_t* s, double* ms, long long* launches)

@@ -187,6 +187,37 @@ int pmb_sqp_set_hessian_options(pmb_sqp_t* s, int exact_every_iteration, int ger
  *                           (tests/control/mpc_wrapper_test.cpp:101-104, cstr_control_test.cpp:128-131 ...). */
 typedef enum pmb_hessian_update { PMB_HESSIAN_BFGS_DENSE = 0, PMB_HESSIAN_BFGS_BLOCK = 1 } pmb_hessian_update_t;
 int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode);
+/* Preconditioner template argument of SQPBase (sqp_base.hpp:605-611, 662-667): m_preconditioner.compute(H, h, A, al, au, lx, ux)
+ * before the QP, unscale(p, p_lambda) and unscale(H, h, A, ...) after it, at every SQP iteration.
+ *   PMB_PRECOND_IDENTITY     IdentityPreconditioner (qp_preconditioners.hpp:28-110) — the default;
+ *   PMB_PRECOND_RUIZ_DENSE   RuizEquilibration<..., DENSE>::compute (qp_preconditioners.hpp:151-220): <= 4 passes of row/column
+ *                            infinity-norm scaling + cost scaling gamma, zero guard = machine epsilon;
+ *   PMB_PRECOND_RUIZ_SPARSE  RuizEquilibration<..., SPARSE>::compute (:236-300): the same passes with the zero guard 1e-4, no
+ *                            guard on |h|_inf and A scaled as e_i * (A_ij * d_j) — what a SPARSE problem class selects
+ *                            (tests/control/valet_parking_mpc_test.cpp:172). */
+typedef enum pmb_preconditioner { PMB_PRECOND_IDENTITY = 0, PMB_PRECOND_RUIZ_DENSE = 1, PMB_PRECOND_RUIZ_SPARSE = 2 } pmb_preconditioner_t;
+int pmb_sqp_set_preconditioner(pmb_sqp_t* s, int kind);
+/* step_size_selection_impl (sqp_base.hpp:378-419):
+ *   PMB_LS_L1_MERIT  the default backtracking on the l1 merit function;
+ *   PMB_LS_FILTER    the filter line search the reference installs in tests/control/valet_parking_mpc_test.cpp:110-155 with
+ *                    LSFilter (src/solvers/line_search.hpp:30-98): a trial point is taken when no filter entry (f_k, v_k)
+ *                    has f_k - beta v_k <= cost and v_k - beta v_k <= violation; accepted points enter the filter (entries
+ *                    they dominate leave it; at max_depth the oldest leaves).  The filter belongs to the solver object: it
+ *                    survives from one solve to the next (pmb_sqp_set_filter / pmb_sqp_get_filter move it, this call empties it).
+ * filter_max_depth in 1..PMB_FILTER_CAP. */
+typedef enum pmb_line_search { PMB_LS_L1_MERIT = 0, PMB_LS_FILTER = 1 } pmb_line_search_t;
+#define PMB_FILTER_CAP 16
+#define PMB_FILTER_DOUBLES (1 + 2 * PMB_FILTER_CAP)   /* per instance: [size, cost[CAP], violation[CAP]], entry 0 = newest */
+int pmb_sqp_set_line_search(pmb_sqp_t* s, int kind, double filter_beta, int filter_max_depth);
+int pmb_sqp_set_filter(pmb_sqp_t* s, const double* state, int stride);   /* stride 0 broadcasts one state to the batch */
+int pmb_sqp_get_filter(const pmb_sqp_t* s, double* state);
+/* RuizEquilibration on host buffers, stand-alone (stage-wise parity): scales batch x {H[N*N], h[N], A[M*N], Al[M], Au[M], l[N],
+ * u[N]} in place and returns D[N], E[M], c[1] per instance; pmb_ruiz_unscale applies RuizEquilibration::unscale to the QP data
+ * and, when x / y are given, to a primal [N] / dual [M+N] solution (qp_preconditioners.hpp:364-404).  variant = pmb_preconditioner_t. */
+int pmb_ruiz_equilibrate(int N, int M, int batch, int variant, double* H, double* h, double* A, double* Al, double* Au, double* l, double* u,
+                         double* D, double* E, double* c);
+int pmb_ruiz_unscale(int N, int M, int batch, const double* D, const double* E, const double* c, double* H, double* h, double* A, double* Al,
+                     double* Au, double* l, double* u, double* x, double* y);
 /* Arithmetic of the KKT linear algebra inside boxADMM (csrc/pmb_qp.hpp vs csrc/pmb_qp_fast.hpp).  Both run the same
  * algorithm with the same pivot permutation (Eigen::LDLT's diagonal rule):
  *   PMB_ARITH_EXACT  every fp64 operation in the order of the CPU oracle: results are bit-identical to it (default);

@@ -223,6 +223,7 @@ struct Matrix : DenseBase<Matrix<T, R, C>> {
     VecBlock<T> segment(int start, int len) { return VecBlock<T>{m + start, len}; }
     VecBlock<T> head(int len) { return segment(0, len); }
     VecBlock<T> tail(int len) { return segment(R * C - len, len); }
+    PMB_EHD Matrix& noalias() { return *this; }              // every shim product is evaluated into a temporary anyway
 
     template <class O> PMB_EHD Matrix& operator+=(const DenseBase<O>& o) { for (int i = 0; i < R * C; ++i) m[i] = m[i] + o.derived().data()[i]; return *this; }
     template <class O> PMB_EHD Matrix& operator-=(const DenseBase<O>& o) { for (int i = 0; i < R * C; ++i) m[i] = m[i] - o.derived().data()[i]; return *this; }

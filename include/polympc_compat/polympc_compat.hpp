@@ -31,9 +31,12 @@
 //   update_linearisation_*_impl      default (gradient + quasi-Newton update)  |  forwarded to linearisation_*_impl (exact
 //                                    Hessian at every iteration, minimal_time_test.cpp:124-143)
 //   hessian_regularisation_*_impl    default (none)  |  the Gershgorin shift of minimal_time_test.cpp:90-122
-// Anything else — an override that does something the menu does not have, an overridden step_size_selection_impl /
-// constraints_violation_impl / max_constraints_violation_impl / termination_criteria_impl, a non-null iteration_callback, a
-// preconditioner other than Identity, a QP solver other than boxADMM — is REFUSED: solve() prints what it found to stderr and
+//   step_size_selection_impl         default (l1 merit)  |  the LSFilter line search of valet_parking_mpc_test.cpp:110-155 (recognised by
+//                                    running it against scripted cost / violation values; the solver's `filter` member is kept in sync)
+//   Preconditioner                   IdentityPreconditioner  |  RuizEquilibration<..., DENSE | SPARSE>
+// Anything else — an override that does something the menu does not have, another step_size_selection_impl, an overridden
+// constraints_violation_impl / max_constraints_violation_impl / termination_criteria_impl, a non-null iteration_callback,
+// a QP solver other than boxADMM — is REFUSED: solve() prints what it found to stderr and
 // returns with status INVALID_SETTINGS instead of silently running a different algorithm.
 // MATRIXFMT == SPARSE selects the SPARSE *semantics* (block-diagonal quasi-Newton update); storage on the device is dense.
 #pragma once
@@ -48,6 +51,7 @@
 #include <initializer_list>
 #include <iostream>
 #include <limits>
+#include <list>
 #include <stdexcept>
 #include <string>
 #include <typeinfo>
@@ -63,9 +67,12 @@ namespace pmb { namespace compat {
 template <class U> const char* problem_name();
 /** recording of what a Derived solver's hooks call while solve() probes them on the host (thread local) */
 struct HookProbe {
-    enum Event { LAG_GRAD = 1, LAG_GRAD_HESS = 2, HESS_UPDATE_DEFAULT = 3, HESS_UPDATE_OCP = 4 };
+    enum Event { LAG_GRAD = 1, LAG_GRAD_HESS = 2, HESS_UPDATE_DEFAULT = 3, HESS_UPDATE_OCP = 4, COST = 5, VIOLATION = 6 };
     int events[16]; int n = 0;
+    double cost_script[8], viol_script[8]; int n_script = 0, cost_cursor = 0, viol_cursor = 0;   // values handed out by the recorded calls
     void push(int e) { if (n < 16) events[n++] = e; }
+    double next_cost() { return cost_cursor < n_script ? cost_script[cost_cursor++] : 0.0; }
+    double next_viol() { return viol_cursor < n_script ? viol_script[viol_cursor++] : 0.0; }
     bool is(std::initializer_list<int> want) const { if ((int)want.size() != n) return false; int k = 0; for (int e : want) if (events[k++] != e) return false; return true; }
 };
 inline HookProbe*& active_probe() { static thread_local HookProbe* p = nullptr; return p; }
@@ -102,9 +109,10 @@ public:
 };
 typedef std::chrono::time_point<std::chrono::system_clock> time_point;
 inline time_point get_time() { return std::chrono::system_clock::now(); }
-struct IdentityPreconditioner {};
+struct IdentityPreconditioner { static constexpr int pmb_engine_preconditioner = 0; };   // PMB_PRECOND_IDENTITY
 template <typename T> POLYMPC_HD inline void ignore_unused_var(const T&) noexcept {}   // src/utils/helpers.hpp
-template <typename Scalar, int N, int M, int FMT> struct RuizEquilibration {};   // a tag only: SQPBase::solve() refuses it (not on the GPU path)
+/** qp_preconditioners.hpp:113-: a tag that selects the engine's device twin (pmb_sqp_set_preconditioner); FMT = DENSE (0) / SPARSE (1) */
+template <typename Scalar, int N, int M, int FMT = 0> struct RuizEquilibration { static constexpr int pmb_engine_preconditioner = FMT == 1 ? 2 : 1; };
 } // namespace polympc
 
 enum MEMORY { DENSE = 0, SPARSE = 1 };
@@ -161,7 +169,10 @@ public:
     // data members and horizon first, so `ocp.Q.diagonal() << ...; ocp.cost(...)` behaves as in the reference).  `_lagrangian`
     // receives what the reference's dense overloads leave in it: the cost value.
     void cost(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p, scalar_t& cost_) const
-    { chk(pmb_ocp_cost(engine(), 1, var.data(), p.data(), &cost_), "cost"); }
+    {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::COST); cost_ = pr->next_cost(); return; }
+        chk(pmb_ocp_cost(engine(), 1, var.data(), p.data(), &cost_), "cost");
+    }
     void cost_gradient(const Eigen::Ref<const nlp_variable_t>& var, const Eigen::Ref<const static_parameter_t>& p, scalar_t& cost_,
                        Eigen::Ref<nlp_variable_t> cost_grad) const
     { chk(pmb_ocp_cost_gradient(engine(), 1, var.data(), p.data(), &cost_, cost_grad.data()), "cost_gradient"); }
@@ -446,6 +457,39 @@ const char* problem_name()
     namespace pmb { IProblem* pmb_make_##ID() { return compat::make_problem<USER_OCP>(); } }
 #endif // __CUDACC__ || PMB_EMU
 
+// ---- LSFilter (src/solvers/line_search.hpp:30-98): the host-side filter object of a solver ----------------------------------
+// The engine keeps one filter per instance on the device (pmb_sqp_set_line_search); SQPBase::solve() moves the contents of the
+// solver's `filter` member there before the solve and back afterwards, so `solver.filter.beta = ...`, `.clear()` and reading
+// `.m_filter` behave as with the reference.  Front of the list = newest entry.
+template <typename Scalar>
+class LSFilter {
+public:
+    using scalar_t = Scalar;
+    using filter_pair_t = std::pair<Scalar, Scalar>;     // (cost, constraint violation)
+    std::list<filter_pair_t> m_filter;
+    int max_depth{10};
+    scalar_t beta{1e-5};
+
+    void print() const noexcept { std::cout << "Filter: \n"; for (const auto& e : m_filter) std::cout << "( " << e.first << " , " << e.second << " )\n"; }
+    void clear() noexcept { m_filter.clear(); }
+    bool is_dominated(const scalar_t& cost, const scalar_t& constraint) const noexcept
+    { for (const auto& e : m_filter) if (e.first <= cost && e.second <= constraint) return true; return false; }
+    /** no entry may be better in both coordinates, with the margin beta * (its violation) */
+    bool is_acceptable(const scalar_t& cost, const scalar_t& constraint) const noexcept
+    {
+        for (const auto& e : m_filter) { const scalar_t margin = beta * e.second; if (e.first - margin <= cost && e.second - margin <= constraint) return false; }
+        return true;
+    }
+    /** below max_depth: entries the new point dominates leave; at max_depth: the oldest leaves */
+    void add(const scalar_t& cost, const scalar_t& constraint) noexcept
+    {
+        if ((int)m_filter.size() < max_depth) m_filter.remove_if([&](const filter_pair_t& e) { return e.first >= cost && e.second >= constraint; });
+        else m_filter.pop_back();
+        m_filter.emplace_front(cost, constraint);
+    }
+    void remove_one() noexcept { m_filter.pop_back(); }
+};
+
 // ---- SQPBase: one NLP instance on the host, solved by the engine (sqp_base.hpp:64-197, 568-696) --------------------------
 template <typename Derived, typename Problem,
           typename QPSolver = boxADMM<Problem::VAR_SIZE, Problem::NUM_EQ + Problem::NUM_INEQ, typename Problem::scalar_t>,
@@ -473,6 +517,8 @@ public:
         bool exact_hessian_every_iteration = false;   // update_linearisation_*_impl forwards to linearisation_*_impl
         bool gershgorin_regularisation = false;       // hessian_regularisation_*_impl is the Gershgorin shift
         bool block_bfgs = false;                      // hessian_update_impl forwards to the SPARSE problem's block BFGS
+        bool filter_line_search = false;              // step_size_selection_impl is the LSFilter line search of valet_parking_mpc_test.cpp
+        int preconditioner = 0;                       // pmb_preconditioner_t of the Preconditioner template argument
         bool probed = false;
         std::string refused;                          // non-empty: why solve() refuses to run (status INVALID_SETTINGS)
     };
@@ -488,6 +534,7 @@ public:
     nlp_dual_t m_lam;
     nlp_ineq_constraints_t m_lbg, m_ubg;
     parameter_t m_p;
+    scalar_t m_cost = scalar_t(0);  // written by user line searches (sqp_base.hpp:139); cost() reports the engine's value
     nlp_hessian_t m_H;              // host mirror used by the hook probe only (user overrides read this->m_H.rows())
     nlp_variable_t m_lag_gradient;
 
@@ -593,7 +640,23 @@ public:
         hessian_update(lag_hessian, x_step, nlp_variable_t(lag_grad - m_lag_gradient));
         m_lag_gradient = lag_grad;
     }
-    /** defaults of the hooks that have no engine-side alternative: overriding any of them is refused */
+    /** constraints_violation (sqp_base.hpp:233-236, 421-444) for user hooks that call it: eps + |c|_1 + the bound violations,
+     *  evaluated with the engine's operators; under the hook probe it records the call and returns the scripted value */
+    scalar_t constraints_violation(const Eigen::Ref<const nlp_variable_t>& x) noexcept
+    {
+        if (pmb::compat::HookProbe* pr = pmb::compat::active_probe()) { pr->push(pmb::compat::HookProbe::VIOLATION); return scalar_t(pr->next_viol()); }
+        scalar_t v = std::numeric_limits<scalar_t>::epsilon();
+        nlp_eq_constraints_t c; problem.equalities(x, m_p, c);
+        for (int i = 0; i < NUM_EQ; ++i) v += std::fabs(c.data()[i]);
+        if (NUM_INEQ > 0) {
+            nlp_ineq_constraints_t g; problem.inequalities(x, m_p, g);
+            for (int i = 0; i < NUM_INEQ; ++i) v += std::fmax(m_lbg.data()[i] - g.data()[i], scalar_t(0)) + std::fmax(g.data()[i] - m_ubg.data()[i], scalar_t(0));
+        }
+        for (int i = 0; i < VAR_SIZE; ++i) v += std::fmax(m_lbx.data()[i] - x.data()[i], scalar_t(0)) + std::fmax(x.data()[i] - m_ubx.data()[i], scalar_t(0));
+        return v;
+    }
+    /** defaults of the hooks that have no engine-side alternative: overriding any of them is refused — except a
+     *  step_size_selection_impl that is the filter line search (see probe_hooks) */
     scalar_t step_size_selection_impl(const Eigen::Ref<const nlp_variable_t>&) noexcept { return scalar_t(1); }
     scalar_t constraints_violation_impl(const Eigen::Ref<const nlp_variable_t>&) const noexcept { return scalar_t(0); }
     scalar_t max_constraints_violation_impl(const Eigen::Ref<const nlp_variable_t>&) const noexcept { return scalar_t(0); }
@@ -614,6 +677,27 @@ private:
     PMB_COMPAT_OVERRIDES(linearisation_dense_impl)
     PMB_COMPAT_OVERRIDES(linearisation_sparse_impl)
 #undef PMB_COMPAT_OVERRIDES
+
+    /** the solver's public `filter` member when it is an LSFilter<scalar_t> (valet_parking_mpc_test.cpp:112), else nullptr */
+    template <class D> static auto filter_of(D& d, int)
+        -> typename std::enable_if<std::is_same<decltype(d.filter), LSFilter<scalar_t>>::value, LSFilter<scalar_t>*>::type { return &d.filter; }
+    template <class D> static LSFilter<scalar_t>* filter_of(D&, long) { return nullptr; }
+
+    /** host model of the engine's filter line search (csrc/pmb_sqp.hpp::step, LS_FILTER) on scripted values: cost[0], viol[0] are
+     *  the values at x, cost[k], viol[k] those of trial k.  Returns the step length; evals = points evaluated. */
+    static scalar_t filter_search_model(LSFilter<scalar_t>& f, const double* cost, const double* viol, scalar_t tau, int ls_max, int& evals)
+    {
+        evals = 1;
+        if (f.is_acceptable(cost[0], viol[0])) f.add(cost[0], viol[0]);
+        scalar_t alpha = 1;
+        for (int i = 1; i < ls_max; ++i) {
+            const double c = cost[evals], v = viol[evals];
+            ++evals;
+            if (f.is_acceptable(c, v)) { f.add(c, v); return alpha; }
+            alpha *= tau;
+        }
+        return alpha;
+    }
 
     /** Gershgorin shift of the reference's minimal_time_test.cpp:90-104 on the host (probe comparison only) */
     static void host_gershgorin(nlp_hessian_t& H)
@@ -637,14 +721,62 @@ private:
         eo = engine_options_t();
         eo.probed = true;
         auto refuse = [&](const std::string& why) { if (eo.refused.empty()) eo.refused = why; };
-        if (overrides_step_size_selection_impl<Derived>::value) refuse("Derived::step_size_selection_impl overrides the l1-merit line search");
+        if (overrides_step_size_selection_impl<Derived>::value) {
+            // the one recognised override: the filter line search of reference tests/control/valet_parking_mpc_test.cpp:110-155 —
+            // violation and cost at x enter the filter if acceptable, then backtracking until the filter accepts a trial point.
+            // The hook is run against scripted (cost, violation) sequences and must agree with the host model of the device twin
+            // (filter_search_model) in the step length, the number of evaluations and the filter it leaves behind.
+            LSFilter<scalar_t>* flt = filter_of(derived(), 0);
+            if (!flt) refuse("Derived::step_size_selection_impl is overridden and the solver has no public LSFilter member `filter` (only the l1-merit "
+                             "and the filter line search have device twins)");
+            else {
+                const LSFilter<scalar_t> saved = *flt;
+                const nlp_settings_t saved_settings = m_settings;
+                const scalar_t saved_cost = m_cost;
+                struct Scenario { int depth, ls_max, n_seed; double seed[2][2]; int n; double cost[5], viol[5]; };
+                static const Scenario scenarios[4] = {
+                    // empty filter; x accepted; trial 1 rejected; trial 2 dominates everything
+                    {10, 10, 0, {{0, 0}, {0, 0}}, 3, {10, 20, -1000}, {10, 20, 0}},
+                    // trial 2 has a HIGHER cost than x but a much smaller violation: the filter takes it, a merit-like extra test would not
+                    {10, 10, 0, {{0, 0}, {0, 0}}, 3, {10, 20, 15}, {10, 20, 1}},
+                    // a full filter (max_depth 2): x is not acceptable, trial 2 is and pushes the oldest entry out
+                    {2, 10, 2, {{5, 5}, {6, 4}}, 3, {100, 4, 3}, {100, 4.5, 10}},
+                    // nothing is ever accepted: line_search_max_iter - 1 trials, alpha = tau^3
+                    {10, 4, 1, {{-1e9, -1e9}, {0, 0}}, 4, {1, 2, 3, 4}, {1, 2, 3, 4}},
+                };
+                bool ok = true;
+                for (const Scenario& sc : scenarios) {
+                    LSFilter<scalar_t> f0; f0.beta = scalar_t(0.25); f0.max_depth = sc.depth;
+                    for (int k = 0; k < sc.n_seed; ++k) f0.m_filter.emplace_back(sc.seed[k][0], sc.seed[k][1]);
+                    LSFilter<scalar_t> model = f0;
+                    int evals = 0;
+                    const scalar_t alpha_model = filter_search_model(model, sc.cost, sc.viol, m_settings.tau, sc.ls_max, evals);
+                    *flt = f0;
+                    m_settings.line_search_max_iter = sc.ls_max;
+                    P rec;
+                    for (int k = 0; k < sc.n; ++k) { rec.cost_script[k] = sc.cost[k]; rec.viol_script[k] = sc.viol[k]; }
+                    rec.n_script = sc.n;
+                    nlp_variable_t pz; pz.setZero();
+                    pmb::compat::active_probe() = &rec;
+                    const scalar_t alpha = derived().step_size_selection_impl(pz);
+                    pmb::compat::active_probe() = nullptr;
+                    ok = ok && alpha == alpha_model && rec.cost_cursor == evals && rec.viol_cursor == evals && rec.n == 2 * evals &&
+                         flt->m_filter == model.m_filter;
+                }
+                *flt = saved; m_settings = saved_settings; m_cost = saved_cost;
+                if (!ok) refuse("Derived::step_size_selection_impl is overridden and is not the LSFilter line search of the reference's "
+                                "valet_parking_mpc_test.cpp (the only line-search override with a device twin)");
+                else if (flt->max_depth < 1 || flt->max_depth > PMB_FILTER_CAP) refuse("filter.max_depth must be in 1..16 (PMB_FILTER_CAP)");
+                else if ((int)flt->m_filter.size() > PMB_FILTER_CAP) refuse("the filter holds more than PMB_FILTER_CAP entries");
+                else eo.filter_line_search = true;
+            }
+        }
         if (overrides_constraints_violation_impl<Derived>::value) refuse("Derived::constraints_violation_impl is overridden");
         if (overrides_max_constraints_violation_impl<Derived>::value) refuse("Derived::max_constraints_violation_impl is overridden");
         if (overrides_termination_criteria_impl<Derived>::value) refuse("Derived::termination_criteria_impl is overridden");
         if (overrides_linearisation_dense_impl<Derived>::value || overrides_linearisation_sparse_impl<Derived>::value)
             refuse("Derived::linearisation_*_impl is overridden (only the exact AD linearisation exists on the device)");
-        if (!std::is_same<Preconditioner, polympc::IdentityPreconditioner>::value)
-            refuse("a preconditioner other than IdentityPreconditioner was requested (RuizEquilibration is not built)");
+        eo.preconditioner = Preconditioner::pmb_engine_preconditioner;     // IdentityPreconditioner or RuizEquilibration<DENSE | SPARSE>
         if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is not boxADMM (the OSQP-style ADMM is not built)");
         if (m_settings.iteration_callback != nullptr) refuse("settings().iteration_callback is set: a host callback cannot fire inside the fused device loop");
 
@@ -701,7 +833,8 @@ private:
         if (!m_engine_options.refused.empty()) {
             std::cerr << "polympc_b200: SQPBase::solve() REFUSED — " << m_engine_options.refused
                       << ".  The fused sm_100a SQP loop runs the reference's default hooks plus a fixed menu (block BFGS, exact "
-                         "Hessian at every iteration, Gershgorin regularisation); it will not silently run a different algorithm.\n";
+                         "Hessian at every iteration, Gershgorin regularisation, Ruiz equilibration, the LSFilter line search); it will "
+                         "not silently run a different algorithm.\n";
             m_info.iter = 0; m_info.qp_solver_iter = 0; m_info.status.value = sqp_status_t::INVALID_SETTINGS;
             return;
         }
@@ -733,6 +866,19 @@ private:
         check(pmb_sqp_set_hessian_options(m_handle, m_engine_options.exact_hessian_every_iteration, m_engine_options.gershgorin_regularisation),
               "set_hessian_options");
         check(pmb_sqp_set_hessian_update(m_handle, m_engine_options.block_bfgs ? PMB_HESSIAN_BFGS_BLOCK : PMB_HESSIAN_BFGS_DENSE), "set_hessian_update");
+        check(pmb_sqp_set_preconditioner(m_handle, m_engine_options.preconditioner), "set_preconditioner");
+        LSFilter<scalar_t>* flt = m_engine_options.filter_line_search ? filter_of(derived(), 0) : nullptr;
+        double fstate[PMB_FILTER_DOUBLES];
+        if (flt) {                                          // the solver's filter travels to the device and back
+            check(pmb_sqp_set_line_search(m_handle, PMB_LS_FILTER, flt->beta, flt->max_depth), "set_line_search");
+            for (double& v : fstate) v = 0.0;
+            int k = 0;
+            for (const auto& e : flt->m_filter) { fstate[1 + k] = e.first; fstate[1 + PMB_FILTER_CAP + k] = e.second; ++k; }
+            fstate[0] = k;
+            check(pmb_sqp_set_filter(m_handle, fstate, PMB_FILTER_DOUBLES), "set_filter");
+        } else {
+            check(pmb_sqp_set_line_search(m_handle, PMB_LS_L1_MERIT, 0.0, 10), "set_line_search");
+        }
         check(pmb_sqp_set_bounds_x(m_handle, m_lbx.data(), m_ubx.data(), VAR_SIZE), "set_bounds_x");
         if (NUM_INEQ > 0) check(pmb_sqp_set_bounds_g(m_handle, m_lbg.data(), m_ubg.data(), NUM_INEQ), "set_bounds_g");
         if (Problem::ND > 0) check(pmb_sqp_set_parameters(m_handle, m_p.data(), Problem::ND), "set_parameters");
@@ -747,6 +893,12 @@ private:
         m_info.status.value = inf.status == PMB_SQP_SOLVED ? sqp_status_t::SOLVED
                             : (inf.status == PMB_SQP_MAX_ITER_EXCEEDED ? sqp_status_t::MAX_ITER_EXCEEDED : sqp_status_t::INVALID_SETTINGS);
         check(pmb_sqp_get_stats(m_handle, m_stats), "get_stats");
+        m_cost = m_stats[0];
+        if (flt) {
+            check(pmb_sqp_get_filter(m_handle, fstate), "get_filter");
+            flt->m_filter.clear();
+            for (int k = 0; k < (int)fstate[0]; ++k) flt->m_filter.emplace_back(fstate[1 + k], fstate[1 + PMB_FILTER_CAP + k]);
+        }
         if (std::getenv("POLYMPC_B200_REPORT")) {     // one line per solve for harnesses that cannot change the calling code
             bool finite = true;
             for (int i = 0; i < VAR_SIZE; ++i) finite = finite && std::isfinite(m_x(i));
@@ -754,7 +906,8 @@ private:
             std::cerr << "polympc_b200: solve status=" << (int)m_info.status.value << " iter=" << m_info.iter << " qp_iter=" << m_info.qp_solver_iter
                       << " finite=" << (finite ? 1 : 0) << " block_bfgs=" << (m_engine_options.block_bfgs ? 1 : 0)
                       << " exact_hessian=" << (m_engine_options.exact_hessian_every_iteration ? 1 : 0)
-                      << " gershgorin=" << (m_engine_options.gershgorin_regularisation ? 1 : 0) << "\n";
+                      << " gershgorin=" << (m_engine_options.gershgorin_regularisation ? 1 : 0)
+                      << " preconditioner=" << m_engine_options.preconditioner << " filter_ls=" << (m_engine_options.filter_line_search ? 1 : 0) << "\n";
         }
     }
 };

@@ -87,6 +87,9 @@ struct ISqpInst {
     virtual QpSettings& qp_settings() = 0;
     virtual void hessian_options(int exact, int gershgorin) = 0;
     virtual void hessian_update(int block) = 0;
+    virtual void preconditioner(int kind) = 0;
+    virtual void line_search(int kind, double beta, int depth) = 0;
+    virtual LsFilter& filter() = 0;
     virtual SqpInfo& info() = 0;
     virtual std::vector<double>& x() = 0;
     virtual std::vector<double>& lam() = 0;
@@ -108,6 +111,9 @@ struct SqpInst : ISqpInst {
     QpSettings& qp_settings() override { return s.qp.settings; }
     void hessian_options(int exact, int gershgorin) override { s.opt_exact_hessian = exact; s.opt_gershgorin = gershgorin; }
     void hessian_update(int block) override { s.opt_block_bfgs = block; }
+    void preconditioner(int kind) override { s.opt_precond = kind; }
+    void line_search(int kind, double beta, int depth) override { s.opt_line_search = kind; s.filter.clear(); s.filter.beta = beta; s.filter.max_depth = depth; }
+    LsFilter& filter() override { return s.filter; }
     SqpInfo& info() override { return s.info; }
     std::vector<double>& x() override { return s.x; }
     std::vector<double>& lam() override { return s.lam; }
@@ -418,6 +424,71 @@ int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
 {
     if (!s || (mode != PMB_HESSIAN_BFGS_DENSE && mode != PMB_HESSIAN_BFGS_BLOCK)) return PMB_ERR_BAD_ARGUMENT;
     for (auto& i : s->inst) i->hessian_update(mode == PMB_HESSIAN_BFGS_BLOCK);
+    return PMB_OK;
+}
+int pmb_sqp_set_preconditioner(pmb_sqp_t* s, int kind)
+{
+    if (!s || kind < PMB_PRECOND_IDENTITY || kind > PMB_PRECOND_RUIZ_SPARSE) return PMB_ERR_BAD_ARGUMENT;
+    for (auto& i : s->inst) i->preconditioner(kind);
+    return PMB_OK;
+}
+int pmb_sqp_set_line_search(pmb_sqp_t* s, int kind, double beta, int depth)
+{
+    if (!s || (kind != PMB_LS_L1_MERIT && kind != PMB_LS_FILTER)) return PMB_ERR_BAD_ARGUMENT;
+    if (kind == PMB_LS_FILTER && (depth < 1 || depth > PMB_FILTER_CAP || !(beta == beta))) return PMB_ERR_BAD_ARGUMENT;
+    for (auto& i : s->inst) i->line_search(kind, beta, kind == PMB_LS_FILTER ? depth : 10);
+    return PMB_OK;
+}
+int pmb_sqp_set_filter(pmb_sqp_t* s, const double* st, int stride)
+{
+    if (!s || !st || (stride != 0 && stride != PMB_FILTER_DOUBLES)) return PMB_ERR_BAD_ARGUMENT;
+    for (int b = 0; b < s->batch; ++b) {
+        const double* f = st + (size_t)b * stride;
+        const int n = (int)f[0];
+        if (n < 0 || n > PMB_FILTER_CAP) return PMB_ERR_BAD_ARGUMENT;
+        LsFilter& F = s->inst[b]->filter();
+        F.size = n;
+        for (int k = 0; k < PMB_FILTER_CAP; ++k) { F.cost[k] = f[1 + k]; F.constr[k] = f[1 + PMB_FILTER_CAP + k]; }
+    }
+    return PMB_OK;
+}
+int pmb_sqp_get_filter(const pmb_sqp_t* s, double* st)
+{
+    if (!s || !st) return PMB_ERR_BAD_ARGUMENT;
+    for (int b = 0; b < s->batch; ++b) {
+        double* f = st + (size_t)b * PMB_FILTER_DOUBLES;
+        const LsFilter& F = s->inst[b]->filter();
+        f[0] = F.size;
+        for (int k = 0; k < PMB_FILTER_CAP; ++k) { f[1 + k] = k < F.size ? F.cost[k] : 0.0; f[1 + PMB_FILTER_CAP + k] = k < F.size ? F.constr[k] : 0.0; }
+    }
+    return PMB_OK;
+}
+int pmb_ruiz_equilibrate(int N, int M, int batch, int variant, double* H, double* h, double* A, double* Al, double* Au, double* l, double* u,
+                         double* D, double* E, double* c)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !h || !A || !Al || !Au || !l || !u || !D || !E || !c) return PMB_ERR_BAD_ARGUMENT;
+    if (variant != PMB_PRECOND_RUIZ_DENSE && variant != PMB_PRECOND_RUIZ_SPARSE) return PMB_ERR_BAD_ARGUMENT;
+    parallel_for(batch, [&](int b) {
+        Ruiz r(N, M, variant);
+        r.compute(H + (size_t)b * N * N, h + (size_t)b * N, A + (size_t)b * M * N, Al + (size_t)b * M, Au + (size_t)b * M, l + (size_t)b * N, u + (size_t)b * N);
+        for (int k = 0; k < N; ++k) D[(size_t)b * N + k] = r.D[k];
+        for (int k = 0; k < M; ++k) E[(size_t)b * M + k] = r.E[k];
+        c[b] = r.c;
+    });
+    return PMB_OK;
+}
+int pmb_ruiz_unscale(int N, int M, int batch, const double* D, const double* E, const double* c, double* H, double* h, double* A, double* Al,
+                     double* Au, double* l, double* u, double* x, double* y)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !D || !E || !c || !H || !h || !A || !Al || !Au || !l || !u) return PMB_ERR_BAD_ARGUMENT;
+    parallel_for(batch, [&](int b) {
+        Ruiz r(N, M, PMB_PRECOND_RUIZ_DENSE);
+        for (int k = 0; k < N; ++k) r.D[k] = D[(size_t)b * N + k];
+        for (int k = 0; k < M; ++k) r.E[k] = E[(size_t)b * M + k];
+        r.c = c[b];
+        if (x && y) r.unscale_solution(x + (size_t)b * N, y + (size_t)b * (M + N));
+        r.unscale_data(H + (size_t)b * N * N, h + (size_t)b * N, A + (size_t)b * M * N, Al + (size_t)b * M, Au + (size_t)b * M, l + (size_t)b * N, u + (size_t)b * N);
+    });
     return PMB_OK;
 }
 /* the oracle has one arithmetic: the canonical orders of canon.hpp */

@@ -6,6 +6,7 @@
 #pragma once
 #include "ocp.hpp"
 #include "qp.hpp"
+#include "precond.hpp"
 #include <limits>
 
 namespace orc {

@@ -58,11 +58,17 @@ ABI_FUNCTIONS = [
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
     "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_preconditioner", "sqp_set_line_search", "sqp_set_filter", "sqp_get_filter", "ruiz_equilibrate", "ruiz_unscale", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_kernel_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
 ]
+
+
+FILTER_CAP = 16
+FILTER_DOUBLES = 1 + 2 * FILTER_CAP
+PRECOND_IDENTITY, PRECOND_RUIZ_DENSE, PRECOND_RUIZ_SPARSE = 0, 1, 2
+LS_L1_MERIT, LS_FILTER = 0, 1
 
 
 class PmbError(RuntimeError):
@@ -130,6 +136,12 @@ class CApi:
         g("sqp_get_qp_settings").argtypes = [C.c_void_p, C.POINTER(QpSettings)]
         g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
         g("sqp_set_hessian_update").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_set_preconditioner").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_set_line_search").argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        g("sqp_set_filter").argtypes = [C.c_void_p, c_double_p, C.c_int]
+        g("sqp_get_filter").argtypes = [C.c_void_p, c_double_p]
+        g("ruiz_equilibrate").argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [c_double_p] * 10
+        g("ruiz_unscale").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 12
         g("sqp_set_trace").argtypes = [C.c_void_p, C.c_int]
         g("sqp_set_schedule").argtypes = [C.c_void_p, C.c_int]
         g("set_default_arithmetic").argtypes = [C.c_int]
@@ -271,6 +283,29 @@ class CApi:
         self._chk(self._fn("kkt_assemble")(N, M, B, _p(Hc), _p(Ac), _p(_f64(rho_box, (B, N))), _p(_f64(rho_inv, (B, M))),
                                            float(sigma), _p(K)), "kkt_assemble")
         return np.transpose(K, (0, 2, 1)).copy()
+
+    def ruiz_equilibrate(self, variant, H, h, A, Al, Au, l, u):
+        """RuizEquilibration::compute on a batch (row-major numpy matrices in, scaled copies + D, E, c out)"""
+        H = np.asarray(H, dtype=np.float64); A = np.asarray(A, dtype=np.float64)
+        B, N, M = H.shape[0], H.shape[1], A.shape[1]
+        Hc = np.ascontiguousarray(np.transpose(H, (0, 2, 1))); Ac = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+        v = [np.array(_f64(a, (B, n)), copy=True) for a, n in ((h, N), (Al, M), (Au, M), (l, N), (u, N))]
+        D = np.zeros((B, N)); E = np.zeros((B, M)); c = np.zeros(B)
+        self._chk(self._fn("ruiz_equilibrate")(N, M, B, int(variant), _p(Hc), _p(v[0]), _p(Ac), _p(v[1]), _p(v[2]), _p(v[3]), _p(v[4]),
+                                               _p(D), _p(E), _p(c)), "ruiz_equilibrate")
+        return dict(H=np.transpose(Hc, (0, 2, 1)).copy(), h=v[0], A=np.transpose(Ac, (0, 2, 1)).copy(), Al=v[1], Au=v[2], l=v[3], u=v[4], D=D, E=E, c=c)
+
+    def ruiz_unscale(self, D, E, c, H, h, A, Al, Au, l, u, x=None, y=None):
+        H = np.asarray(H, dtype=np.float64); A = np.asarray(A, dtype=np.float64)
+        B, N, M = H.shape[0], H.shape[1], A.shape[1]
+        Hc = np.ascontiguousarray(np.transpose(H, (0, 2, 1))); Ac = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+        v = [np.array(_f64(a, (B, n)), copy=True) for a, n in ((h, N), (Al, M), (Au, M), (l, N), (u, N))]
+        xs = np.array(_f64(x, (B, N)), copy=True) if x is not None else None
+        ys = np.array(_f64(y, (B, M + N)), copy=True) if y is not None else None
+        self._chk(self._fn("ruiz_unscale")(N, M, B, _p(_f64(D, (B, N))), _p(_f64(E, (B, M))), _p(_f64(c, (B,))), _p(Hc), _p(v[0]), _p(Ac),
+                                           _p(v[1]), _p(v[2]), _p(v[3]), _p(v[4]), _p(xs) if xs is not None else None,
+                                           _p(ys) if ys is not None else None), "ruiz_unscale")
+        return dict(H=np.transpose(Hc, (0, 2, 1)).copy(), h=v[0], A=np.transpose(Ac, (0, 2, 1)).copy(), Al=v[1], Au=v[2], l=v[3], u=v[4], x=xs, y=ys)
 
     def bfgs_update(self, Bm, s, y):
         Bm = np.asarray(Bm, dtype=np.float64)
@@ -441,6 +476,24 @@ class Sqp:
         """the fixed menu of SQPBase CRTP overrides (reference tests/control/minimal_time_test.cpp:90-135)"""
         self.api._chk(self.api._fn("sqp_set_hessian_options")(self.h, int(exact_every_iteration), int(gershgorin_regularisation)),
                       "sqp_set_hessian_options")
+
+    def set_preconditioner(self, kind: int):
+        """0 identity, 1 RuizEquilibration<DENSE>, 2 RuizEquilibration<SPARSE> (pmb_preconditioner_t)"""
+        self.api._chk(self.api._fn("sqp_set_preconditioner")(self.h, int(kind)), "sqp_set_preconditioner")
+
+    def set_line_search(self, kind: int, beta: float = 1e-5, max_depth: int = 10):
+        """0 l1 merit, 1 filter line search (pmb_line_search_t); empties the filters"""
+        self.api._chk(self.api._fn("sqp_set_line_search")(self.h, int(kind), float(beta), int(max_depth)), "sqp_set_line_search")
+
+    def set_filter(self, state):
+        state = _f64(state)
+        stride = 0 if state.ndim == 1 else state.shape[1]
+        self.api._chk(self.api._fn("sqp_set_filter")(self.h, _p(state), stride), "sqp_set_filter")
+
+    def filter(self):
+        out = np.zeros((self.batch, FILTER_DOUBLES))
+        self.api._chk(self.api._fn("sqp_get_filter")(self.h, _p(out)), "sqp_get_filter")
+        return out
 
     def set_hessian_update(self, mode: int):
         """0 = dense damped BFGS (SQPBase default), 1 = the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)"""

@@ -176,6 +176,11 @@ struct pmb_sqp {
     pmb_qp_settings_t qp_settings;
     int opt_exact_hessian = 0, opt_gershgorin = 0;   // pmb_sqp_set_hessian_options
     int opt_block_bfgs = 0;                          // pmb_sqp_set_hessian_update
+    int opt_precond = PMB_PRECOND_IDENTITY;          // pmb_sqp_set_preconditioner
+    int opt_line_search = PMB_LS_L1_MERIT;           // pmb_sqp_set_line_search
+    int filter_depth = 10;
+    double filter_beta = 1e-5;
+    pmb::DevBuf<double> ruiz, filter;                // allocated when the option is switched on
     int arithmetic = PMB_ARITH_EXACT;                // pmb_sqp_set_arithmetic
     int schedule = PMB_SCHEDULE_LPT_HISTORY;         // pmb_sqp_set_schedule
     bool have_history = false;                       // info holds the iteration counts of a completed solve of this handle
@@ -449,6 +454,65 @@ int pmb_bfgs_update(int N, int batch, double* Bm, const double* s, const double*
     return PMB_OK;
 }
 
+int pmb_ruiz_equilibrate(int N, int M, int batch, int variant, double* H, double* h, double* A, double* Al, double* Au, double* l, double* u,
+                         double* D, double* E, double* c)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !h || !A || !Al || !Au || !l || !u || !D || !E || !c) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ruiz_equilibrate: bad argument");
+    if (variant != PMB_PRECOND_RUIZ_DENSE && variant != PMB_PRECOND_RUIZ_SPARSE) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ruiz_equilibrate: variant must be PMB_PRECOND_RUIZ_DENSE or _SPARSE");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch, S = (size_t)N + M + 1;
+    Staging st;
+    RuizArgs a{};
+    a.H = st.in((const double*)H, B * N * N); a.h = st.in((const double*)h, B * N); a.A = M ? st.in((const double*)A, B * M * N) : st.out((const double*)A, 1);       // M == 0: never dereferenced, but not null
+    a.Al = M ? st.in((const double*)Al, B * M) : st.out((const double*)Al, 1); a.Au = M ? st.in((const double*)Au, B * M) : st.out((const double*)Au, 1);
+    a.l = st.in((const double*)l, B * N); a.u = st.in((const double*)u, B * N);
+    a.st = st.out((const double*)D, B * S);
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!rt_launch<RuizComputeBody>(batch, RuizComputeBody::smem_bytes(N, M), st.s, N, M, variant, a)) return PMB_ERR_CUDA;
+    std::vector<double> hs(B * S);
+    st.back(H, (const double*)a.H, B * N * N); st.back(h, (const double*)a.h, B * N); st.back(A, (const double*)a.A, B * M * N);
+    st.back(Al, (const double*)a.Al, B * M); st.back(Au, (const double*)a.Au, B * M); st.back(l, (const double*)a.l, B * N); st.back(u, (const double*)a.u, B * N);
+    st.back(hs.data(), (const double*)a.st, B * S);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    for (size_t b = 0; b < B; ++b) {
+        for (int k = 0; k < N; ++k) D[b * N + k] = hs[b * S + k];
+        for (int k = 0; k < M; ++k) E[b * M + k] = hs[b * S + N + k];
+        c[b] = hs[b * S + N + M];
+    }
+    return PMB_OK;
+}
+
+int pmb_ruiz_unscale(int N, int M, int batch, const double* D, const double* E, const double* c, double* H, double* h, double* A, double* Al,
+                     double* Au, double* l, double* u, double* x, double* y)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !D || !E || !c || !H || !h || !A || !Al || !Au || !l || !u) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ruiz_unscale: bad argument");
+    if ((x == nullptr) != (y == nullptr)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "ruiz_unscale: give both x and y or neither");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch, S = (size_t)N + M + 1;
+    std::vector<double> hs(B * S);
+    for (size_t b = 0; b < B; ++b) {
+        for (int k = 0; k < N; ++k) hs[b * S + k] = D[b * N + k];
+        for (int k = 0; k < M; ++k) hs[b * S + N + k] = E[b * M + k];
+        hs[b * S + N + M] = c[b];
+    }
+    Staging st;
+    RuizArgs a{};
+    a.H = st.in((const double*)H, B * N * N); a.h = st.in((const double*)h, B * N); a.A = M ? st.in((const double*)A, B * M * N) : st.out((const double*)A, 1);       // M == 0: never dereferenced, but not null
+    a.Al = M ? st.in((const double*)Al, B * M) : st.out((const double*)Al, 1); a.Au = M ? st.in((const double*)Au, B * M) : st.out((const double*)Au, 1);
+    a.l = st.in((const double*)l, B * N); a.u = st.in((const double*)u, B * N);
+    a.st = st.in((const double*)hs.data(), B * S);
+    a.x = st.in((const double*)x, B * N); a.y = st.in((const double*)y, B * ((size_t)N + M));
+    if (!st.ok) return PMB_ERR_CUDA;
+    if (!rt_launch<RuizUnscaleBody>(batch, RuizUnscaleBody::SMEM, st.s, N, M, a)) return PMB_ERR_CUDA;
+    st.back(H, (const double*)a.H, B * N * N); st.back(h, (const double*)a.h, B * N); st.back(A, (const double*)a.A, B * M * N);
+    st.back(Al, (const double*)a.Al, B * M); st.back(Au, (const double*)a.Au, B * M); st.back(l, (const double*)a.l, B * N); st.back(u, (const double*)a.u, B * N);
+    st.back(x, (const double*)a.x, B * N); st.back(y, (const double*)a.y, B * ((size_t)N + M));
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
 int pmb_ocp_block_bfgs_update(pmb_ocp_t* h, int batch, double* Bm, const double* s, const double* y, int* branch)
 {
     if (!h || batch < 0 || !Bm || !s || !y) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "block_bfgs_update: bad argument");
@@ -535,6 +599,65 @@ int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
     s->opt_block_bfgs = mode == PMB_HESSIAN_BFGS_BLOCK;
     return PMB_OK;
 }
+int pmb_sqp_set_preconditioner(pmb_sqp_t* s, int kind)
+{
+    if (!s || kind < PMB_PRECOND_IDENTITY || kind > PMB_PRECOND_RUIZ_SPARSE) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_preconditioner: bad argument");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const pmb_dims_t& d = s->ocp.impl->dims;
+    if (kind != PMB_PRECOND_IDENTITY && !s->ruiz.resize((size_t)s->batch * (d.N + d.M + 1))) return PMB_ERR_CUDA;
+    s->opt_precond = kind;
+    return PMB_OK;
+}
+
+int pmb_sqp_set_line_search(pmb_sqp_t* s, int kind, double beta, int depth)
+{
+    if (!s || (kind != PMB_LS_L1_MERIT && kind != PMB_LS_FILTER)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_line_search: bad argument");
+    if (kind == PMB_LS_FILTER && (depth < 1 || depth > PMB_FILTER_CAP || !(beta == beta)))
+        PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_line_search: filter_max_depth must be in 1..PMB_FILTER_CAP and filter_beta a number");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    if (kind == PMB_LS_FILTER) {
+        const size_t n = (size_t)s->batch * PMB_FILTER_DOUBLES;
+        if (!s->filter.resize(n) || !rt_memset(s->filter.p, 0, n * sizeof(double), s->stream)) return PMB_ERR_CUDA;   // size 0.0 = empty
+        s->filter_beta = beta; s->filter_depth = depth;
+    }
+    s->opt_line_search = kind;
+    return PMB_OK;
+}
+
+int pmb_sqp_set_filter(pmb_sqp_t* s, const double* state, int stride)
+{
+    if (!s || !state || (stride != 0 && stride != PMB_FILTER_DOUBLES)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_filter: bad argument");
+    if (s->opt_line_search != PMB_LS_FILTER) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_filter: the filter line search is not selected (pmb_sqp_set_line_search)");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const size_t B = s->batch;
+    std::vector<double> tmp;
+    const double* src = state;
+    for (size_t b = 0; b < (stride ? B : 1); ++b) {
+        const double n = state[b * PMB_FILTER_DOUBLES];
+        if (!(n >= 0 && n <= PMB_FILTER_CAP && n == (double)(int)n)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_filter: size out of range");
+    }
+    if (stride == 0) {
+        tmp.resize(B * PMB_FILTER_DOUBLES);
+        for (size_t b = 0; b < B; ++b) std::memcpy(tmp.data() + b * PMB_FILTER_DOUBLES, state, PMB_FILTER_DOUBLES * sizeof(double));
+        src = tmp.data();
+    }
+    return (rt_h2d(s->filter.p, src, B * PMB_FILTER_DOUBLES * sizeof(double), s->stream) && rt_sync(s->stream)) ? PMB_OK : PMB_ERR_CUDA;
+}
+
+int pmb_sqp_get_filter(const pmb_sqp_t* s, double* state)
+{
+    if (!s || !state) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
+    if (s->opt_line_search != PMB_LS_FILTER) PMB_FAIL(PMB_ERR_UNSUPPORTED, "get_filter: the filter line search is not selected (pmb_sqp_set_line_search)");
+    if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    const size_t B = s->batch;
+    if (!(rt_d2h(state, s->filter.p, B * PMB_FILTER_DOUBLES * sizeof(double), s->stream) && rt_sync(s->stream))) return PMB_ERR_CUDA;
+    for (size_t b = 0; b < B; ++b) {            // entries beyond `size` are unspecified on the device: report zeros
+        double* f = state + b * PMB_FILTER_DOUBLES;
+        for (int k = (int)f[0]; k < PMB_FILTER_CAP; ++k) { f[1 + k] = 0.0; f[1 + PMB_FILTER_CAP + k] = 0.0; }
+    }
+    return PMB_OK;
+}
+
 int pmb_set_default_arithmetic(int mode)
 {
     if (mode != PMB_ARITH_EXACT && mode != PMB_ARITH_FAST) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_default_arithmetic: bad mode");
@@ -691,6 +814,8 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     if (rows > 0) { ws.tr_qp_iter = s->tr_qp_iter.p; ws.tr_bfgs = s->tr_bfgs.p; ws.tr_ls = s->tr_ls.p; ws.tr_qp_factor = s->tr_qp_factor.p; ws.tr_alpha = s->tr_alpha.p; }
     ws.trace_rows = rows;
     ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin; ws.opt_block_bfgs = s->opt_block_bfgs;
+    ws.opt_precond = s->opt_precond; ws.opt_line_search = s->opt_line_search; ws.filter_depth = s->filter_depth; ws.filter_beta = s->filter_beta;
+    ws.ruiz = s->ruiz.p; ws.filter = s->filter.p;
     ws.order = nullptr;
     if (s->schedule == PMB_SCHEDULE_LPT_HISTORY && s->have_history && B > s->grid) {
         // longest-processing-time-first from the previous solve's iteration counts (still in s->info at this point of the stream)

@@ -207,6 +207,37 @@ struct BfgsBody {
     }
 };
 
+// ---- RuizEquilibration operators (C ABI pmb_ruiz_equilibrate / pmb_ruiz_unscale), sizes at run time ----------------------------
+struct RuizArgs { double *H, *h, *A, *Al, *Au, *l, *u, *st, *x, *y; };
+struct RuizComputeBody {
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    static size_t smem_bytes(int N, int M) { return (Cta::SCRATCH_DOUBLES + (size_t)N + M) * sizeof(double); }
+    static constexpr const char* NAME = "ruiz_equilibrate";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, int N, int M, int variant, RuizArgs a)
+    {
+        Cta c(w, reinterpret_cast<double*>(smem));
+        const size_t sb = b;
+        RuizCta<0, 0>::compute(c, N, M, variant, a.H + sb * N * N, a.h + sb * N, a.A + sb * M * N, a.Al + sb * M, a.Au + sb * M, a.l + sb * N,
+                               a.u + sb * N, a.st + sb * (N + M + 1), reinterpret_cast<double*>(smem) + Cta::SCRATCH_DOUBLES);
+    }
+};
+struct RuizUnscaleBody {
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = Cta::SCRATCH_DOUBLES * sizeof(double);
+    static constexpr const char* NAME = "ruiz_unscale";
+    static constexpr size_t EMU_STACK_BYTES = 256u << 10;
+    PMB_DEV static void run(const Warp& w, int b, unsigned char* smem, int N, int M, RuizArgs a)
+    {
+        Cta c(w, reinterpret_cast<double*>(smem));
+        const size_t sb = b;
+        RuizCta<0, 0>::unscale(c, N, M, a.st + sb * (N + M + 1), a.H + sb * N * N, a.h + sb * N, a.A + sb * M * N, a.Al + sb * M, a.Au + sb * M,
+                               a.l + sb * N, a.u + sb * N, a.x ? a.x + sb * N : nullptr, a.y ? a.y + sb * (N + M) : nullptr);
+    }
+};
+
 // ---- block BFGS operator (C ABI pmb_ocp_block_bfgs_update): ContinuousOCP<..., SPARSE>::hessian_update_impl ---------------
 template <class O>
 struct BlockBfgsBody {

@@ -11,6 +11,7 @@
 #pragma once
 #include "pmb_ocp.hpp"
 #include "pmb_qp.hpp"
+#include "pmb_precond.hpp"
 
 namespace pmb {
 
@@ -147,6 +148,12 @@ struct SqpWs {
     int opt_exact_hessian;       // pmb_sqp_set_hessian_options: exact Lagrangian Hessian at every iteration (no BFGS)
     int opt_gershgorin;          //                              Gershgorin shift after every exact Hessian
     int opt_block_bfgs;          // pmb_sqp_set_hessian_update: the OCP's block BFGS instead of the dense damped BFGS
+    int opt_precond;             // pmb_sqp_set_preconditioner: PRECOND_IDENTITY / RUIZ_DENSE / RUIZ_SPARSE
+    int opt_line_search;         // pmb_sqp_set_line_search: LS_L1_MERIT / LS_FILTER
+    int filter_depth;            //                          LSFilter::max_depth
+    double filter_beta;          //                          LSFilter::beta
+    double* ruiz;                // batch x (N + M + 1): D, E, c of the current QP (only with a preconditioner)
+    double* filter;              // batch x FILTER_DOUBLES: the filter of each solver object (only with the filter line search)
     const int* order;            // work-queue order (pmb_sqp_set_schedule): ticket q solves instance order[q]; nullptr = identity
     unsigned long long* phase;   // profiling, cycles of thread 0 summed over CTAs: {linearise, qp, step}, [3] = instance-iterations,
                                  // [4..9] = QP {pivot, gather, factor, solve, update, resid}, [10] = ADMM trips, [11] = line-search trials
@@ -166,6 +173,7 @@ struct SqpInst {
     PMB_INST_F(double, p, O::N) PMB_INST_F(double, plam, O::DUAL) PMB_INST_F(double, stats, 4)
     PMB_INST_F(const double, lbx, O::N) PMB_INST_F(const double, ubx, O::N) PMB_INST_F(const double, lbg, O::NUM_INEQ)
     PMB_INST_F(const double, ubg, O::NUM_INEQ) PMB_INST_F(const double, d, O::ND)
+    PMB_INST_F(double, ruiz, O::N + O::M + 1) PMB_INST_F(double, filter, FILTER_DOUBLES)
     PMB_INST_F(pmb_sqp_info_t, info, 1) PMB_INST_F(pmb_qp_info_t, qp_info, 1) PMB_INST_F(int, qp_nfac, 1)
 #undef PMB_INST_F
     // decision trace rows (arrays may be null)
@@ -339,7 +347,8 @@ struct SqpDev {
 
         // ---- step_size_selection_impl (378-419)
         double constr_l1, cost_1;
-        if (NUM_INEQ == 0) {
+        const bool filter_ls = s.ws.opt_line_search == LS_FILTER;
+        if (NUM_INEQ == 0 && s.ws.opt_precond == PRECOND_IDENTITY && !filter_ls) {
             // |c(x)|_1 from the QP bounds al = -c(x) (|-c| == |c| bit for bit), cost(x) from the linearisation
             double cl1 = DBL_EPSILON;
             cl1 += sum_tree32(c, NUM_EQ, [&](int i, double acc) { return acc + dm::fabs(s.al()[i]); });
@@ -350,21 +359,37 @@ struct SqpDev {
         } else {
             merit_terms(c, o, s.x(), s, cg, cost_1, constr_l1);
         }
-        const double mu = norm_inf_cta(c, s.lam_k(), DUAL);
-        const double phi_l1 = cost_1 + mu * constr_l1;
-        const double Dp_phi_l1 = dot_tree32(c, s.h(), s.p(), N) - mu * constr_l1;
         double alpha = 1.0, cost_step = 0.0;
         int trials = 0;
         bool accepted = false;          // cg holds c(x + alpha p) of the accepted trial
-        for (int it = 1; it < st.line_search_max_iter; ++it) {
-            for (int j = tid; j < N; j += nt) { double v = alpha * s.p()[j]; v += s.x()[j]; x_step[j] = v; }
-            c.sync();
-            double viol_step;
-            merit_terms(c, o, x_step, s, cg, cost_step, viol_step);
-            ++trials;
-            const double phi_l1_step = cost_step + mu * viol_step;
-            if (phi_l1_step <= (phi_l1 + alpha * st.eta * Dp_phi_l1)) { accepted = true; break; }
-            alpha = st.tau * alpha;
+        if (!filter_ls) {
+            const double mu = norm_inf_cta(c, s.lam_k(), DUAL);
+            const double phi_l1 = cost_1 + mu * constr_l1;
+            const double Dp_phi_l1 = dot_tree32(c, s.h(), s.p(), N) - mu * constr_l1;
+            for (int it = 1; it < st.line_search_max_iter; ++it) {
+                for (int j = tid; j < N; j += nt) { double v = alpha * s.p()[j]; v += s.x()[j]; x_step[j] = v; }
+                c.sync();
+                double viol_step;
+                merit_terms(c, o, x_step, s, cg, cost_step, viol_step);
+                ++trials;
+                const double phi_l1_step = cost_step + mu * viol_step;
+                if (phi_l1_step <= (phi_l1 + alpha * st.eta * Dp_phi_l1)) { accepted = true; break; }
+                alpha = st.tau * alpha;
+            }
+        } else {
+            // the filter line search of reference tests/control/valet_parking_mpc_test.cpp:110-155 (LSFilter, line_search.hpp:30-98)
+            double* flt = s.filter();
+            const double beta = s.ws.filter_beta;
+            if (filter_is_acceptable(flt, beta, cost_1, constr_l1)) filter_add(c, flt, s.ws.filter_depth, cost_1, constr_l1);
+            for (int it = 1; it < st.line_search_max_iter; ++it) {
+                for (int j = tid; j < N; j += nt) { double v = alpha * s.p()[j]; v += s.x()[j]; x_step[j] = v; }
+                c.sync();
+                double viol_step;
+                merit_terms(c, o, x_step, s, cg, cost_step, viol_step);
+                ++trials;
+                if (filter_is_acceptable(flt, beta, cost_step, viol_step)) { filter_add(c, flt, s.ws.filter_depth, cost_step, viol_step); accepted = true; break; }
+                alpha *= st.tau;
+            }
         }
 
         // ---- take the step (626-632)
@@ -405,7 +430,11 @@ struct SqpDev {
             const unsigned long long t0 = c.w.clock();
             const double cost_x = linearise<FAST>(c, o, s, it == 1 || s.ws.opt_exact_hessian != 0, row, scratch);
             const unsigned long long t1 = c.w.clock();
+            if (s.ws.opt_precond != PRECOND_IDENTITY)      // m_preconditioner.compute (sqp_base.hpp:605, 662)
+                RuizCta<N, M>::compute(c, N, M, s.ws.opt_precond, s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.ruiz(), scratch);
             qp_solve_cta<R, N, M, NW, FAST>(c, qst, qa, Lp, vec);
+            if (s.ws.opt_precond != PRECOND_IDENTITY)      // unscale(p, p_lambda), unscale(H, h, A, ...) (609-611, 666-667)
+                RuizCta<N, M>::unscale(c, N, M, s.ruiz(), s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.p(), s.plam());
             const unsigned long long t2 = c.w.clock();
             const bool done = step(c, o, s, st, row, scratch, cost_x);
             const unsigned long long t3 = c.w.clock();

@@ -57,9 +57,36 @@ public:
     void hessian_regularisation_dense_impl(Eigen::Ref<nlp_hessian_t> H) noexcept { for (int i = 0; i < Problem::VAR_SIZE; ++i) H(i, i) += 1.0; }
 };
 
-// (f) Ruiz preconditioner requested: refused; (g) OSQP-style ADMM requested: refused
+// (f) Ruiz preconditioner requested: accepted (pmb_sqp_set_preconditioner); (g) OSQP-style ADMM requested: refused
 using Ruiz = polympc::RuizEquilibration<double, OCP::VAR_SIZE, OCP::NUM_EQ, DENSE>;
 template <typename Problem, typename QPSolver = BoxQP> class WithRuiz : public SQPBase<WithRuiz<Problem, QPSolver>, Problem, QPSolver, Ruiz> {};
+
+// (h) a filter line search written like the reference's tests/control/valet_parking_mpc_test.cpp:110-155: accepted;
+// (i) the same with an extra sufficient-decrease test the engine does not have: refused
+template <typename Problem, bool EXTRA_TEST, typename QPSolver = BoxQP>
+class FilterSearch : public SQPBase<FilterSearch<Problem, EXTRA_TEST, QPSolver>, Problem, QPSolver> {
+public:
+    using Base = SQPBase<FilterSearch<Problem, EXTRA_TEST, QPSolver>, Problem, QPSolver>;
+    using typename Base::scalar_t; using typename Base::nlp_variable_t; using typename Base::nlp_hessian_t;
+    LSFilter<scalar_t> filter;
+    scalar_t step_size_selection_impl(const Eigen::Ref<const nlp_variable_t>& p) noexcept
+    {
+        scalar_t v0 = this->constraints_violation(this->m_x), f0;
+        this->problem.cost(this->m_x, this->m_p, f0);
+        if (filter.is_acceptable(f0, v0)) filter.add(f0, v0);
+        scalar_t alpha = 1;
+        for (int i = 1; i < this->m_settings.line_search_max_iter; i++) {
+            nlp_variable_t xs = alpha * p; xs += this->m_x;
+            scalar_t f, v;
+            this->problem.cost(xs, this->m_p, f);
+            v = this->constraints_violation(xs);
+            this->m_cost = f;
+            if (filter.is_acceptable(f, v) && (!EXTRA_TEST || f < f0)) { filter.add(f, v); return alpha; }
+            alpha *= this->m_settings.tau;
+        }
+        return alpha;
+    }
+};
 using OsqpAdmm = ADMM<OCP::VAR_SIZE, OCP::NUM_EQ + OCP::NUM_INEQ, double>;
 template <typename Problem, typename QPSolver = OsqpAdmm> class WithAdmm : public SQPBase<WithAdmm<Problem, QPSolver>, Problem, QPSolver> {};
 
@@ -88,7 +115,13 @@ int main(int argc, char** argv)
     { Sr1<OCP> s; EXPECT(run(s, "home-made SR1") == sqp_status_t::INVALID_SETTINGS); }
     { FullStep<OCP> s; EXPECT(run(s, "custom line search") == sqp_status_t::INVALID_SETTINGS); }
     { ShiftAll<OCP> s; EXPECT(run(s, "custom regulariser") == sqp_status_t::INVALID_SETTINGS); }
-    { WithRuiz<OCP> s; EXPECT(run(s, "RuizEquilibration") == sqp_status_t::INVALID_SETTINGS); }
+    { FilterSearch<OCP, true> s; EXPECT(run(s, "filter search + extra test") == sqp_status_t::INVALID_SETTINGS); }
+    if (have_engine) {
+        WithRuiz<OCP> r; EXPECT(run(r, "RuizEquilibration") != sqp_status_t::INVALID_SETTINGS); EXPECT(r.engine_options().preconditioner == 1);
+        FilterSearch<OCP, false> f; f.filter.beta = 0.1; f.filter.add(1e9, 1e9);
+        EXPECT(run(f, "filter line search") != sqp_status_t::INVALID_SETTINGS); EXPECT(f.engine_options().filter_line_search);
+        EXPECT(f.filter.beta == 0.1 && f.filter.m_filter.size() >= 1 && f.filter.m_filter.back().first != 1e9);   // probed without a trace; synced back (the dominated seed left)
+    }
     { WithAdmm<OCP> s; EXPECT(run(s, "OSQP-style ADMM") == sqp_status_t::INVALID_SETTINGS); }
     { Plain<OCP> s; s.settings().iteration_callback = &on_iteration; EXPECT(run(s, "iteration_callback") == sqp_status_t::INVALID_SETTINGS); }
     std::printf("%d failures\n", g_fail);

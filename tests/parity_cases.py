@@ -168,24 +168,63 @@ def kkt_case(api, orc, N, M, B=3, seed=0):
     assert_same(api.kkt_assemble(H, A, rb, ri, 1e-6), orc.kkt_assemble(H, A, rb, ri, 1e-6), "kkt")
 
 
-def solve_workload(api, w, lo=0, hi=None, name=None, hessian_update=0):
+def solve_workload(api, w, lo=0, hi=None, name=None, hessian_update=0, preconditioner=0, line_search=0, filter_beta=0.1, filter_depth=10,
+                   solves=1):
     hi = w.batch if hi is None else hi
     s = api.sqp(name or w.name, hi - lo)
     W.configure(s, w, lo, hi)
     s.set_trace(True)
     if hessian_update:
         s.set_hessian_update(hessian_update)
-    s.solve()
+    if preconditioner:
+        s.set_preconditioner(preconditioner)
+    if line_search:
+        s.set_line_search(line_search, filter_beta, filter_depth)
+    for _ in range(solves):            # a second solve warm-starts from the kept iterate (and the kept filter)
+        s.solve()
     out = dict(x=s.primal(), lam=s.dual(), info=s.info(), stats=s.stats(), trace=s.trace(w.sqp_max_iter),
                ms=s.last_solve_ms(), launches=s.last_solve_launches())
+    if line_search:
+        out["filter"] = s.filter()
     s.close()
     return out
 
 
-def sqp_case(api, orc, w, hessian_update=0):
+def ruiz_case(api, orc, N, M, B=4, seed=0, variant=1):
+    """RuizEquilibration::compute and both unscale overloads as operators (qp_preconditioners.hpp:151-300, 364-404): badly scaled
+    data, an empty row / column (the zero guards), infinite box bounds"""
+    rng = np.random.default_rng(seed)
+    H = rng.standard_normal((B, N, N)); H = H + H.transpose(0, 2, 1)
+    A = rng.standard_normal((B, M, N)) * 10.0 ** rng.integers(-3, 4, (B, M, 1))
+    h = rng.standard_normal((B, N)) * 50
+    if B > 1:
+        H[1, :, N // 2] = 0; H[1, N // 2, :] = 0; A[1, :, N // 2] = 0      # a zero column of [H; A]
+    if B > 2 and M > 0:
+        A[2, M // 2, :] = 0                                              # a zero row of A
+    if B > 3:
+        H[3] *= 1e-6; A[3] *= 1e-5; h[3] = 0.0                           # below the SPARSE guard 1e-4, zero gradient
+    l = -np.abs(rng.standard_normal((B, N))); u = np.abs(rng.standard_normal((B, N)))
+    l[:, 0] = -np.inf; u[:, 1] = np.inf
+    args = (H, h, A, -np.abs(rng.standard_normal((B, M))), np.abs(rng.standard_normal((B, M))), l, u)
+    ra, rb = api.ruiz_equilibrate(variant, *args), orc.ruiz_equilibrate(variant, *args)
+    for k in rb:
+        assert_same(ra[k], rb[k], "ruiz." + k)
+    x = rng.standard_normal((B, N)); y = rng.standard_normal((B, N + M))
+    un = lambda a, r: a.ruiz_unscale(r["D"], r["E"], r["c"], r["H"], r["h"], r["A"], r["Al"], r["Au"], r["l"], r["u"], x=x, y=y)
+    ua, ub = un(api, rb), un(orc, rb)
+    for k in ub:
+        assert_same(ua[k], ub[k], "ruiz_unscale." + k)
+    # the round trip restores the QP data to rounding
+    assert np.abs(ub["H"] - H).max() <= 1e-12 * max(1.0, np.abs(H).max()) and (M == 0 or np.abs(ub["A"] - A).max() <= 1e-12 * np.abs(A).max())
+    return rb
+
+
+def sqp_case(api, orc, w, hessian_update=0, **opts):
     """a11-a14, a22: whole SQP solves; iterates, multipliers, info and the per-iteration decision trace"""
-    ra = solve_workload(api, w, hessian_update=hessian_update)
-    rb = solve_workload(orc, w, name=ORACLE_TWIN.get(w.name, w.name), hessian_update=hessian_update)
+    ra = solve_workload(api, w, hessian_update=hessian_update, **opts)
+    rb = solve_workload(orc, w, name=ORACLE_TWIN.get(w.name, w.name), hessian_update=hessian_update, **opts)
+    if "filter" in rb:
+        assert_same(ra["filter"], rb["filter"], "sqp.filter")
     for f in ("iter", "qp_solver_iter", "status"):
         assert_same(ra["info"][f], rb["info"][f], "sqp.info." + f)
     for k in ("qp_iter", "bfgs", "ls_trials", "qp_factor", "alpha"):
@@ -193,4 +232,47 @@ def sqp_case(api, orc, w, hessian_update=0):
     assert_same(ra["x"], rb["x"], "sqp.x")
     assert_same(ra["lam"], rb["lam"], "sqp.lam")
     assert_same(ra["stats"], rb["stats"], "sqp.stats")
+    return ra, rb
+
+
+def valet_parking_solve(api, x0_first, x0_second, preconditioner=2, line_search=1, name="mobile_robot_5x3"):
+    """the setup of reference tests/control/valet_parking_mpc_test.cpp:175-235 for a batch of (first, second) initial states:
+    robot 5 x 3 on [0, 2], d = 2, SQP 10 / 10, QP max_iter 1000, filter beta 0.1, block BFGS (SPARSE problem), Ruiz equilibration
+    (SPARSE), controls bounded on the last 11 nodes only (`tail(22)`), the state pinned at offset 30 (`segment(30, 3)`) — both as the
+    test writes them —, then a second, warm-started solve from another pinned state.  Returns the results of both solves."""
+    x0_first = np.atleast_2d(np.asarray(x0_first, dtype=np.float64)); x0_second = np.atleast_2d(np.asarray(x0_second, dtype=np.float64))
+    B = x0_first.shape[0]
+    s = api.sqp(name, B)
+    d = s.d
+    s.problem.set_time_limits(0.0, 2.0)
+    st = s.settings(); st.max_iter = 10; st.line_search_max_iter = 10; s.set_settings(st)
+    q = s.qp_settings(); q.max_iter = 1000; s.set_qp_settings(q)
+    s.set_parameters(np.array([2.0]))
+    s.set_trace(True)
+    s.set_hessian_update(1); s.set_preconditioner(preconditioner); s.set_line_search(line_search, 0.1, 10)
+    N = d["N"]
+    lb = np.full((B, N), -np.inf); ub = np.full((B, N), np.inf)
+    ub[:, -22:] = np.tile([1.5, 0.75], 11); lb[:, -22:] = np.tile([-1.5, -0.75], 11)
+    s.set_primal(np.zeros(N)); s.set_dual(np.zeros(d["DUAL"]))
+    outs = []
+    for x0 in (x0_first, x0_second):
+        lb[:, 30:33] = x0; ub[:, 30:33] = x0
+        s.set_bounds_x(lb, ub)
+        s.solve()
+        outs.append(dict(x=s.primal(), lam=s.dual(), info=s.info(), stats=s.stats(), trace=s.trace(10),
+                         filter=s.filter() if line_search else None))
+    s.close()
+    return outs
+
+
+def valet_parking_case(api, orc, x0_first, x0_second, **kw):
+    ra, rb = valet_parking_solve(api, x0_first, x0_second, **kw), valet_parking_solve(orc, x0_first, x0_second, **kw)
+    for k, (a, b) in enumerate(zip(ra, rb)):
+        for f in ("iter", "qp_solver_iter", "status"):
+            assert_same(a["info"][f], b["info"][f], f"valet solve {k}: info." + f)
+        for f in ("qp_iter", "bfgs", "ls_trials", "qp_factor", "alpha"):
+            assert_same(a["trace"][f], b["trace"][f], f"valet solve {k}: trace." + f)
+        assert_same(a["x"], b["x"], f"valet solve {k}: x"); assert_same(a["lam"], b["lam"], f"valet solve {k}: lam")
+        if b["filter"] is not None:
+            assert_same(a["filter"], b["filter"], f"valet solve {k}: filter")
     return ra, rb

@@ -38,6 +38,30 @@ def test_null_and_size_checks(emu):
     s.close()
 
 
+def test_preconditioner_and_line_search_arguments(emu):
+    s = emu.sqp("mobile_robot_6x2", 2)
+    f = emu._fn
+    assert f("sqp_set_preconditioner")(s.h, 3) == -2 and f("sqp_set_preconditioner")(s.h, -1) == -2
+    assert f("sqp_set_line_search")(s.h, 2, 0.1, 10) == -2
+    assert f("sqp_set_line_search")(s.h, 1, 0.1, 0) == -2 and f("sqp_set_line_search")(s.h, 1, 0.1, 17) == -2     # depth in 1..PMB_FILTER_CAP
+    assert f("sqp_set_line_search")(s.h, 1, float("nan"), 10) == -2
+    buf = np.zeros((2, 33)); p = buf.ctypes.data_as(C.POINTER(C.c_double))
+    assert f("sqp_get_filter")(s.h, p) == -5                             # PMB_ERR_UNSUPPORTED: the filter line search is off
+    s.set_line_search(1, 0.1, 4)
+    assert (s.filter() == 0).all()
+    buf[:, 0] = 17
+    assert f("sqp_set_filter")(s.h, p, 33) == -2                         # size out of range
+    buf[:, 0] = 2; buf[:, 1:3] = [5.0, 6.0]; buf[:, 17:19] = [1.0, 0.5]
+    s.set_filter(buf)
+    assert np.array_equal(s.filter(), buf)
+    s.set_line_search(1, 0.1, 4)                                         # selecting the line search again empties the filters
+    assert (s.filter()[:, 0] == 0).all()
+    d = np.zeros(4); pd = d.ctypes.data_as(C.POINTER(C.c_double))
+    assert f("ruiz_equilibrate")(2, 1, 1, 0, pd, pd, pd, pd, pd, pd, pd, pd, pd, pd) == -2      # variant must be a Ruiz variant
+    assert f("ruiz_equilibrate")(2, 1, 1, 1, None, pd, pd, pd, pd, pd, pd, pd, pd, pd) == -2
+    s.close()
+
+
 def test_zero_max_iter_and_empty_work(emu, orc):
     """max_iter = 0: like the reference (sqp_base.hpp:583-637 precede the while loop) exactly one iteration is done"""
     from polympc_b200 import workloads as W

@@ -240,3 +240,21 @@ def test_sqp_minimal_time_parking(emu, orc):
     ra, rb = pc.sqp_case(emu, orc, w)
     assert rb["info"]["status"][0] == 0 and rb["info"]["iter"][0] < w.sqp_max_iter
     assert 0.0 < rb["x"][0, -1] < 10.0
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_ruiz_operators(emu, orc, variant):
+    """RuizEquilibration::compute / unscale (qp_preconditioners.hpp:151-300, 364-404), DENSE and SPARSE variants, bit for bit"""
+    pc.ruiz_case(emu, orc, 9, 5, B=4, seed=1, variant=variant)
+    pc.ruiz_case(emu, orc, 33, 20, B=4, seed=2, variant=variant)
+    pc.ruiz_case(emu, orc, 7, 0, B=2, seed=3, variant=variant)
+
+
+def test_sqp_ruiz_and_filter_line_search(emu, orc):
+    """SQPBase with a RuizEquilibration preconditioner (sqp_base.hpp:605-611, 662-667) and the filter line search of the
+    reference's valet_parking_mpc_test.cpp:110-155; two solves, so the second one starts from the kept iterate AND the kept
+    filter (max_depth 3 makes the oldest entry leave)"""
+    w = W.mobile_robot(2, seed=11, sqp_max_iter=3, ls_max_iter=6)
+    ra, rb = pc.sqp_case(emu, orc, w, preconditioner=2, line_search=1, filter_depth=3, solves=2)
+    assert (rb["filter"][:, 0] >= 2).all()
+    pc.sqp_case(emu, orc, w, preconditioner=1)

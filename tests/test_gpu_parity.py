@@ -324,3 +324,37 @@ def test_sqp_codegen_test_setup(pmb, orc):
         s.solve(); outs.append((s.primal(), s.dual(), s.info())); s.close()
     pc.assert_same(outs[0][0], outs[1][0], "x"); pc.assert_same(outs[0][1], outs[1][1], "lam")
     assert outs[1][2]["status"][0] == 0 and outs[1][2]["iter"][0] < 10
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("N,M", [(9, 5), (7, 0), (65, 39), (80, 48), (208, 169)])
+def test_ruiz_operators(pmb, orc, N, M, variant):
+    """RuizEquilibration::compute / unscale (qp_preconditioners.hpp:151-300, 364-404) as batched operators, bit for bit"""
+    pc.ruiz_case(pmb, orc, N, M, B=16, seed=N + variant, variant=variant)
+
+
+@pytest.mark.parametrize("pre,ls", [(1, 0), (2, 0), (0, 1), (2, 1)])
+def test_sqp_preconditioner_and_line_search_vs_oracle(pmb, orc, pre, ls):
+    """RuizEquilibration (DENSE / SPARSE) around every QP and the filter line search, robot 6 x 2, two solves (kept filter)"""
+    w = W.mobile_robot(512, sqp_max_iter=20, ls_max_iter=20)
+    ra, rb = pc.sqp_case(pmb, orc, w, preconditioner=pre, line_search=ls, filter_depth=4, solves=2)
+    assert np.isfinite(rb["x"]).all() and (rb["info"]["status"] == 0).mean() > 0.9
+
+
+def test_sqp_ruiz_cstr_vs_oracle(pmb, orc):
+    """the CSTR's badly scaled QPs (states ~100, inputs ~1e4) are what equilibration is for"""
+    w = W.cstr(256, sqp_max_iter=20, ls_max_iter=20)
+    ra, rb = pc.sqp_case(pmb, orc, w, hessian_update=1, preconditioner=2)
+    assert np.isfinite(rb["x"]).all()
+
+
+def test_valet_parking_test_setup_vs_oracle(pmb, orc):
+    """tests/control/valet_parking_mpc_test.cpp:175-235 on 256 pairs of pinned states; pair 0 is the reference's own
+    ((0.5, 0.5, 0.5) then (0.3, 0.4, 0.45): SOLVED, iter < 10 both times)"""
+    rng = np.random.default_rng(5)
+    a = np.column_stack([rng.uniform(-1, 1, 256), rng.uniform(-1, 1, 256), rng.uniform(-0.7, 0.7, 256)]); a[0] = [0.5, 0.5, 0.5]
+    b = a + rng.uniform(-0.2, 0.2, a.shape); b[0] = [0.3, 0.4, 0.45]
+    ra, rb = pc.valet_parking_case(pmb, orc, a, b)
+    for r in rb:
+        assert r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 10
+    assert (rb[0]["info"]["status"] == 0).mean() > 0.8

@@ -63,3 +63,32 @@ def test_minimal_time_setup(orc):
     s = orc.sqp(w.name, 1); W.configure(s, w); s.solve()
     info, x = s.info(), s.primal(); s.close()
     assert info["status"][0] == 0 and info["iter"][0] < 20 and 0.0 < x[0, -1] < 10.0
+
+
+def test_valet_parking_test_setup(orc):
+    """tests/control/valet_parking_mpc_test.cpp:175-235 (filter line search with LSFilter, block BFGS, RuizEquilibration<SPARSE>):
+    the reference asserts SOLVED and iter < max_iter for the cold solve and for the warm-started one"""
+    import parity_cases as pc
+    first, second = pc.valet_parking_solve(orc, [0.5, 0.5, 0.5], [0.3, 0.4, 0.45])
+    for r in (first, second):
+        assert r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 10
+    assert second["filter"][0, 0] >= 1                       # the filter lives on between the two solves
+    # the dense variant of the preconditioner and the identity solve the same problem
+    for pre in (0, 1):
+        a, b = pc.valet_parking_solve(orc, [0.5, 0.5, 0.5], [0.3, 0.4, 0.45], preconditioner=pre)
+        assert a["info"]["status"][0] == 0 and b["info"]["status"][0] == 0
+        assert np.abs(a["x"] - first["x"]).max() < 1e-2
+
+
+def test_ruiz_equilibration_properties(orc):
+    """RuizEquilibration::compute (qp_preconditioners.hpp:151-300): after <= 4 passes the row / column infinity norms of the
+    scaled [H A'; A 0] are within a factor of a few of each other, zero rows / columns are left alone, the scaling is undone by
+    unscale() to rounding, and infinite box bounds stay infinite"""
+    import parity_cases as pc
+    for variant in (1, 2):
+        r = pc.ruiz_case(orc, orc, 20, 11, B=4, seed=5, variant=variant)
+        assert np.isfinite(r["D"]).all() and np.isfinite(r["E"]).all() and (r["c"] > 0).all()
+        assert np.isinf(r["l"][:, 0]).all() and np.isinf(r["u"][:, 1]).all()
+        assert r["D"][1, 10] == 1.0                           # the empty column keeps scale 1 (the zero guard)
+        coln = np.maximum(np.abs(r["H"][0]).max(axis=0) / r["c"][0], np.abs(r["A"][0]).max(axis=0))
+        assert coln.max() / coln.min() < 30.0

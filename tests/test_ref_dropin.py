@@ -76,6 +76,25 @@ def _check_minimal_time(rc, out):
     assert len(sol) == 1 and sol[0]["exact_hessian"] == 1 and sol[0]["gershgorin"] == 1 and sol[0]["status"] == 0 and sol[0]["finite"] == 1, out
 
 
+def _check_valet_parking(rc, out):
+    """valet_parking_mpc_test.cpp:175-235: a Solver with the LSFilter line search, block BFGS and RuizEquilibration<SPARSE>; the
+    reference asserts SOLVED and iter < max_iter for the cold and for the warm-started solve.  Oracle: 6 and 4 iterations."""
+    assert rc == 0 and "0 failed expectations" in out, out
+    sol = _solves(out)
+    assert len(sol) == 2 and all(r["status"] == 0 and r["finite"] == 1 and r["block_bfgs"] == 1 and r["preconditioner"] == 2 and
+                                 r["filter_ls"] == 1 for r in sol), out
+    assert [r["iter"] for r in sol] == [6, 4], out
+
+
+def test_reference_valet_parking_test_passes_on_the_emulator(emu):
+    _check_valet_parking(*_run(_binary("emu_valet_parking_mpc_test", "emu")))
+
+
+@pytest.mark.gpu
+def test_reference_valet_parking_test_passes_on_the_gpu(pmb):
+    _check_valet_parking(*_run(_binary("valet_parking_mpc_test", "all")))
+
+
 def test_reference_minimal_time_test_passes_on_the_emulator(emu):
     _check_minimal_time(*_run(_binary("emu_minimal_time_test", "emu")))
 
@@ -86,9 +105,10 @@ def test_reference_minimal_time_test_passes_on_the_gpu(pmb):
 
 
 def test_unsupported_hook_overrides_are_refused(emu):
-    """tests/cpp/test_hook_refusal.cpp: a home-made quasi-Newton update, a custom line search, a custom regulariser, a Ruiz
-    preconditioner, the OSQP-style ADMM and an iteration callback are each refused with INVALID_SETTINGS and a message on
-    stderr; the default solver and one that forwards hessian_update_impl to a DENSE problem are accepted and agree bit for bit"""
+    """tests/cpp/test_hook_refusal.cpp: a home-made quasi-Newton update, a custom line search, a filter line search with an extra
+    acceptance test, a custom regulariser, the OSQP-style ADMM and an iteration callback are each refused with INVALID_SETTINGS
+    and a message on stderr; the default solver, one that forwards hessian_update_impl to a DENSE problem (bit-identical to the
+    default), one with a RuizEquilibration preconditioner and one with the reference-style LSFilter line search are accepted"""
     rc, out = _run(_binary("emu_hook_refusal_test", "emu_hooks", needs_reference=False), "with_engine")
     assert rc == 0 and "0 failures" in out, out
     assert out.count("SQPBase::solve() REFUSED") == 6, out

@@ -316,13 +316,18 @@ struct SqpSolveBody {
 #else
     static constexpr int MIN_BLOCKS = !IN_SMEM ? 1 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
 #endif
-    /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors      (factor in shared memory)
-     *                 Cta scratch | SQP scratch | QP vectors                              (factor in global scratch) */
+    /** exact arithmetic with the factor in a global slot: the 32 x 32 diagonal blocks of the factor are staged in shared memory
+     *  for the substitutions (pmb_qp.hpp::ldlt_stage_diag_blocks) */
+    static constexpr size_t DIAG_WANT = staged_solve_doubles(O::N + O::M, THREADS / 32) * sizeof(double) + 16;
+    static constexpr size_t DIAG_BYTES = (!IN_SMEM && !FAST && Cta::SCRATCH_DOUBLES * sizeof(double) + SCRATCH_BYTES + qp_vec_bytes(O::N, O::M) +
+                                          DIAG_WANT <= 227 * 1024) ? DIAG_WANT : 0;
+    /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors                    (factor in shared memory)
+     *                 Cta scratch | SQP scratch | QP vectors | diagonal blocks of the factor (exact)    (factor in global scratch) */
     static size_t smem_bytes()
     {
         const size_t fac = FACTOR_DOUBLES * sizeof(double);
         const size_t first = IN_SMEM ? (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES) : SCRATCH_BYTES;
-        return Cta::SCRATCH_DOUBLES * sizeof(double) + first + qp_vec_bytes(O::N, O::M);
+        return Cta::SCRATCH_DOUBLES * sizeof(double) + first + qp_vec_bytes(O::N, O::M) + DIAG_BYTES;
     }
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st, pmb_qp_settings_t qst,
                             FactorStore fs, int batch, int* queue)
@@ -340,12 +345,13 @@ struct SqpSolveBody {
             const size_t fac = FACTOR_DOUBLES * sizeof(double);
             vec = base + (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES);
         }
+        double* Ld = DIAG_BYTES ? reinterpret_cast<double*>(vec + ((qp_vec_bytes(O::N, O::M) + 15) & ~(size_t)15)) : nullptr;
         for (;;) {
             const int ticket = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (ticket >= batch) break;
             const int b = ws.order ? ws.order[ticket] : ticket;
             const SqpInst<O> s{ws, b};
-            SqpDev<O>::template solve<R, THREADS / 32, FAST>(c, o, s, st, qst, Lp, vec, scratch);
+            SqpDev<O>::template solve<R, THREADS / 32, FAST, !IN_SMEM>(c, o, s, st, qst, Lp, vec, scratch, Ld);
         }
     }
 };

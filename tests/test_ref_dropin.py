@@ -95,8 +95,8 @@ def test_reference_valet_parking_test_passes_on_the_gpu(pmb):
     _check_valet_parking(*_run(_binary("valet_parking_mpc_test", "all")))
 
 
-def test_reference_minimal_time_test_passes_on_the_emulator(emu):
-    _check_minimal_time(*_run(_binary("emu_minimal_time_test", "emu")))
+# (minimal_time_test and cstr_control_test need 47 s and 103 s on the warp emulator: they are built for it — `make emu` — but run
+# in the GPU suite only; mpc_wrapper_test and valet_parking_mpc_test run on both)
 
 
 @pytest.mark.gpu
@@ -112,10 +112,6 @@ def test_unsupported_hook_overrides_are_refused(emu):
     rc, out = _run(_binary("emu_hook_refusal_test", "emu_hooks", needs_reference=False), "with_engine")
     assert rc == 0 and "0 failures" in out, out
     assert out.count("SQPBase::solve() REFUSED") == 6, out
-
-
-def test_reference_cstr_control_test_on_the_emulator(emu):
-    _check_cstr(*_run(_binary("emu_cstr_control_test", "emu")))
 
 
 @pytest.mark.gpu

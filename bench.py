@@ -602,7 +602,7 @@ def main():
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
     if args.cpu_sample is None:
-        args.cpu_sample = {"mobile_robot": 2048, "cstr": 1024, "kite": 64}[args.workload]
+        args.cpu_sample = {"mobile_robot": 8192, "cstr": 4096, "kite": 64}[args.workload]    # the parity object covers the whole default batch
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

@@ -20,6 +20,10 @@ if max_iter != 100:
 s.set_arithmetic(int(_os.environ.get("PMB_ARITH", "0")))          # 0 exact, 1 fast
 if int(_os.environ.get("PMB_BLOCK_BFGS", "0")):
     s.set_hessian_update(1)
+if int(_os.environ.get("PMB_PRECOND", "0")):
+    s.set_preconditioner(int(_os.environ["PMB_PRECOND"]))        # 1 Ruiz dense, 2 Ruiz sparse
+if int(_os.environ.get("PMB_FILTER_LS", "0")):
+    s.set_line_search(1, 0.1, 4)
 s.set_profiling(bool(int(_os.environ.get("PMB_PROFILE", "1"))))
 for _ in range(solves):
     s.reset_guess()

@@ -147,6 +147,18 @@ int pmb_qp_solve(int N, int M, int batch,
                  const pmb_qp_settings_t* settings,
                  double* x, double* y, pmb_qp_info_t* info,
                  double* z, double* q, int* perm, int* ctype, int* n_factor);
+/* ---- QPBase<ADMM<N,M,double,DENSE,LDLT,Lower>>::solve (qp_base.hpp:161-175, admm.hpp:112-213) ----------------------- */
+/* The OSQP-style splitting: the box constraints are appended to A as identity rows (Ae = [A; I]), one auxiliary / multiplier
+ * vector of size M + N, KKT system of size 2N + M.  Same inputs and settings as pmb_qp_solve.  Outputs: x[batch*N],
+ * y[batch*(M+N)] = [y_A ; y_box]; optional (may be NULL): z[batch*(M+N)] = m_z (the active set is {i: z_i == bound_i}),
+ * perm[batch*(2N+M)], ctype[batch*(M+N)], n_factor[batch].  Exact arithmetic only (bit-identical to the CPU oracle).
+ * Stand-alone operator: inside SQPBase the engine's QP solver is boxADMM (what the reference instantiates by default). */
+int pmb_qp_solve_admm(int N, int M, int batch,
+                      const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
+                      const double* xlb, const double* xub, const double* x_guess, const double* y_guess,
+                      const pmb_qp_settings_t* settings,
+                      double* x, double* y, pmb_qp_info_t* info,
+                      double* z, int* perm, int* ctype, int* n_factor);
 
 /* a17: boxADMM::construct_kkt_matrix, dense (box_admm.hpp:207-223).  K[batch*(N+M)^2] column-major; like the reference
  * only the lower triangle and the diagonal blocks are written (upper-right block is zero). */

@@ -278,10 +278,11 @@ typedef enum { SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, UNINITIALIZED, INFEASIBLE, I
 template <typename Scalar>
 struct qp_solver_info_t { status_t status = UNINITIALIZED; int iter = 0; int rho_updates = 0; Scalar rho_estimate = 0, res_prim = 1, res_dual = 1; };
 
-template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
-          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
-struct boxADMM {
-    static constexpr bool pmb_engine_inner_solver = true;   // SQPBase::solve() refuses QP solver types without this tag
+namespace pmb { namespace compat {
+/** the QPBase object concept (qp_base.hpp:148-175) shared by boxADMM<> and ADMM<>: one instance through pmb_qp_solve /
+ *  pmb_qp_solve_admm on the device */
+template <int N, int M, typename Scalar, bool OSQP_SPLITTING>
+struct QpObject {
     using scalar_t = Scalar;
     using settings_t = qp_solver_settings_t<Scalar>;
     using info_t = qp_solver_info_t<Scalar>;
@@ -295,7 +296,7 @@ struct boxADMM {
     qp_var_t m_x;
     qp_dual_t m_y;
     int iter{0};                                  // box_admm.hpp:44 (public in the reference, read by its tests)
-    boxADMM() { m_x.setZero(); m_y.setZero(); }
+    QpObject() { m_x.setZero(); m_y.setZero(); }
     settings_t& settings() noexcept { return m_settings; }
     const settings_t& settings() const noexcept { return m_settings; }
     const info_t& info() const noexcept { return m_info; }
@@ -326,8 +327,10 @@ private:
         q.adaptive_rho_tolerance = s.adaptive_rho_tolerance; q.adaptive_rho_interval = s.adaptive_rho_interval;
         q.reuse_pattern = s.reuse_pattern; q.verbose = s.verbose;
         pmb_qp_info_t inf;
-        const int rc = pmb_qp_solve(N, M, 1, H, h, A, Alb, Aub, xlb, xub, xg, yg, &q, m_x.data(), m_y.data(), &inf, nullptr, nullptr, nullptr, nullptr, nullptr);
-        if (rc != PMB_OK) throw std::runtime_error(std::string("boxADMM::solve failed (") + std::to_string(rc) + "): " + pmb_last_error());
+        const int rc = OSQP_SPLITTING
+            ? pmb_qp_solve_admm(N, M, 1, H, h, A, Alb, Aub, xlb, xub, xg, yg, &q, m_x.data(), m_y.data(), &inf, nullptr, nullptr, nullptr, nullptr)
+            : pmb_qp_solve(N, M, 1, H, h, A, Alb, Aub, xlb, xub, xg, yg, &q, m_x.data(), m_y.data(), &inf, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc != PMB_OK) throw std::runtime_error(std::string(OSQP_SPLITTING ? "ADMM::solve failed (" : "boxADMM::solve failed (") + std::to_string(rc) + "): " + pmb_last_error());
         const int prev_updates = m_info.rho_updates;           // accumulates across solves (box_admm.hpp:395)
         m_info.status = (status_t)inf.status; m_info.iter = inf.iter; m_info.rho_updates = prev_updates + inf.rho_updates;
         iter = inf.iter;
@@ -335,17 +338,19 @@ private:
         return m_info.status;
     }
 };
-/** the OSQP-style ADMM of src/solvers/admm.hpp (box constraints stacked under A, a (2N+M) KKT system) is NOT built: it is a
- *  distinct type without the engine tag, so SQPBase::solve() refuses it instead of running boxADMM in its place */
+} }
 template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
           template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
-struct ADMM {
+struct boxADMM : pmb::compat::QpObject<N, M, Scalar, false> {
+    static constexpr bool pmb_engine_inner_solver = true;   // SQPBase::solve() refuses QP solver types without this tag
+};
+/** the OSQP-style ADMM of src/solvers/admm.hpp (box constraints stacked under A, a (2N + M)-dimensional KKT system): built as a
+ *  stand-alone QPBase object (pmb_qp_solve_admm).  It carries no engine tag: the fused SQP loop runs boxADMM only, so
+ *  SQPBase::solve() refuses a solver that asks for ADMM<> instead of running boxADMM in its place. */
+template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
+          template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
+struct ADMM : pmb::compat::QpObject<N, M, Scalar, true> {
     static constexpr bool pmb_engine_inner_solver = false;
-    using scalar_t = Scalar;
-    using settings_t = qp_solver_settings_t<Scalar>;
-    settings_t m_settings;
-    settings_t& settings() noexcept { return m_settings; }
-    const settings_t& settings() const noexcept { return m_settings; }
 };
 
 // ---- device side: adapter from the Eigen-style functors to the engine's functor concept ---------------------------------
@@ -777,7 +782,7 @@ private:
         if (overrides_linearisation_dense_impl<Derived>::value || overrides_linearisation_sparse_impl<Derived>::value)
             refuse("Derived::linearisation_*_impl is overridden (only the exact AD linearisation exists on the device)");
         eo.preconditioner = Preconditioner::pmb_engine_preconditioner;     // IdentityPreconditioner or RuizEquilibration<DENSE | SPARSE>
-        if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is not boxADMM (the OSQP-style ADMM is not built)");
+        if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is not boxADMM (the OSQP-style ADMM exists as a stand-alone QP object only: the fused SQP loop runs boxADMM)");
         if (m_settings.iteration_callback != nullptr) refuse("settings().iteration_callback is set: a host callback cannot fire inside the fused device loop");
 
         // test data: a symmetric matrix whose Gershgorin discs partly reach into the negative half plane, so that a Gershgorin

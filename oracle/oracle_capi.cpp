@@ -6,6 +6,7 @@
 #include "orc_names.h"
 #include "../include/polympc_b200.h"
 #include "sqp.hpp"
+#include "admm_qp.hpp"
 
 #include <cmath>
 #include <cstring>
@@ -334,6 +335,34 @@ int pmb_qp_solve(int N, int M, int batch, const double* H, const double* h, cons
         if (ctype) {
             for (int i = 0; i < M; ++i) ctype[(size_t)b * (N + M) + i] = s.constr_type[i];
             for (int i = 0; i < N; ++i) ctype[(size_t)b * (N + M) + M + i] = s.box_constr_type[i];
+        }
+        if (n_factor) n_factor[b] = s.n_factor;
+    });
+    return PMB_OK;
+}
+
+int pmb_qp_solve_admm(int N, int M, int batch, const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
+                      const double* xlb, const double* xub, const double* x_guess, const double* y_guess, const pmb_qp_settings_t* st,
+                      double* x, double* y, pmb_qp_info_t* info, double* z, int* perm, int* ctype, int* n_factor)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !h || (M > 0 && (!A || !Alb || !Aub)) || !xlb || !xub || !st || !x || !y || !info)
+        return PMB_ERR_BAD_ARGUMENT;
+    parallel_for(batch, [&](int b) {
+        OsqpAdmm s(N, M);
+        to_qp(*st, s.settings);
+        s.solve(H + (size_t)b * N * N, h + (size_t)b * N, A + (size_t)b * M * N, Alb + (size_t)b * M, Aub + (size_t)b * M,
+                xlb + (size_t)b * N, xub + (size_t)b * N, x_guess ? x_guess + (size_t)b * N : nullptr,
+                y_guess ? y_guess + (size_t)b * (N + M) : nullptr);
+        const size_t Me = (size_t)N + M, Kd = 2 * (size_t)N + M;
+        for (int i = 0; i < N; ++i) x[(size_t)b * N + i] = s.x[i];
+        for (size_t i = 0; i < Me; ++i) y[b * Me + i] = s.y[i];
+        info[b].status = s.info.status; info[b].iter = s.info.iter; info[b].rho_updates = s.info.rho_updates; info[b]._pad = 0;
+        info[b].rho_estimate = s.info.rho_estimate; info[b].res_prim = s.info.res_prim; info[b].res_dual = s.info.res_dual;
+        if (z) for (size_t i = 0; i < Me; ++i) z[b * Me + i] = s.z[i];
+        if (perm) for (size_t i = 0; i < Kd; ++i) perm[b * Kd + i] = s.first_perm[i];
+        if (ctype) {
+            for (int i = 0; i < M; ++i) ctype[b * Me + i] = s.constr_type[i];
+            for (int i = 0; i < N; ++i) ctype[b * Me + M + i] = s.box_constr_type[i];
         }
         if (n_factor) n_factor[b] = s.n_factor;
     });

@@ -56,7 +56,7 @@ ABI_FUNCTIONS = [
     "ocp_create", "ocp_destroy", "ocp_dims", "ocp_set_params", "ocp_get_params", "ocp_set_time_limits", "ocp_time_nodes",
     "ocp_cost", "ocp_equalities", "ocp_inequalities", "ocp_equalities_linearised", "ocp_cost_gradient",
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
-    "qp_solve", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
+    "qp_solve", "qp_solve_admm", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
     "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_preconditioner", "sqp_set_line_search", "sqp_set_filter", "sqp_get_filter", "ruiz_equilibrate", "ruiz_unscale", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
@@ -120,6 +120,8 @@ class CApi:
         g("dm_eval").argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
         g("qp_solve").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 9 + [C.POINTER(QpSettings)] + \
             [c_double_p, c_double_p, C.c_void_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p]
+        g("qp_solve_admm").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 9 + [C.POINTER(QpSettings)] + \
+            [c_double_p, c_double_p, C.c_void_p, c_double_p, c_int_p, c_int_p, c_int_p]
         g("kkt_assemble").argtypes = [C.c_int, C.c_int, C.c_int] + [c_double_p] * 4 + [C.c_double, c_double_p]
         g("bfgs_update").argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]
         g("ocp_block_bfgs_update").argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]
@@ -271,6 +273,28 @@ class CApi:
                                   _pi(ctype), _pi(nf))
         self._chk(rc, "qp_solve")
         return dict(x=x, y=y, info=info, z=z, q=q, perm=perm, ctype=ctype, n_factor=nf)
+
+    def qp_solve_admm(self, H, h, A, Alb, Aub, xlb, xub, settings: QpSettings, x_guess=None, y_guess=None, extras=True):
+        """the OSQP-style ADMM<> of the reference (box rows appended to A); same conventions as qp_solve"""
+        H = np.asarray(H, dtype=np.float64)
+        B, N = H.shape[0], H.shape[1]
+        A = np.asarray(A, dtype=np.float64)
+        M = A.shape[1] if A.ndim == 3 else (A.size // max(1, B * N))
+        A = A.reshape(B, M, N)
+        Hc = np.ascontiguousarray(np.transpose(H, (0, 2, 1)))
+        Ac = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+        h = _f64(h, (B, N)); Alb = _f64(Alb, (B, M)); Aub = _f64(Aub, (B, M)); xlb = _f64(xlb, (B, N)); xub = _f64(xub, (B, N))
+        xg = None if x_guess is None else _f64(x_guess, (B, N))
+        yg = None if y_guess is None else _f64(y_guess, (B, N + M))
+        x = np.zeros((B, N)); y = np.zeros((B, N + M)); info = np.zeros(B, dtype=QP_INFO_DTYPE)
+        z = np.zeros((B, M + N)) if extras else None
+        perm = np.zeros((B, 2 * N + M), dtype=np.int32) if extras else None
+        ctype = np.zeros((B, N + M), dtype=np.int32) if extras else None
+        nf = np.zeros(B, dtype=np.int32) if extras else None
+        rc = self._fn("qp_solve_admm")(N, M, B, _p(Hc), _p(h), _p(Ac), _p(Alb), _p(Aub), _p(xlb), _p(xub), _p(xg), _p(yg),
+                                       C.byref(settings), _p(x), _p(y), info.ctypes.data_as(C.c_void_p), _p(z), _pi(perm), _pi(ctype), _pi(nf))
+        self._chk(rc, "qp_solve_admm")
+        return dict(x=x, y=y, info=info, z=z, perm=perm, ctype=ctype, n_factor=nf)
 
     def kkt_assemble(self, H, A, rho_box, rho_inv, sigma):
         H = np.asarray(H, dtype=np.float64)

@@ -155,6 +155,39 @@ bool launch_qp(stream_t s, const pmb_qp_settings_t& st, const QpBatch& qb, int b
     return false;
 }
 
+template <int R, bool IN_SMEM> bool launch_admm_r(size_t fac_doubles, size_t vec_bytes, stream_t s, const pmb_qp_settings_t& st, const AdmmBatch& qb,
+                                                  int batch, int* queue, DevBuf<double>& scratch)
+{
+    using Body = QpAdmmBody<R, IN_SMEM>;
+    const size_t base = Cta::SCRATCH_DOUBLES * sizeof(double) + vec_bytes;
+    const size_t smem = IN_SMEM ? base + fac_doubles * sizeof(double) : base;
+    int grid = resident_ctas<Body, pmb_qp_settings_t, AdmmBatch, FactorStore, int, int*>(smem, st, qb, FactorStore{}, 0, (int*)nullptr);
+    if (grid <= 0) { last_error_string() = "qp_solve_admm: kernel does not fit on the device"; return false; }
+    if (!IN_SMEM) grid = grid > 2 * 148 ? 2 * 148 : grid;
+    if (grid > batch) grid = batch;
+    FactorStore fs{nullptr, fac_doubles, rt_sm_count()};
+    if (!IN_SMEM) { if (!scratch.resize((size_t)grid * fac_doubles)) return false; fs.global = scratch.p; }
+    return rt_launch<Body>(grid, smem, s, st, qb, fs, batch, queue);
+}
+
+bool launch_admm(stream_t s, const pmb_qp_settings_t& st, const AdmmBatch& qb, int batch, int* queue, DevBuf<double>& scratch)
+{
+    const int n = 2 * qb.N + qb.M;
+    const int R = (n + 31) / 32;
+    const size_t fd = (size_t)n * (n + 1) / 2, vb = admm_vec_bytes(qb.N, qb.M);
+    const bool in_smem = Cta::SCRATCH_DOUBLES * sizeof(double) + vb + fd * sizeof(double) <= SMEM_CTA_MAX;
+    switch (R) {
+#define PMB_ADMM_SMEM(r) case r: return launch_admm_r<r, true>(fd, vb, s, st, qb, batch, queue, scratch);
+    PMB_ADMM_SMEM(1) PMB_ADMM_SMEM(2) PMB_ADMM_SMEM(3) PMB_ADMM_SMEM(4) PMB_ADMM_SMEM(5) PMB_ADMM_SMEM(6)
+    case 7: return in_smem ? launch_admm_r<7, true>(fd, vb, s, st, qb, batch, queue, scratch) : launch_admm_r<7, false>(fd, vb, s, st, qb, batch, queue, scratch);
+    case 8: return launch_admm_r<8, false>(fd, vb, s, st, qb, batch, queue, scratch);
+#undef PMB_ADMM_SMEM
+    default: break;
+    }
+    last_error_string() = "qp_solve_admm: KKT dimension 2N + M > 256 is not instantiated";
+    return false;
+}
+
 void sqp_defaults(pmb_sqp_settings_t* s)
 { s->tau = 0.5; s->eta = 0.25; s->rho = 0.5; s->eps_prim = 1e-3; s->eps_dual = 1e-3; s->max_iter = 100; s->line_search_max_iter = 100; }
 void qp_defaults(pmb_qp_settings_t* s)
@@ -406,6 +439,41 @@ int pmb_qp_solve(int N, int M, int batch, const double* H, const double* h, cons
     if (!launch_qp(st.s, *settings, qb, batch, queue.p, scratch)) return PMB_ERR_CUDA;
     st.back(x, qb.x, B * N); st.back(y, qb.y, B * n); st.back(info, qb.info, B); st.back(z, qb.z, B * M); st.back(q, qb.q, B * N);
     st.back(perm, qb.perm, B * n); st.back(ctype, qb.ctype, B * n); st.back(n_factor, qb.nfac, B);
+    if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
+    return PMB_OK;
+}
+
+int pmb_qp_solve_admm(int N, int M, int batch, const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
+                      const double* xlb, const double* xub, const double* x_guess, const double* y_guess, const pmb_qp_settings_t* settings,
+                      double* x, double* y, pmb_qp_info_t* info, double* z, int* perm, int* ctype, int* n_factor)
+{
+    if (N <= 0 || M < 0 || batch < 0 || !H || !h || (M > 0 && (!A || !Alb || !Aub)) || !xlb || !xub || !settings || !x || !y || !info)
+        PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "qp_solve_admm: bad argument");
+    if (!have_device()) PMB_FAIL(PMB_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (batch == 0) return PMB_OK;
+    const size_t B = batch, Me = (size_t)N + M, n = (size_t)N + Me;
+    // construct_A (admm.hpp:215-222): Ae = [A; I], column-major (M + N) x N per instance
+    std::vector<double> Ae(B * Me * N, 0.0);
+    for (size_t b = 0; b < B; ++b)
+        for (size_t j = 0; j < (size_t)N; ++j) {
+            double* col = Ae.data() + (b * N + j) * Me;
+            for (size_t i = 0; i < (size_t)M; ++i) col[i] = A[(b * N + j) * M + i];
+            col[M + j] = 1.0;
+        }
+    Staging st;
+    AdmmBatch qb{};
+    qb.N = N; qb.M = M;
+    qb.H = st.in(H, B * N * N); qb.h = st.in(h, B * N); qb.Ae = st.in((const double*)Ae.data(), B * Me * N);
+    qb.Alb = M ? st.in(Alb, B * M) : nullptr; qb.Aub = M ? st.in(Aub, B * M) : nullptr;
+    qb.xlb = st.in(xlb, B * N); qb.xub = st.in(xub, B * N); qb.xg = st.in(x_guess, B * N); qb.yg = st.in(y_guess, B * Me);
+    qb.x = st.out(x, B * N); qb.y = st.out(y, B * Me); qb.info = st.out(info, B); qb.z = st.out(z, B * Me);
+    qb.perm = st.out(perm, B * n); qb.ctype = st.out(ctype, B * Me); qb.nfac = st.out(n_factor, B);
+    DevBuf<int> queue;
+    DevBuf<double> scratch;
+    if (!st.ok || !queue.resize(1) || !rt_memset(queue.p, 0, sizeof(int), st.s)) return PMB_ERR_CUDA;
+    if (!launch_admm(st.s, *settings, qb, batch, queue.p, scratch)) return PMB_ERR_CUDA;
+    st.back(x, qb.x, B * N); st.back(y, qb.y, B * Me); st.back(info, qb.info, B); st.back(z, qb.z, B * Me);
+    st.back(perm, qb.perm, B * n); st.back(ctype, qb.ctype, B * Me); st.back(n_factor, qb.nfac, B);
     if (!st.ok || !rt_sync(st.s)) return PMB_ERR_CUDA;
     return PMB_OK;
 }

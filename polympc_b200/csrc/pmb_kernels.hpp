@@ -4,6 +4,7 @@
 #include "pmb_ocp.hpp"
 #include "pmb_qp.hpp"
 #include "pmb_sqp.hpp"
+#include "pmb_qp_admm.hpp"
 
 namespace pmb {
 
@@ -100,6 +101,44 @@ struct QpBody {
             if (b >= batch) break;
             const QpArgs a = qp_instance(qb, b);
             qp_solve_cta<R, 0, 0, 4, FAST>(c, st, a, Lp, vec);
+        }
+    }
+};
+
+// ---- the reference's OSQP-style ADMM<> as a stand-alone batched operator (C ABI pmb_qp_solve_admm) ----------------------------
+struct AdmmBatch {
+    int N, M;
+    const double *H, *h, *Ae, *Alb, *Aub, *xlb, *xub, *xg, *yg;
+    double *x, *y;
+    pmb_qp_info_t* info;
+    double* z;
+    int *perm, *ctype, *nfac;
+};
+template <int R, bool IN_SMEM>
+struct QpAdmmBody {
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = R <= 4 ? 4 : (R <= 6 ? 2 : 1);
+    static constexpr const char* NAME = "qp_osqp_admm";
+    static constexpr size_t EMU_STACK_BYTES = 1u << 20;
+    PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, pmb_qp_settings_t st, AdmmBatch qb, FactorStore fs, int batch, int* queue)
+    {
+        Cta c(w, reinterpret_cast<double*>(smem), fs.sm_count > 0 ? blk + blk / fs.sm_count : 0);
+        unsigned char* ws = smem + Cta::SCRATCH_DOUBLES * sizeof(double);
+        double* Lp = IN_SMEM ? reinterpret_cast<double*>(ws) : fs.global + (size_t)blk * fs.doubles;
+        unsigned char* vec = IN_SMEM ? ws + fs.doubles * sizeof(double) : ws;
+        for (;;) {
+            const int b = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
+            if (b >= batch) break;
+            const size_t N = qb.N, M = qb.M, Me = N + M, n = N + Me, sb = b;
+            AdmmArgs a;
+            a.N = qb.N; a.M = qb.M;
+            a.H = qb.H + sb * N * N; a.h = qb.h + sb * N; a.Ae = qb.Ae + sb * Me * N; a.Alb = qb.Alb + sb * M; a.Aub = qb.Aub + sb * M;
+            a.xlb = qb.xlb + sb * N; a.xub = qb.xub + sb * N;
+            a.xg = qb.xg ? qb.xg + sb * N : nullptr; a.yg = qb.yg ? qb.yg + sb * Me : nullptr;
+            a.x = qb.x + sb * N; a.y = qb.y + sb * Me; a.info = qb.info ? qb.info + sb : nullptr;
+            a.z = qb.z ? qb.z + sb * Me : nullptr; a.perm = qb.perm ? qb.perm + sb * n : nullptr;
+            a.ctype = qb.ctype ? qb.ctype + sb * Me : nullptr; a.nfac = qb.nfac ? qb.nfac + sb : nullptr;
+            admm_solve_cta<R, 4>(c, st, a, Lp, vec);
         }
     }
 };

@@ -92,6 +92,21 @@ template <typename Problem, typename QPSolver = OsqpAdmm> class WithAdmm : publi
 
 static void on_iteration(void*) {}
 
+/** the QPBase object concept stand-alone: the reference's tests/solvers/qp/admm_solver_test.cpp:16-45 (admmSimpleQP) and
+ *  box_admm_test.cpp:15-45 through ADMM<2, 1> and boxADMM<2, 1> */
+template <class QP> static void simple_qp(const char* what)
+{
+    Eigen::Matrix<double, 2, 2> H; Eigen::Matrix<double, 2, 1> h, xl, xu, solution; Eigen::Matrix<double, 1, 2> A; Eigen::Matrix<double, 1, 1> al, au;
+    H << 4, 1, 1, 2; h << 1, 1; A << 1, 1; al << 1; au << 1; xl << 0, 0; xu << 0.7, 0.7; solution << 0.3, 0.7;
+    QP prob;
+    prob.settings().max_iter = 1000;
+    prob.solve(H, h, A, al, au, xl, xu);
+    std::printf("%-28s x = (%.6f, %.6f) status=%d iter=%d\n", what, prob.primal_solution()(0), prob.primal_solution()(1), (int)prob.info().status, prob.iter);
+    EXPECT(prob.primal_solution().isApprox(solution, 1e-2));
+    EXPECT(prob.iter < prob.settings().max_iter);
+    EXPECT(prob.info().status == SOLVED);
+}
+
 template <class S> static int run(S& s, const char* what)
 {
     s.settings().max_iter = 3; s.settings().line_search_max_iter = 3;
@@ -117,6 +132,8 @@ int main(int argc, char** argv)
     { ShiftAll<OCP> s; EXPECT(run(s, "custom regulariser") == sqp_status_t::INVALID_SETTINGS); }
     { FilterSearch<OCP, true> s; EXPECT(run(s, "filter search + extra test") == sqp_status_t::INVALID_SETTINGS); }
     if (have_engine) {
+        simple_qp<ADMM<2, 1, double>>("ADMM<2,1> stand-alone");
+        simple_qp<boxADMM<2, 1, double>>("boxADMM<2,1> stand-alone");
         WithRuiz<OCP> r; EXPECT(run(r, "RuizEquilibration") != sqp_status_t::INVALID_SETTINGS); EXPECT(r.engine_options().preconditioner == 1);
         FilterSearch<OCP, false> f; f.filter.beta = 0.1; f.filter.add(1e9, 1e9);
         EXPECT(run(f, "filter line search") != sqp_status_t::INVALID_SETTINGS); EXPECT(f.engine_options().filter_line_search);

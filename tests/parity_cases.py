@@ -126,6 +126,27 @@ def qp_case(api, orc, N, M, B=3, seed=0, settings=None, warm=False, **kw):
     return rb
 
 
+def admm_case(api, orc, N, M, B=3, seed=0, settings=None, warm=False, **kw):
+    """the reference's OSQP-style ADMM<> (admm.hpp:112-213) as a batched operator: iterates, multipliers, the auxiliary vector z
+    of size M + N and its active set, classification, pivot order of the (2N + M)-dimensional KKT system, trip counts"""
+    rng = np.random.default_rng(seed)
+    H, h, A, Alb, Aub, xlb, xub = random_qp(rng, B, N, M, **kw)
+    st = settings if settings is not None else orc.sqp_default_qp_settings()
+    xg = rng.uniform(-0.1, 0.1, (B, N)) if warm else None
+    yg = rng.uniform(-0.1, 0.1, (B, N + M)) if warm else None
+    ra = api.qp_solve_admm(H, h, A, Alb, Aub, xlb, xub, st, x_guess=xg, y_guess=yg)
+    rb = orc.qp_solve_admm(H, h, A, Alb, Aub, xlb, xub, st, x_guess=xg, y_guess=yg)
+    for k in ("perm", "ctype", "n_factor"):
+        assert_same(ra[k], rb[k], "admm." + k)
+    for f in ("status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual"):
+        assert_same(ra["info"][f], rb["info"][f], "admm.info." + f)
+    for k in ("x", "y", "z"):
+        assert_same(ra[k], rb[k], "admm." + k)
+    lo, hi = np.concatenate([Alb, xlb], axis=1), np.concatenate([Aub, xub], axis=1)
+    assert np.array_equal((ra["z"] == lo) | (ra["z"] == hi), (rb["z"] == lo) | (rb["z"] == hi))
+    return rb
+
+
 def bfgs_case(api, orc, N, B=4, seed=0):
     rng = np.random.default_rng(seed)
     G = rng.standard_normal((B, N, N))

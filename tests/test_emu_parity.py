@@ -266,3 +266,15 @@ def test_sqp_factor_in_a_global_slot(emu, orc):
     the last block is partial).  One SQP iteration = one QP with ~100 solves, bit for bit."""
     w = W.kite(1, grid="4x2", sqp_max_iter=1, ls_max_iter=4)
     pc.sqp_case(emu, orc, w)
+
+
+@pytest.mark.parametrize("N,M", [(1, 0), (2, 1), (5, 5), (12, 7), (20, 13)])
+def test_osqp_style_admm(emu, orc, N, M):
+    """ADMM<N, M> of the reference (admm.hpp:112-213; KKT system of size 2N + M) as a batched operator, bit for bit"""
+    pc.admm_case(emu, orc, N, M, B=3, seed=N)
+
+
+def test_osqp_style_admm_adaptive_rho_relaxation_warm_start(emu, orc):
+    st = orc.sqp_default_qp_settings(); st.adaptive_rho = 1; st.adaptive_rho_interval = 10; st.max_iter = 60; st.alpha = 1.6
+    r = pc.admm_case(emu, orc, 9, 4, B=3, seed=5, settings=st, warm=True)
+    assert (r["n_factor"] >= 2).any()

@@ -372,3 +372,23 @@ def test_sqp_full_batch_bit_exact_vs_oracle(pmb, orc, kind, batch):
     ra, rb = pc.sqp_case(pmb, orc, w)
     assert ra["x"].shape[0] == batch
     assert (rb["info"]["status"] == 0).mean() > 0.95
+
+
+@pytest.mark.parametrize("N,M", [(1, 0), (2, 1), (5, 5), (12, 7), (33, 20), (65, 39), (80, 48), (100, 56)])
+def test_osqp_style_admm(pmb, orc, N, M):
+    """ADMM<N, M> of the reference (admm.hpp:112-213) as a batched operator: KKT systems of size 2N + M up to 256 (factor in shared
+    memory up to 192, in a global slot beyond), bit for bit — incl. the robot's (65, 39) and the 5 x 3 grid's (80, 48)"""
+    pc.admm_case(pmb, orc, N, M, B=24, seed=N + 1)
+
+
+def test_osqp_style_admm_adaptive_rho_relaxation_warm_start(pmb, orc):
+    st = orc.sqp_default_qp_settings(); st.adaptive_rho = 1; st.adaptive_rho_interval = 10; st.max_iter = 200; st.alpha = 1.6
+    r = pc.admm_case(pmb, orc, 20, 9, B=64, seed=5, settings=st, warm=True)
+    assert (r["n_factor"] >= 2).any() and (r["info"]["status"] == 0).any()
+
+
+def test_osqp_style_admm_reference_known_answer(pmb):
+    """admm_solver_test.cpp:16-45 (admmSimpleQP) on the GPU: (0.3, 0.7) to 1e-2, SOLVED, iter < 1000"""
+    st = pmb.qp_default_settings(); st.max_iter = 1000
+    r = pmb.qp_solve_admm(np.array([[[4.0, 1.0], [1.0, 2.0]]]), [[1.0, 1.0]], np.array([[[1.0, 1.0]]]), [[1.0]], [[1.0]], [[0.0, 0.0]], [[0.7, 0.7]], st)
+    assert np.allclose(r["x"][0], [0.3, 0.7], rtol=1e-2) and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 1000

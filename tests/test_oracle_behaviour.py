@@ -92,3 +92,36 @@ def test_ruiz_equilibration_properties(orc):
         assert r["D"][1, 10] == 1.0                           # the empty column keeps scale 1 (the zero guard)
         coln = np.maximum(np.abs(r["H"][0]).max(axis=0) / r["c"][0], np.abs(r["A"][0]).max(axis=0))
         assert coln.max() / coln.min() < 30.0
+
+
+def test_osqp_style_admm_known_answers(orc):
+    """tests/solvers/qp/admm_solver_test.cpp: admmSimpleQP (:16-45), admmConstraintViolation (:114-151), admmSimpleLP (:303-334),
+    admmNonConvex (:336-371), admmAdaptiveRho-style settings — the reference's own known answers for ADMM<>"""
+    st = lambda **kw: _qp_settings(orc, **kw)
+    H = np.array([[[4.0, 1.0], [1.0, 2.0]]]); h = np.array([[1.0, 1.0]]); A = np.array([[[1.0, 1.0]]])
+    r = orc.qp_solve_admm(H, h, A, [[1.0]], [[1.0]], [[0.0, 0.0]], [[0.7, 0.7]], st(max_iter=1000))
+    assert np.allclose(r["x"][0], [0.3, 0.7], rtol=1e-2) and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 1000
+    r = orc.qp_solve_admm(H, h, A, [[1.0]], [[1.0]], [[0.0, 0.0]], [[0.7, 0.7]], st(eps_rel=1e-4, eps_abs=1e-4))
+    x = r["x"][0]
+    assert min(x.sum() - 1.0, x.min()) >= -1e-3 and max(x.sum() - 1.0, (x - 0.7).max()) <= 1e-3
+    none = (np.zeros((1, 0, 1)), np.zeros((1, 0)), np.zeros((1, 0)))
+    r = orc.qp_solve_admm(np.array([[[0.0]]]), [[1.0]], none[0], none[1], none[2], [[-1e6]], [[1e6]],
+                          st(max_iter=200, alpha=1.0, adaptive_rho=1, check_termination=10))
+    assert abs(r["x"][0, 0] + 1e6) <= 1e-2 * 1e6 and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 200
+    r = orc.qp_solve_admm(np.array([[[-1.0]]]), [[0.0]], none[0], none[1], none[2], [[-1.0]], [[2.0]],
+                          st(max_iter=200, alpha=1.0, adaptive_rho=1, rho=2.0, check_termination=10), x_guess=[[0.1]], y_guess=[[0.1]])
+    assert abs(r["x"][0, 0] - 2.0) <= 2e-2 and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 200
+    # same optimum as boxADMM on a random strictly convex QP
+    import parity_cases as pc
+    rng = np.random.default_rng(3)
+    q = pc.random_qp(rng, 4, 8, 3)
+    s = st(max_iter=4000, eps_abs=1e-8, eps_rel=1e-8, check_termination=10)
+    a, b = orc.qp_solve_admm(*q, s), orc.qp_solve(*q, s)
+    assert (a["info"]["status"] == 0).all() and np.abs(a["x"] - b["x"]).max() < 1e-5
+
+
+def _qp_settings(orc, **kw):
+    s = orc.qp_default_settings()
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s

@@ -230,6 +230,13 @@ int pmb_ruiz_equilibrate(int N, int M, int batch, int variant, double* H, double
                          double* D, double* E, double* c);
 int pmb_ruiz_unscale(int N, int M, int batch, const double* D, const double* E, const double* c, double* H, double* h, double* A, double* Al,
                      double* Au, double* l, double* u, double* x, double* y);
+/* QPSolver template argument of SQPBase (sqp_base.hpp:64-70): the QP solver of the SQP loop.
+ *   PMB_QP_BOX_ADMM   boxADMM<> (src/solvers/box_admm.hpp) — the reference's default; both arithmetics;
+ *   PMB_QP_OSQP_ADMM  ADMM<> (src/solvers/admm.hpp:112-213), the OSQP-style splitting with the box rows appended to A (KKT
+ *                     systems of size 2N + M); exact arithmetic only, instantiated for 2N + M <= 256 (PMB_ERR_UNSUPPORTED
+ *                     beyond, and when the handle is in fast arithmetic at solve time). */
+typedef enum pmb_qp_solver { PMB_QP_BOX_ADMM = 0, PMB_QP_OSQP_ADMM = 1 } pmb_qp_solver_t;
+int pmb_sqp_set_qp_solver(pmb_sqp_t* s, int kind);
 /* Arithmetic of the KKT linear algebra inside boxADMM (csrc/pmb_qp.hpp vs csrc/pmb_qp_fast.hpp).  Both run the same
  * algorithm with the same pivot permutation (Eigen::LDLT's diagonal rule):
  *   PMB_ARITH_EXACT  every fp64 operation in the order of the CPU oracle: results are bit-identical to it (default);

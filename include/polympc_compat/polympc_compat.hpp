@@ -343,14 +343,16 @@ template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
           template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
 struct boxADMM : pmb::compat::QpObject<N, M, Scalar, false> {
     static constexpr bool pmb_engine_inner_solver = true;   // SQPBase::solve() refuses QP solver types without this tag
+    static constexpr int pmb_engine_qp_solver = 0;          // PMB_QP_BOX_ADMM
 };
-/** the OSQP-style ADMM of src/solvers/admm.hpp (box constraints stacked under A, a (2N + M)-dimensional KKT system): built as a
- *  stand-alone QPBase object (pmb_qp_solve_admm).  It carries no engine tag: the fused SQP loop runs boxADMM only, so
- *  SQPBase::solve() refuses a solver that asks for ADMM<> instead of running boxADMM in its place. */
+/** the OSQP-style ADMM of src/solvers/admm.hpp (box constraints stacked under A, a (2N + M)-dimensional KKT system): a QPBase
+ *  object stand-alone (pmb_qp_solve_admm) and a selectable QP solver of the fused SQP loop (pmb_sqp_set_qp_solver; exact
+ *  arithmetic, 2N + M <= 256) */
 template <int N, int M, typename Scalar = double, int MatrixType = DENSE,
           template <typename, int, typename...> class LinearSolver = linear_solver_traits<DENSE>::template default_solver, int LinearSolver_UpLo = 1>
 struct ADMM : pmb::compat::QpObject<N, M, Scalar, true> {
-    static constexpr bool pmb_engine_inner_solver = false;
+    static constexpr bool pmb_engine_inner_solver = true;
+    static constexpr int pmb_engine_qp_solver = 1;          // PMB_QP_OSQP_ADMM
 };
 
 // ---- device side: adapter from the Eigen-style functors to the engine's functor concept ---------------------------------
@@ -782,7 +784,7 @@ private:
         if (overrides_linearisation_dense_impl<Derived>::value || overrides_linearisation_sparse_impl<Derived>::value)
             refuse("Derived::linearisation_*_impl is overridden (only the exact AD linearisation exists on the device)");
         eo.preconditioner = Preconditioner::pmb_engine_preconditioner;     // IdentityPreconditioner or RuizEquilibration<DENSE | SPARSE>
-        if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is not boxADMM (the OSQP-style ADMM exists as a stand-alone QP object only: the fused SQP loop runs boxADMM)");
+        if (!QPSolver::pmb_engine_inner_solver) refuse("the QP solver type is neither boxADMM<> nor ADMM<> (no device twin)");
         if (m_settings.iteration_callback != nullptr) refuse("settings().iteration_callback is set: a host callback cannot fire inside the fused device loop");
 
         // test data: a symmetric matrix whose Gershgorin discs partly reach into the negative half plane, so that a Gershgorin
@@ -871,6 +873,7 @@ private:
         check(pmb_sqp_set_hessian_options(m_handle, m_engine_options.exact_hessian_every_iteration, m_engine_options.gershgorin_regularisation),
               "set_hessian_options");
         check(pmb_sqp_set_hessian_update(m_handle, m_engine_options.block_bfgs ? PMB_HESSIAN_BFGS_BLOCK : PMB_HESSIAN_BFGS_DENSE), "set_hessian_update");
+        check(pmb_sqp_set_qp_solver(m_handle, QPSolver::pmb_engine_qp_solver), "set_qp_solver");
         check(pmb_sqp_set_preconditioner(m_handle, m_engine_options.preconditioner), "set_preconditioner");
         LSFilter<scalar_t>* flt = m_engine_options.filter_line_search ? filter_of(derived(), 0) : nullptr;
         double fstate[PMB_FILTER_DOUBLES];
@@ -912,7 +915,7 @@ private:
                       << " finite=" << (finite ? 1 : 0) << " block_bfgs=" << (m_engine_options.block_bfgs ? 1 : 0)
                       << " exact_hessian=" << (m_engine_options.exact_hessian_every_iteration ? 1 : 0)
                       << " gershgorin=" << (m_engine_options.gershgorin_regularisation ? 1 : 0)
-                      << " preconditioner=" << m_engine_options.preconditioner << " filter_ls=" << (m_engine_options.filter_line_search ? 1 : 0) << "\n";
+                      << " qp_solver=" << (int)QPSolver::pmb_engine_qp_solver << " preconditioner=" << m_engine_options.preconditioner << " filter_ls=" << (m_engine_options.filter_line_search ? 1 : 0) << "\n";
         }
     }
 };

@@ -89,6 +89,7 @@ struct ISqpInst {
     virtual void hessian_options(int exact, int gershgorin) = 0;
     virtual void hessian_update(int block) = 0;
     virtual void preconditioner(int kind) = 0;
+    virtual void qp_solver(int kind) = 0;
     virtual void line_search(int kind, double beta, int depth) = 0;
     virtual LsFilter& filter() = 0;
     virtual SqpInfo& info() = 0;
@@ -113,6 +114,7 @@ struct SqpInst : ISqpInst {
     void hessian_options(int exact, int gershgorin) override { s.opt_exact_hessian = exact; s.opt_gershgorin = gershgorin; }
     void hessian_update(int block) override { s.opt_block_bfgs = block; }
     void preconditioner(int kind) override { s.opt_precond = kind; }
+    void qp_solver(int kind) override { s.opt_qp_solver = kind; }
     void line_search(int kind, double beta, int depth) override { s.opt_line_search = kind; s.filter.clear(); s.filter.beta = beta; s.filter.max_depth = depth; }
     LsFilter& filter() override { return s.filter; }
     SqpInfo& info() override { return s.info; }
@@ -453,6 +455,12 @@ int pmb_sqp_set_hessian_update(pmb_sqp_t* s, int mode)
 {
     if (!s || (mode != PMB_HESSIAN_BFGS_DENSE && mode != PMB_HESSIAN_BFGS_BLOCK)) return PMB_ERR_BAD_ARGUMENT;
     for (auto& i : s->inst) i->hessian_update(mode == PMB_HESSIAN_BFGS_BLOCK);
+    return PMB_OK;
+}
+int pmb_sqp_set_qp_solver(pmb_sqp_t* s, int kind)
+{
+    if (!s || (kind != PMB_QP_BOX_ADMM && kind != PMB_QP_OSQP_ADMM)) return PMB_ERR_BAD_ARGUMENT;
+    for (auto& i : s->inst) i->qp_solver(kind);
     return PMB_OK;
 }
 int pmb_sqp_set_preconditioner(pmb_sqp_t* s, int kind)

@@ -7,6 +7,7 @@
 #include "ocp.hpp"
 #include "qp.hpp"
 #include "precond.hpp"
+#include "admm_qp.hpp"
 #include <limits>
 
 namespace orc {
@@ -232,6 +233,8 @@ struct Sqp {
     int opt_exact_hessian = 0;   // update_linearisation_dense_impl := linearisation_dense_impl (exact Hessian at every iteration)
     int opt_gershgorin = 0;      // hessian_regularisation_dense_impl := Gershgorin shift of the diagonal
     int opt_block_bfgs = 0;      // hessian_update_impl := the OCP's block BFGS (ContinuousOCP<..., SPARSE>::hessian_update_impl)
+    int opt_qp_solver = 0;       // QPSolver template argument: 0 boxADMM<>, 1 ADMM<> (the OSQP-style splitting, admm.hpp)
+    OsqpAdmm qp_admm{N, M};
     int opt_precond = PRECOND_IDENTITY;   // Preconditioner template argument: RuizEquilibration<..., DENSE | SPARSE> (sqp_base.hpp:605-611, 662-667)
     int opt_line_search = 0;     // 0: l1 merit (default), 1: the filter line search of tests/control/valet_parking_mpc_test.cpp:110-155
     LsFilter filter;             // the solver member `filter` of that test: it lives as long as the solver object
@@ -265,14 +268,21 @@ struct Sqp {
             ruiz.variant = opt_precond;
             ruiz.compute(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data());
         }
-        qp.solve(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data(), nullptr, nullptr);
-        info.qp_solver_iter += qp.info.iter;
-        p = qp.x; p_lambda = qp.y;
+        int qp_iter, qp_nfac;
+        if (opt_qp_solver == 1) {
+            qp_admm.settings = qp.settings;
+            qp_admm.solve(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data(), nullptr, nullptr);
+            p = qp_admm.x; p_lambda = qp_admm.y; qp_iter = qp_admm.info.iter; qp_nfac = qp_admm.n_factor;
+        } else {
+            qp.solve(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data(), nullptr, nullptr);
+            p = qp.x; p_lambda = qp.y; qp_iter = qp.info.iter; qp_nfac = qp.n_factor;
+        }
+        info.qp_solver_iter += qp_iter;
         if (opt_precond != PRECOND_IDENTITY) {
             ruiz.unscale_solution(p.data(), p_lambda.data());
             ruiz.unscale_data(H.data(), h.data(), A.data(), al.data(), au.data(), lx.data(), ux.data());
         }
-        tr_qp_iter.push_back(qp.info.iter); tr_qp_factor.push_back(qp.n_factor);
+        tr_qp_iter.push_back(qp_iter); tr_qp_factor.push_back(qp_nfac);
         lam_k = p_lambda;
         for (int i = 0; i < DUAL; ++i) p_lambda[i] -= lam[i];
         int trials = 0;

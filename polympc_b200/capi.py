@@ -58,7 +58,7 @@ ABI_FUNCTIONS = [
     "ocp_cost_gradient_hessian", "ocp_lagrangian_gradient", "ocp_lagrangian_gradient_hessian", "ocp_block_bfgs_update",
     "qp_solve", "qp_solve_admm", "kkt_assemble", "kkt_assemble_dev", "bfgs_update",
     "sqp_create", "sqp_destroy", "sqp_problem", "sqp_batch", "sqp_set_settings", "sqp_get_settings",
-    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_preconditioner", "sqp_set_line_search", "sqp_set_filter", "sqp_get_filter", "ruiz_equilibrate", "ruiz_unscale", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
+    "sqp_set_qp_settings", "sqp_get_qp_settings", "sqp_set_hessian_options", "sqp_set_hessian_update", "sqp_set_qp_solver", "sqp_set_preconditioner", "sqp_set_line_search", "sqp_set_filter", "sqp_get_filter", "ruiz_equilibrate", "ruiz_unscale", "sqp_set_trace", "sqp_set_schedule", "set_default_arithmetic", "get_default_arithmetic", "sqp_set_arithmetic", "sqp_get_arithmetic", "sqp_set_bounds_x", "sqp_set_bounds_g", "sqp_set_parameters",
     "sqp_set_primal", "sqp_set_dual", "sqp_set_initial_conditions", "sqp_reset_guess", "sqp_solve", "sqp_solve_async", "sqp_wait", "sqp_get_primal", "sqp_get_dual",
     "sqp_get_info", "sqp_get_stats", "sqp_get_trace", "sqp_last_solve_ms", "sqp_last_kernel_ms", "sqp_last_solve_launches", "sqp_set_profiling",
     "sqp_get_kernel_times", "sqp_get_phase_cycles", "sqp_set_stream",
@@ -139,6 +139,7 @@ class CApi:
         g("sqp_set_hessian_options").argtypes = [C.c_void_p, C.c_int, C.c_int]
         g("sqp_set_hessian_update").argtypes = [C.c_void_p, C.c_int]
         g("sqp_set_preconditioner").argtypes = [C.c_void_p, C.c_int]
+        g("sqp_set_qp_solver").argtypes = [C.c_void_p, C.c_int]
         g("sqp_set_line_search").argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         g("sqp_set_filter").argtypes = [C.c_void_p, c_double_p, C.c_int]
         g("sqp_get_filter").argtypes = [C.c_void_p, c_double_p]
@@ -500,6 +501,10 @@ class Sqp:
         """the fixed menu of SQPBase CRTP overrides (reference tests/control/minimal_time_test.cpp:90-135)"""
         self.api._chk(self.api._fn("sqp_set_hessian_options")(self.h, int(exact_every_iteration), int(gershgorin_regularisation)),
                       "sqp_set_hessian_options")
+
+    def set_qp_solver(self, kind: int):
+        """0 boxADMM<> (default), 1 the OSQP-style ADMM<> (pmb_qp_solver_t)"""
+        self.api._chk(self.api._fn("sqp_set_qp_solver")(self.h, int(kind)), "sqp_set_qp_solver")
 
     def set_preconditioner(self, kind: int):
         """0 identity, 1 RuizEquilibration<DENSE>, 2 RuizEquilibration<SPARSE> (pmb_preconditioner_t)"""

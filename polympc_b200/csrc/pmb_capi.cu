@@ -214,6 +214,9 @@ struct pmb_sqp {
     int filter_depth = 10;
     double filter_beta = 1e-5;
     pmb::DevBuf<double> ruiz, filter;                // allocated when the option is switched on
+    int qp_solver = PMB_QP_BOX_ADMM;                 // pmb_sqp_set_qp_solver
+    int grid_admm = 0;
+    pmb::DevBuf<double> factor_scratch_admm, Ae;
     int arithmetic = PMB_ARITH_EXACT;                // pmb_sqp_set_arithmetic
     int schedule = PMB_SCHEDULE_LPT_HISTORY;         // pmb_sqp_set_schedule
     bool have_history = false;                       // info holds the iteration counts of a completed solve of this handle
@@ -752,6 +755,27 @@ int pmb_sqp_set_arithmetic(pmb_sqp_t* s, int mode)
     s->arithmetic = mode;
     return PMB_OK;
 }
+int pmb_sqp_set_qp_solver(pmb_sqp_t* s, int kind)
+{
+    if (!s || (kind != PMB_QP_BOX_ADMM && kind != PMB_QP_OSQP_ADMM)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_qp_solver: bad argument");
+    if (kind == PMB_QP_OSQP_ADMM) {
+        const IProblem& P = *s->ocp.impl;
+        if (!P.admm_supported()) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_qp_solver: the OSQP-style ADMM is instantiated for 2N + M <= 256");
+        if (P.admm_smem_bytes() > SMEM_CTA_MAX) PMB_FAIL(PMB_ERR_UNSUPPORTED, "set_qp_solver: problem too large for shared memory");
+        if (s->grid_admm == 0) {
+            if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+            int grid = P.admm_resident_ctas();
+            if (grid <= 0) PMB_FAIL(PMB_ERR_CUDA, "set_qp_solver: the sqp_solve_osqp_admm kernel does not fit on the device");
+            if (!P.admm_in_smem()) grid = grid > 2 * 148 ? 2 * 148 : grid;
+            grid = grid > s->batch ? s->batch : grid;
+            if (!P.admm_in_smem() && !s->factor_scratch_admm.resize((size_t)grid * P.admm_factor_doubles())) return PMB_ERR_CUDA;
+            if (!s->Ae.resize((size_t)s->batch * (P.dims.N + P.dims.M) * P.dims.N)) return PMB_ERR_CUDA;
+            s->grid_admm = grid;
+        }
+    }
+    s->qp_solver = kind;
+    return PMB_OK;
+}
 int pmb_sqp_set_schedule(pmb_sqp_t* s, int schedule)
 {
     if (!s || (schedule != PMB_SCHEDULE_FIFO && schedule != PMB_SCHEDULE_LPT_HISTORY)) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "set_schedule: bad argument");
@@ -857,6 +881,8 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
 {
     if (!s) PMB_FAIL(PMB_ERR_BAD_ARGUMENT, "null");
     if (!rt_set_device(s->device)) return PMB_ERR_CUDA;
+    if (s->qp_solver == PMB_QP_OSQP_ADMM && s->arithmetic == PMB_ARITH_FAST)
+        PMB_FAIL(PMB_ERR_UNSUPPORTED, "sqp_solve: the OSQP-style ADMM runs in exact arithmetic only (pmb_sqp_set_arithmetic)");
     const int B = s->batch;
     const int rows = !s->trace_on ? 0 : (s->settings.max_iter > 0 ? s->settings.max_iter : 1);
     if (rows != s->trace_rows) {
@@ -883,7 +909,7 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     ws.trace_rows = rows;
     ws.opt_exact_hessian = s->opt_exact_hessian; ws.opt_gershgorin = s->opt_gershgorin; ws.opt_block_bfgs = s->opt_block_bfgs;
     ws.opt_precond = s->opt_precond; ws.opt_line_search = s->opt_line_search; ws.filter_depth = s->filter_depth; ws.filter_beta = s->filter_beta;
-    ws.ruiz = s->ruiz.p; ws.filter = s->filter.p;
+    ws.ruiz = s->ruiz.p; ws.filter = s->filter.p; ws.Ae = s->Ae.p;
     ws.order = nullptr;
     if (s->schedule == PMB_SCHEDULE_LPT_HISTORY && s->have_history && B > s->grid) {
         // longest-processing-time-first from the previous solve's iteration counts (still in s->info at this point of the stream)
@@ -898,7 +924,8 @@ int pmb_sqp_solve_async(pmb_sqp_t* s)
     }
     // one persistent launch: CTAs draw instances from the queue and run their whole SQP loop on the device
     ok = ok && rt_event_record(s->kev0, st);
-    if (s->arithmetic == PMB_ARITH_FAST) ok = ok && s->ocp.impl->launch_solve_fast(s->grid_fast, ws, s->settings, s->qp_settings, s->factor_scratch_fast.p, B, s->queue.p, st);
+    if (s->qp_solver == PMB_QP_OSQP_ADMM) ok = ok && s->ocp.impl->launch_solve_admm(s->grid_admm, ws, s->settings, s->qp_settings, s->factor_scratch_admm.p, B, s->queue.p, st);
+    else if (s->arithmetic == PMB_ARITH_FAST) ok = ok && s->ocp.impl->launch_solve_fast(s->grid_fast, ws, s->settings, s->qp_settings, s->factor_scratch_fast.p, B, s->queue.p, st);
     else ok = ok && s->ocp.impl->launch_solve(s->grid, ws, s->settings, s->qp_settings, s->factor_scratch.p, B, s->queue.p, st);
     ok = ok && rt_event_record(s->kev1, st);
     ++launches;

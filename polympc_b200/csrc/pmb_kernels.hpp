@@ -4,7 +4,6 @@
 #include "pmb_ocp.hpp"
 #include "pmb_qp.hpp"
 #include "pmb_sqp.hpp"
-#include "pmb_qp_admm.hpp"
 
 namespace pmb {
 
@@ -326,16 +325,21 @@ struct LptOrderBody {
 /** the whole SQPBase::solve of the batch in ONE persistent launch: each CTA draws an instance from the atomic queue and
  *  iterates linearise -> boxADMM -> line search / step on it until it converges (no host round trip per iteration, no
  *  wave quantisation: a slow instance only occupies its own CTA). */
-template <class O, bool FAST = false>
+/** QPK: the QP solver of the loop — 0 boxADMM, 1 the OSQP-style ADMM<> (exact arithmetic; KKT dimension 2N + M) */
+template <class O, bool FAST = false, int QPK = 0>
 struct SqpSolveBody {
-    static constexpr const char* NAME = FAST ? "sqp_solve_fast" : "sqp_solve";
+    static_assert(!(FAST && QPK != 0), "the OSQP-style ADMM runs in exact arithmetic only");
+    static constexpr const char* NAME = QPK ? "sqp_solve_osqp_admm" : (FAST ? "sqp_solve_fast" : "sqp_solve");
     static constexpr size_t EMU_STACK_BYTES = 4u << 20;
-    static constexpr int R = (O::N + O::M + 31) / 32;
+    static constexpr int KN = QPK ? 2 * O::N + O::M : O::N + O::M;       // dimension of the KKT system
+    static constexpr int R = (KN + 31) / 32;
     /** doubles of the LDL^T workspace: packed lower triangle (exact arithmetic) or the tile workspace of pmb_qp_fast.hpp */
-    static constexpr size_t FACTOR_DOUBLES = FAST ? fast::workspace_doubles(O::N + O::M) : (size_t)(O::N + O::M) * (O::N + O::M + 1) / 2;
+    static constexpr size_t FACTOR_DOUBLES = FAST ? fast::workspace_doubles(O::N + O::M) : (size_t)KN * (KN + 1) / 2;
     static constexpr size_t SCRATCH_BYTES = SqpDev<O>::SCRATCH_DOUBLES * sizeof(double);
-    static constexpr size_t SMEM_IN = Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
-                                      (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
+    static constexpr size_t VEC_BYTES = QPK ? admm_vec_bytes(O::N, O::M) : qp_vec_bytes(O::N, O::M);
+    static constexpr size_t SMEM_IN = QPK ? Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + VEC_BYTES + 1024
+                                          : Cta::SCRATCH_DOUBLES * sizeof(double) + FACTOR_DOUBLES * sizeof(double) + 3 * (O::N + O::M) * 8 +
+                                            (6 * O::N + 4 * O::M) * 8 + 2 * (O::N + O::M) * 4 + 16 + 1024;
     static constexpr bool IN_SMEM = SMEM_IN <= 227 * 1024;    // placement of the factor, fixed per problem at compile time
     /** Threads per CTA and resident CTAs per SM the register allocation is asked to allow.
      *  Factor in shared memory: 128 threads, at most 3 CTAs per SM (168 registers per thread; measured on the mobile robot:
@@ -358,7 +362,7 @@ struct SqpSolveBody {
     /** exact arithmetic with the factor in a global slot: the 32 x 32 diagonal blocks of the factor are staged in shared memory
      *  for the substitutions (pmb_qp.hpp::ldlt_stage_diag_blocks) */
     static constexpr size_t DIAG_WANT = staged_solve_doubles(O::N + O::M, THREADS / 32) * sizeof(double) + 16;
-    static constexpr size_t DIAG_BYTES = (!IN_SMEM && !FAST && Cta::SCRATCH_DOUBLES * sizeof(double) + SCRATCH_BYTES + qp_vec_bytes(O::N, O::M) +
+    static constexpr size_t DIAG_BYTES = (!IN_SMEM && !FAST && QPK == 0 && Cta::SCRATCH_DOUBLES * sizeof(double) + SCRATCH_BYTES + qp_vec_bytes(O::N, O::M) +
                                           DIAG_WANT <= 227 * 1024) ? DIAG_WANT : 0;
     /** shared memory: Cta scratch | factor (aliased by the SQP scratch) | QP vectors                    (factor in shared memory)
      *                 Cta scratch | SQP scratch | QP vectors | diagonal blocks of the factor (exact)    (factor in global scratch) */
@@ -366,7 +370,7 @@ struct SqpSolveBody {
     {
         const size_t fac = FACTOR_DOUBLES * sizeof(double);
         const size_t first = IN_SMEM ? (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES) : SCRATCH_BYTES;
-        return Cta::SCRATCH_DOUBLES * sizeof(double) + first + qp_vec_bytes(O::N, O::M) + DIAG_BYTES;
+        return Cta::SCRATCH_DOUBLES * sizeof(double) + first + VEC_BYTES + DIAG_BYTES;
     }
     PMB_DEV static void run(const Warp& w, int blk, unsigned char* smem, O o, SqpWs ws, pmb_sqp_settings_t st, pmb_qp_settings_t qst,
                             FactorStore fs, int batch, int* queue)
@@ -384,13 +388,13 @@ struct SqpSolveBody {
             const size_t fac = FACTOR_DOUBLES * sizeof(double);
             vec = base + (fac > SCRATCH_BYTES ? fac : SCRATCH_BYTES);
         }
-        double* Ld = DIAG_BYTES ? reinterpret_cast<double*>(vec + ((qp_vec_bytes(O::N, O::M) + 15) & ~(size_t)15)) : nullptr;
+        double* Ld = DIAG_BYTES ? reinterpret_cast<double*>(vec + ((VEC_BYTES + 15) & ~(size_t)15)) : nullptr;
         for (;;) {
             const int ticket = c.bcast_int(c.tid() == 0 ? atomic_add(queue, 1) : 0);
             if (ticket >= batch) break;
             const int b = ws.order ? ws.order[ticket] : ticket;
             const SqpInst<O> s{ws, b};
-            SqpDev<O>::template solve<R, THREADS / 32, FAST, !IN_SMEM>(c, o, s, st, qst, Lp, vec, scratch, Ld);
+            SqpDev<O>::template solve<R, THREADS / 32, FAST, !IN_SMEM, QPK>(c, o, s, st, qst, Lp, vec, scratch, Ld);
         }
     }
 };

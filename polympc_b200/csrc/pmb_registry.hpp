@@ -37,6 +37,14 @@ struct IProblem {
     virtual int fast_resident_ctas() const = 0;
     virtual bool launch_solve_fast(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                                    double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
+    /** the same loop with the OSQP-style ADMM<> as its QP solver (exact arithmetic; instantiated for 2N + M <= 256) */
+    virtual bool admm_supported() const = 0;
+    virtual bool admm_in_smem() const = 0;
+    virtual size_t admm_smem_bytes() const = 0;
+    virtual size_t admm_factor_doubles() const = 0;
+    virtual int admm_resident_ctas() const = 0;
+    virtual bool launch_solve_admm(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
+                                   double* factor_scratch, int batch, int* queue, stream_t s) const = 0;
 };
 
 template <class O>
@@ -98,6 +106,24 @@ struct ProblemImpl : IProblem {
     {
         FactorStore fs{SolveFast::IN_SMEM ? nullptr : factor_scratch, SolveFast::FACTOR_DOUBLES, rt_sm_count()};
         return rt_launch<SolveFast>(grid, SolveFast::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
+    }
+    static constexpr bool ADMM_OK = 2 * O::N + O::M <= 256;
+    using SolveAdmm = SqpSolveBody<O, false, ADMM_OK ? 1 : 0>;     // (too large: an alias of the boxADMM kernel that is never launched)
+    bool admm_supported() const override { return ADMM_OK; }
+    bool admm_in_smem() const override { return SolveAdmm::IN_SMEM; }
+    size_t admm_smem_bytes() const override { return SolveAdmm::smem_bytes(); }
+    size_t admm_factor_doubles() const override { return SolveAdmm::FACTOR_DOUBLES; }
+    int admm_resident_ctas() const override
+    {
+        return resident_ctas<SolveAdmm, O, SqpWs, pmb_sqp_settings_t, pmb_qp_settings_t, FactorStore, int, int*>(
+            SolveAdmm::smem_bytes(), o, SqpWs{}, pmb_sqp_settings_t{}, pmb_qp_settings_t{}, FactorStore{}, 0, (int*)nullptr);
+    }
+    bool launch_solve_admm(int grid, const SqpWs& ws, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst, double* factor_scratch,
+                           int batch, int* queue, stream_t s) const override
+    {
+        if (!ADMM_OK) return false;
+        FactorStore fs{SolveAdmm::IN_SMEM ? nullptr : factor_scratch, SolveAdmm::FACTOR_DOUBLES, rt_sm_count()};
+        return rt_launch<SolveAdmm>(grid, SolveAdmm::smem_bytes(), s, o, ws, st, qst, fs, batch, queue);
     }
 };
 

@@ -12,6 +12,7 @@
 #include "pmb_ocp.hpp"
 #include "pmb_qp.hpp"
 #include "pmb_precond.hpp"
+#include "pmb_qp_admm.hpp"
 
 namespace pmb {
 
@@ -152,6 +153,7 @@ struct SqpWs {
     int opt_line_search;         // pmb_sqp_set_line_search: LS_L1_MERIT / LS_FILTER
     int filter_depth;            //                          LSFilter::max_depth
     double filter_beta;          //                          LSFilter::beta
+    double* Ae;                  // batch x (M + N) x N: [A; I] of ADMM<> (only with pmb_sqp_set_qp_solver(PMB_QP_OSQP_ADMM))
     double* ruiz;                // batch x (N + M + 1): D, E, c of the current QP (only with a preconditioner)
     double* filter;              // batch x FILTER_DOUBLES: the filter of each solver object (only with the filter line search)
     const int* order;            // work-queue order (pmb_sqp_set_schedule): ticket q solves instance order[q]; nullptr = identity
@@ -173,7 +175,7 @@ struct SqpInst {
     PMB_INST_F(double, p, O::N) PMB_INST_F(double, plam, O::DUAL) PMB_INST_F(double, stats, 4)
     PMB_INST_F(const double, lbx, O::N) PMB_INST_F(const double, ubx, O::N) PMB_INST_F(const double, lbg, O::NUM_INEQ)
     PMB_INST_F(const double, ubg, O::NUM_INEQ) PMB_INST_F(const double, d, O::ND)
-    PMB_INST_F(double, ruiz, O::N + O::M + 1) PMB_INST_F(double, filter, FILTER_DOUBLES)
+    PMB_INST_F(double, Ae, (O::N + O::M) * O::N) PMB_INST_F(double, ruiz, O::N + O::M + 1) PMB_INST_F(double, filter, FILTER_DOUBLES)
     PMB_INST_F(pmb_sqp_info_t, info, 1) PMB_INST_F(pmb_qp_info_t, qp_info, 1) PMB_INST_F(int, qp_nfac, 1)
 #undef PMB_INST_F
     // decision trace rows (arrays may be null)
@@ -412,7 +414,8 @@ struct SqpDev {
 
     /** SQPBase::solve (sqp_base.hpp:568-696) of one instance: iterate linearise -> QP -> line search / step until the
      *  termination test holds or max_iter QPs were solved.  Lp / vec: QP workspaces (pmb_qp.hpp), scratch: SCRATCH_DOUBLES. */
-    template <int R, int NW, bool FAST = false, bool GLOBAL_SLOT = false>
+    /** QPK: 0 = boxADMM (pmb_qp.hpp), 1 = the OSQP-style ADMM<> (pmb_qp_admm.hpp; R then counts the chunks of 2N + M) */
+    template <int R, int NW, bool FAST = false, bool GLOBAL_SLOT = false, int QPK = 0>
     PMB_DEV static void solve(Cta& c, const O& o, const SqpInst<O>& s, const pmb_sqp_settings_t& st, const pmb_qp_settings_t& qst,
                               double* Lp, unsigned char* vec, double* scratch, double* Ld = nullptr)
     {
@@ -423,6 +426,10 @@ struct SqpDev {
         qa.perm = nullptr; qa.ctype = nullptr; qa.nfac = s.qp_nfac();
         QpProf qprof;
         qa.prof = s.phase() ? &qprof : nullptr;
+        AdmmArgs aa;
+        aa.N = N; aa.M = M; aa.H = s.H(); aa.h = s.h(); aa.Ae = QPK == 1 ? s.Ae() : nullptr; aa.Alb = s.al(); aa.Aub = s.au(); aa.xlb = s.lx(); aa.xub = s.ux();
+        aa.xg = nullptr; aa.yg = nullptr; aa.x = s.p(); aa.y = s.plam(); aa.info = s.qp_info(); aa.z = nullptr; aa.perm = nullptr; aa.ctype = nullptr;
+        aa.nfac = s.qp_nfac();
         c.sync();
         unsigned long long t_lin = 0, t_qp = 0, t_step = 0, n_it = 0;
         for (int it = 1; ; ++it) {                   // the first iteration always runs (sqp_base.hpp:583-637 precede the loop)
@@ -432,7 +439,17 @@ struct SqpDev {
             const unsigned long long t1 = c.w.clock();
             if (s.ws.opt_precond != PRECOND_IDENTITY)      // m_preconditioner.compute (sqp_base.hpp:605, 662)
                 RuizCta<N, M>::compute(c, N, M, s.ws.opt_precond, s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.ruiz(), scratch);
-            qp_solve_cta<R, N, M, NW, FAST, GLOBAL_SLOT>(c, qst, qa, Lp, vec, Ld);
+            if (QPK == 1) {
+                // ADMM::construct_A (admm.hpp:215-222) on the (scaled) Jacobian of this iteration: Ae = [A; I]
+                double* Ae = s.Ae();
+                const double* Am = s.A();
+                constexpr int Me = M + N;
+                for (int e = c.tid(); e < Me * N; e += c.nthreads()) { const int j = e / Me, i = e - j * Me; Ae[e] = i < M ? Am[i + (size_t)j * M] : (i - M == j ? 1.0 : 0.0); }
+                c.sync();
+                admm_solve_cta<R, NW>(c, qst, aa, Lp, vec);
+            } else {
+                qp_solve_cta<R, N, M, NW, FAST, GLOBAL_SLOT>(c, qst, qa, Lp, vec, Ld);
+            }
             if (s.ws.opt_precond != PRECOND_IDENTITY)      // unscale(p, p_lambda), unscale(H, h, A, ...) (609-611, 666-667)
                 RuizCta<N, M>::unscale(c, N, M, s.ruiz(), s.H(), s.h(), s.A(), s.al(), s.au(), s.lx(), s.ux(), s.p(), s.plam());
             const unsigned long long t2 = c.w.clock();

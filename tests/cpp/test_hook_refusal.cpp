@@ -57,7 +57,10 @@ public:
     void hessian_regularisation_dense_impl(Eigen::Ref<nlp_hessian_t> H) noexcept { for (int i = 0; i < Problem::VAR_SIZE; ++i) H(i, i) += 1.0; }
 };
 
-// (f) Ruiz preconditioner requested: accepted (pmb_sqp_set_preconditioner); (g) OSQP-style ADMM requested: refused
+// (f) Ruiz preconditioner requested: accepted (pmb_sqp_set_preconditioner); (g) OSQP-style ADMM requested: accepted
+// (pmb_sqp_set_qp_solver); (g') a QP solver type the engine does not know: refused
+template <int N, int M> struct HomeMadeQP : boxADMM<N, M, double> { static constexpr bool pmb_engine_inner_solver = false; };
+template <typename Problem, typename QPSolver = HomeMadeQP<OCP::VAR_SIZE, OCP::NUM_EQ + OCP::NUM_INEQ>> class WithOwnQP : public SQPBase<WithOwnQP<Problem, QPSolver>, Problem, QPSolver> {};
 using Ruiz = polympc::RuizEquilibration<double, OCP::VAR_SIZE, OCP::NUM_EQ, DENSE>;
 template <typename Problem, typename QPSolver = BoxQP> class WithRuiz : public SQPBase<WithRuiz<Problem, QPSolver>, Problem, QPSolver, Ruiz> {};
 
@@ -139,7 +142,18 @@ int main(int argc, char** argv)
         EXPECT(run(f, "filter line search") != sqp_status_t::INVALID_SETTINGS); EXPECT(f.engine_options().filter_line_search);
         EXPECT(f.filter.beta == 0.1 && f.filter.m_filter.size() >= 1 && f.filter.m_filter.back().first != 1e9);   // probed without a trace; synced back (the dominated seed left)
     }
-    { WithAdmm<OCP> s; EXPECT(run(s, "OSQP-style ADMM") == sqp_status_t::INVALID_SETTINGS); }
+    { WithOwnQP<OCP> s; EXPECT(run(s, "unknown QP solver type") == sqp_status_t::INVALID_SETTINGS); }
+    if (have_engine) {
+        WithAdmm<OCP> s; Plain<OCP> p;
+        for (int k = 0; k < OCP::NX; ++k) {        // a non-trivial problem: the initial state pinned at (0.5, 0.5, 0.5)
+            s.lower_bound_x()(OCP::VARX_SIZE - OCP::NX + k) = s.upper_bound_x()(OCP::VARX_SIZE - OCP::NX + k) = 0.5;
+            p.lower_bound_x()(OCP::VARX_SIZE - OCP::NX + k) = p.upper_bound_x()(OCP::VARX_SIZE - OCP::NX + k) = 0.5;
+        }
+        EXPECT(run(s, "OSQP-style ADMM") != sqp_status_t::INVALID_SETTINGS); run(p, "boxADMM (again)");
+        double d = 0; for (int i = 0; i < OCP::VAR_SIZE; ++i) d = std::fmax(d, std::fabs(s.primal_solution()(i) - p.primal_solution()(i)));
+        std::printf("ADMM vs boxADMM after 3 SQP iterations: max |dx| = %.3e\n", d);
+        EXPECT(d < 1e-2 && d > 0.0);              // a different QP solver: close, not identical
+    }
     { Plain<OCP> s; s.settings().iteration_callback = &on_iteration; EXPECT(run(s, "iteration_callback") == sqp_status_t::INVALID_SETTINGS); }
     std::printf("%d failures\n", g_fail);
     return g_fail ? 1 : 0;

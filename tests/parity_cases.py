@@ -190,7 +190,7 @@ def kkt_case(api, orc, N, M, B=3, seed=0):
 
 
 def solve_workload(api, w, lo=0, hi=None, name=None, hessian_update=0, preconditioner=0, line_search=0, filter_beta=0.1, filter_depth=10,
-                   solves=1):
+                   solves=1, qp_solver=0):
     hi = w.batch if hi is None else hi
     s = api.sqp(name or w.name, hi - lo)
     W.configure(s, w, lo, hi)
@@ -201,6 +201,8 @@ def solve_workload(api, w, lo=0, hi=None, name=None, hessian_update=0, precondit
         s.set_preconditioner(preconditioner)
     if line_search:
         s.set_line_search(line_search, filter_beta, filter_depth)
+    if qp_solver:
+        s.set_qp_solver(qp_solver)
     for _ in range(solves):            # a second solve warm-starts from the kept iterate (and the kept filter)
         s.solve()
     out = dict(x=s.primal(), lam=s.dual(), info=s.info(), stats=s.stats(), trace=s.trace(w.sqp_max_iter),
@@ -256,7 +258,7 @@ def sqp_case(api, orc, w, hessian_update=0, **opts):
     return ra, rb
 
 
-def valet_parking_solve(api, x0_first, x0_second, preconditioner=2, line_search=1, name="mobile_robot_5x3"):
+def valet_parking_solve(api, x0_first, x0_second, preconditioner=2, line_search=1, name="mobile_robot_5x3", qp_solver=0):
     """the setup of reference tests/control/valet_parking_mpc_test.cpp:175-235 for a batch of (first, second) initial states:
     robot 5 x 3 on [0, 2], d = 2, SQP 10 / 10, QP max_iter 1000, filter beta 0.1, block BFGS (SPARSE problem), Ruiz equilibration
     (SPARSE), controls bounded on the last 11 nodes only (`tail(22)`), the state pinned at offset 30 (`segment(30, 3)`) — both as the
@@ -271,6 +273,8 @@ def valet_parking_solve(api, x0_first, x0_second, preconditioner=2, line_search=
     s.set_parameters(np.array([2.0]))
     s.set_trace(True)
     s.set_hessian_update(1); s.set_preconditioner(preconditioner); s.set_line_search(line_search, 0.1, 10)
+    if qp_solver:
+        s.set_qp_solver(qp_solver)
     N = d["N"]
     lb = np.full((B, N), -np.inf); ub = np.full((B, N), np.inf)
     ub[:, -22:] = np.tile([1.5, 0.75], 11); lb[:, -22:] = np.tile([-1.5, -0.75], 11)

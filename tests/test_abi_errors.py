@@ -42,6 +42,7 @@ def test_preconditioner_and_line_search_arguments(emu):
     s = emu.sqp("mobile_robot_6x2", 2)
     f = emu._fn
     assert f("sqp_set_preconditioner")(s.h, 3) == -2 and f("sqp_set_preconditioner")(s.h, -1) == -2
+    assert f("sqp_set_qp_solver")(s.h, 2) == -2 and f("sqp_set_qp_solver")(None, 0) == -2
     assert f("sqp_set_line_search")(s.h, 2, 0.1, 10) == -2
     assert f("sqp_set_line_search")(s.h, 1, 0.1, 0) == -2 and f("sqp_set_line_search")(s.h, 1, 0.1, 17) == -2     # depth in 1..PMB_FILTER_CAP
     assert f("sqp_set_line_search")(s.h, 1, float("nan"), 10) == -2

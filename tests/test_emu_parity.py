@@ -278,3 +278,11 @@ def test_osqp_style_admm_adaptive_rho_relaxation_warm_start(emu, orc):
     st = orc.sqp_default_qp_settings(); st.adaptive_rho = 1; st.adaptive_rho_interval = 10; st.max_iter = 60; st.alpha = 1.6
     r = pc.admm_case(emu, orc, 9, 4, B=3, seed=5, settings=st, warm=True)
     assert (r["n_factor"] >= 2).any()
+
+
+def test_sqp_with_osqp_style_admm(emu, orc):
+    """SQPBase<..., ADMM<>> (pmb_sqp_set_qp_solver): the OSQP-style ADMM as the QP solver of the fused loop — alone and together
+    with block BFGS, Ruiz equilibration and the filter line search, the combination valet_parking_mpc_test.cpp:168-172 aliases"""
+    w = W.mobile_robot(2, seed=3, sqp_max_iter=3, ls_max_iter=6)
+    pc.sqp_case(emu, orc, w, qp_solver=1)
+    pc.sqp_case(emu, orc, w, qp_solver=1, preconditioner=2, line_search=1, hessian_update=1)

@@ -57,7 +57,7 @@ def test_fast_qp_vs_oracle(fast_default, orc, N, M):
     assert np.array_equal(act_a, act_b)
 
 
-def _solve(api, w, arithmetic, trace=False, hessian_update=0, lo=0, hi=None):
+def _solve(api, w, arithmetic, trace=False, hessian_update=0, lo=0, hi=None, preconditioner=0, line_search=0):
     hi = w.batch if hi is None else hi
     s = api.sqp(w.name, hi - lo)
     W.configure(s, w, lo, hi)
@@ -65,6 +65,10 @@ def _solve(api, w, arithmetic, trace=False, hessian_update=0, lo=0, hi=None):
         s.set_arithmetic(arithmetic)
     if hessian_update:
         s.set_hessian_update(hessian_update)
+    if preconditioner:
+        s.set_preconditioner(preconditioner)
+    if line_search:
+        s.set_line_search(line_search, 0.1, 10)
     if trace:
         s.set_trace(True)
     s.solve()
@@ -137,6 +141,18 @@ def test_fast_block_bfgs_and_minimal_time(pmb, orc):
     a, b = _solve(pmb, w, 0), _solve(pmb, w, 1)
     assert (a["info"]["status"] == b["info"]["status"]).mean() >= 0.99
     assert (b["info"]["status"] == 0).mean() >= 0.85
+
+
+def test_fast_ruiz_and_filter_line_search(pmb, orc):
+    """Ruiz equilibration and the filter line search on the fast path: one SQP iteration agrees with the exact path to tolerance
+    (same ADMM trip counts and step lengths), whole solves converge like the oracle's"""
+    w = W.mobile_robot(1024, sqp_max_iter=1)
+    a, b = _solve(pmb, w, 0, trace=True, preconditioner=2, line_search=1), _solve(pmb, w, 1, trace=True, preconditioner=2, line_search=1)
+    pc.assert_same(a["trace"]["qp_iter"], b["trace"]["qp_iter"], "qp_iter"); pc.assert_same(a["trace"]["alpha"], b["trace"]["alpha"], "alpha")
+    assert np.maximum(rel(b["x"], a["x"]), rel(b["lam"], a["lam"])).max() <= TOL
+    w = W.mobile_robot(1024, sqp_max_iter=20, ls_max_iter=20)
+    f, o = _solve(pmb, w, 1, preconditioner=1, line_search=1), _solve(orc, w, 0, preconditioner=1, line_search=1)
+    assert (f["info"]["status"] == o["info"]["status"]).mean() >= 0.99 and (f["info"]["status"] == 0).mean() > 0.9
 
 
 def test_fast_kite_is_available_but_not_within_tolerance(pmb):

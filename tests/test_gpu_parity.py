@@ -392,3 +392,36 @@ def test_osqp_style_admm_reference_known_answer(pmb):
     st = pmb.qp_default_settings(); st.max_iter = 1000
     r = pmb.qp_solve_admm(np.array([[[4.0, 1.0], [1.0, 2.0]]]), [[1.0, 1.0]], np.array([[[1.0, 1.0]]]), [[1.0]], [[1.0]], [[0.0, 0.0]], [[0.7, 0.7]], st)
     assert np.allclose(r["x"][0], [0.3, 0.7], rtol=1e-2) and r["info"]["status"][0] == 0 and r["info"]["iter"][0] < 1000
+
+
+@pytest.mark.parametrize("kind,batch", [("mobile_robot", 1024), ("cstr", 256), ("robot_obstacle", 256)])
+def test_sqp_with_osqp_style_admm_vs_oracle(pmb, orc, kind, batch):
+    """SQPBase<..., ADMM<>>: the OSQP-style ADMM (KKT systems of size 2N + M = 169 / 176 / 176) as the QP solver of the fused loop"""
+    w = W.WORKLOADS[kind](batch, sqp_max_iter=20, ls_max_iter=20)
+    ra, rb = pc.sqp_case(pmb, orc, w, qp_solver=1)
+    assert np.isfinite(rb["x"]).all() and (rb["info"]["status"] == 0).mean() > (0.5 if kind == "robot_obstacle" else 0.8)   # 20 / 20 iterations
+
+
+def test_sqp_with_osqp_style_admm_and_the_valet_options(pmb, orc):
+    """ADMM<> + block BFGS + RuizEquilibration<SPARSE> + filter line search on the valet-parking setup (5 x 3 grid, 2N + M = 208)"""
+    rng = np.random.default_rng(6)
+    a = np.column_stack([rng.uniform(-1, 1, 128), rng.uniform(-1, 1, 128), rng.uniform(-0.7, 0.7, 128)]); a[0] = [0.5, 0.5, 0.5]
+    b = a + rng.uniform(-0.2, 0.2, a.shape); b[0] = [0.3, 0.4, 0.45]
+    ra, rb = pc.valet_parking_case(pmb, orc, a, b, qp_solver=1)
+    assert rb[0]["info"]["status"][0] == 0 and rb[1]["info"]["status"][0] == 0
+
+
+def test_osqp_style_admm_limits(pmb):
+    """exact arithmetic only; instantiated up to 2N + M = 256 (the kite's 585 is refused with PMB_ERR_UNSUPPORTED)"""
+    from polympc_b200.capi import PmbError
+    s = pmb.sqp("kite_12x1", 2)
+    with pytest.raises(PmbError):
+        s.set_qp_solver(1)
+    s.close()
+    w = W.mobile_robot(4)
+    s = pmb.sqp(w.name, 4); W.configure(s, w); s.set_qp_solver(1); s.set_arithmetic(1)
+    with pytest.raises(PmbError):
+        s.solve()
+    s.set_arithmetic(0); s.solve()
+    assert (s.info()["status"] == 0).all()
+    s.close()

@@ -106,9 +106,10 @@ def test_reference_minimal_time_test_passes_on_the_gpu(pmb):
 
 def test_unsupported_hook_overrides_are_refused(emu):
     """tests/cpp/test_hook_refusal.cpp: a home-made quasi-Newton update, a custom line search, a filter line search with an extra
-    acceptance test, a custom regulariser, the OSQP-style ADMM and an iteration callback are each refused with INVALID_SETTINGS
-    and a message on stderr; the default solver, one that forwards hessian_update_impl to a DENSE problem (bit-identical to the
-    default), one with a RuizEquilibration preconditioner and one with the reference-style LSFilter line search are accepted"""
+    acceptance test, a custom regulariser, an unknown QP solver type and an iteration callback are each refused with
+    INVALID_SETTINGS and a message on stderr; the default solver, one that forwards hessian_update_impl to a DENSE problem
+    (bit-identical to the default), one with a RuizEquilibration preconditioner, one with the reference-style LSFilter line search
+    and one with the OSQP-style ADMM<> as its QP solver are accepted; boxADMM<> and ADMM<> also work as stand-alone QP objects"""
     rc, out = _run(_binary("emu_hook_refusal_test", "emu_hooks", needs_reference=False), "with_engine")
     assert rc == 0 and "0 failures" in out, out
     assert out.count("SQPBase::solve() REFUSED") == 6, out

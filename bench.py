@@ -524,7 +524,7 @@ def run_gpu(args):
     if not args.no_configs:
         configs = {}
 
-        def quick(workload, batch_per_rank, arithmetic, steps=2, **kw):
+        def quick(workload, batch_per_rank, arithmetic, steps=2, options=None, **kw):
             """it/s of `workload` with batch_per_rank instances on every rank (rank r solves block r of the sweep)"""
             try:
                 wq = W.WORKLOADS[workload](batch_per_rank * world, **kw)
@@ -532,6 +532,8 @@ def run_gpu(args):
                 sq.set_stream(stream.cuda_stream)
                 W.configure(sq, wq, rank * batch_per_rank, (rank + 1) * batch_per_rank)
                 sq.set_arithmetic(ARITH[arithmetic])
+                for name, val in (options or {}).items():      # solver options of the reference's other operators (capi.Sqp setters)
+                    getattr(sq, name)(*val)
                 v, ms = device_rate(sq, steps, warm=2)
                 solved = sum_over_ranks(float((sq.info()["status"] == 0).sum())) / (batch_per_rank * world)
                 sq.close()
@@ -547,6 +549,12 @@ def run_gpu(args):
                                                           "377 x 377 KKT systems (tests/test_gpu_fast.py)"}
         configs["mobile_robot_batch_sweep"] = {str(b): quick("mobile_robot", b, args.arithmetic) for b in (256, 1024, 4096, 16384, 65536)}   # config 5
         configs["mobile_robot_reference_test_settings"] = quick("mobile_robot", B, args.arithmetic, sqp_max_iter=10, ls_max_iter=10)
+        # the other operators behind the same API, robot batch B: the solver of the reference's
+        # control tests (block BFGS) with RuizEquilibration<SPARSE> around every QP, and ADMM<> as the QP solver.  (The filter line
+        # search is left out here: its filter lives across solves, so repeated timed solves are not the same work.)
+        configs["mobile_robot_block_bfgs_ruiz"] = quick("mobile_robot", B, args.arithmetic, options={
+            "set_hessian_update": (1,), "set_preconditioner": (2,)})
+        configs["mobile_robot_osqp_style_admm"] = quick("mobile_robot", B, "exact", options={"set_qp_solver": (1,)})
         configs["note"] = "per-GPU batch; under --gpus N every rank solves its own block of the sweep (weak scaling) except the kite, which is sharded"
 
     if rank == 0:

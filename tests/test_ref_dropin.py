@@ -104,6 +104,18 @@ def test_reference_minimal_time_test_passes_on_the_gpu(pmb):
     _check_minimal_time(*_run(_binary("minimal_time_test", "all")))
 
 
+@pytest.mark.gpu
+def test_reference_nonlinear_constraints_program_runs_on_the_gpu(pmb):
+    """tests/control/nonlinear_constraints_test.cpp — not a gtest but a demo main (no assertions): NP = 1 and NG = 1 together, exact
+    Hessian at every iteration + Gershgorin, final-state box, 20 / 10 iterations.  Compiled unmodified; it must run to the end
+    with the algorithm its source asks for and finite iterates.  (A minute on the warp emulator: GPU suite only.)"""
+    rc, out = _run(_binary("nonlinear_constraints_test", "all"))
+    assert rc == 0, out
+    sol = _solves(out)
+    assert len(sol) == 1 and sol[0]["exact_hessian"] == 1 and sol[0]["gershgorin"] == 1 and sol[0]["finite"] == 1 and sol[0]["iter"] <= 20, out
+    assert "Solution P:" in out
+
+
 def test_unsupported_hook_overrides_are_refused(emu):
     """tests/cpp/test_hook_refusal.cpp: a home-made quasi-Newton update, a custom line search, a filter line search with an extra
     acceptance test, a custom regulariser, an unknown QP solver type and an iteration callback are each refused with

@@ -348,16 +348,18 @@ struct SqpSolveBody {
      *  Factor in a global (L2) slot — large problems with heavy AD code (kite 12 x 1): ONE CTA of 256 threads per SM.  Per-instance
      *  latency is what counts there (one SQP iteration is 10-25 M cycles) and the 255-register budget halves the spills:
      *  measured on kite 12 x 1, batch 1024: 128 threads x 2 CTAs 4.1 k / 8.4 k it/s (exact / fast), 256 x 2 4.8 k / 10.9 k,
-     *  256 x 1 6.5 k / 16.1 k. */
+     *  256 x 1 6.5 k / 16.1 k.  The same holds for a factor in shared memory that is so large that only one CTA fits per SM
+     *  (the OSQP-style ADMM variant of the robot: 115 KB; 253 k -> 294 k it/s with 256 threads). */
 #ifdef PMB_SQP_THREADS
     static constexpr int THREADS = PMB_SQP_THREADS;
 #else
-    static constexpr int THREADS = IN_SMEM ? 128 : 256;
+    static constexpr bool ALONE_ON_SM = !IN_SMEM || (228 * 1024) / SMEM_IN < 2;   // one CTA per SM either way: give it 8 warps
+    static constexpr int THREADS = ALONE_ON_SM ? 256 : 128;
 #endif
 #ifdef PMB_MINB
     static constexpr int MIN_BLOCKS = PMB_MINB;
 #else
-    static constexpr int MIN_BLOCKS = !IN_SMEM ? 1 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
+    static constexpr int MIN_BLOCKS = THREADS == 256 ? 1 : ((228 * 1024) / SMEM_IN > 3 ? 3 : (int)((228 * 1024) / SMEM_IN));
 #endif
     /** exact arithmetic with the factor in a global slot: the 32 x 32 diagonal blocks of the factor are staged in shared memory
      *  for the substitutions (pmb_qp.hpp::ldlt_stage_diag_blocks) */

@@ -152,7 +152,7 @@ int pmb_qp_solve(int N, int M, int batch,
  * vector of size M + N, KKT system of size 2N + M.  Same inputs and settings as pmb_qp_solve.  Outputs: x[batch*N],
  * y[batch*(M+N)] = [y_A ; y_box]; optional (may be NULL): z[batch*(M+N)] = m_z (the active set is {i: z_i == bound_i}),
  * perm[batch*(2N+M)], ctype[batch*(M+N)], n_factor[batch].  Exact arithmetic only (bit-identical to the CPU oracle).
- * Stand-alone operator: inside SQPBase the engine's QP solver is boxADMM (what the reference instantiates by default). */
+ * The same solver runs inside the fused SQP loop when selected with pmb_sqp_set_qp_solver(PMB_QP_OSQP_ADMM). */
 int pmb_qp_solve_admm(int N, int M, int batch,
                       const double* H, const double* h, const double* A, const double* Alb, const double* Aub,
                       const double* xlb, const double* xub, const double* x_guess, const double* y_guess,

@@ -12,7 +12,9 @@
 //   SQPBase<Derived, Problem, QPSolver>           (src/solvers/sqp_base.hpp:64-197, 568) host object, one instance, same
 //                                                                                        getters / setters, solve() runs the
 //                                                                                        fused sm_100a kernel
-//   boxADMM<...>, ADMM<...>, qp_solver_settings_t (src/solvers/box_admm.hpp:15, qp_base.hpp:17-53)  settings carrier
+//   boxADMM<...>, ADMM<...>, qp_solver_settings_t (src/solvers/box_admm.hpp:15, admm.hpp:15, qp_base.hpp:17-175)  QPBase objects
+//                                                                                        (solve 7 / 9 arguments on the device) and the
+//                                                                                        QPSolver argument of SQPBase
 //   MPC<OCP, Solver, Args...>                     (src/control/mpc_wrapper.hpp:17-298)   same methods
 //
 // The GPU side: pmb::compat::Model<OCP> adapts the Eigen-style functors of a problem class to the engine's pointer-style
@@ -34,9 +36,10 @@
 //   step_size_selection_impl         default (l1 merit)  |  the LSFilter line search of valet_parking_mpc_test.cpp:110-155 (recognised by
 //                                    running it against scripted cost / violation values; the solver's `filter` member is kept in sync)
 //   Preconditioner                   IdentityPreconditioner  |  RuizEquilibration<..., DENSE | SPARSE>
+//   QPSolver                         boxADMM<...>  |  ADMM<...> (the OSQP-style splitting, exact arithmetic, 2N + M <= 256)
 // Anything else — an override that does something the menu does not have, another step_size_selection_impl, an overridden
 // constraints_violation_impl / max_constraints_violation_impl / termination_criteria_impl, a non-null iteration_callback,
-// a QP solver other than boxADMM — is REFUSED: solve() prints what it found to stderr and
+// a QP solver type other than boxADMM<> / ADMM<> — is REFUSED: solve() prints what it found to stderr and
 // returns with status INVALID_SETTINGS instead of silently running a different algorithm.
 // MATRIXFMT == SPARSE selects the SPARSE *semantics* (block-diagonal quasi-Newton update); storage on the device is dense.
 #pragma once
